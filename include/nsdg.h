@@ -1,0 +1,171 @@
+/*
+ * nsdg.h -- C ABI of libnsdg_cuda.so, the B200-native (sm_100a, FP64) implementation of
+ * neXtSIM_DG's dynamics hot path (DG advection + subcycled CG momentum with mEVP / BBM).
+ *
+ * This is the drop-in boundary: the entry points are exactly what a CUDAMEVPDynamics /
+ * CUDABBMDynamics IDynamics module needs from its kernel object.  Each one names the
+ * reference interface it replaces (paths relative to the nextsimdg source tree).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns 0 on success, non-zero on
+ *    error; nsdg_last_error() gives the message of the last failure on this thread
+ *    (the C++ module wrapper rethrows it as std::runtime_error, like the reference's
+ *    exceptions at IDynamics.hpp:116).
+ *  - host arrays are the raw buffers of the model's ModelArrays: row-major N x ncomp
+ *    (core/src/include/ModelArray.hpp:92), element index i + nx*j (x fastest).
+ *  - a handle is not re-entrant; calls are synchronous (results are complete on return),
+ *    matching the single model thread that calls IDynamics::update
+ *    (core/src/PrognosticData.cpp:95).
+ *  - there is no CPU fallback: every call fails with an error if no CUDA device is usable.
+ */
+#ifndef NSDG_H
+#define NSDG_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsdg_handle_s* nsdg_handle;
+
+/* Rheology = which reference kernel is replaced. */
+enum nsdg_rheology {
+    NSDG_MEVP = 0, /* MEVPDynamicsKernel  (dynamics/src/include/MEVPDynamicsKernel.hpp:17-37) */
+    NSDG_BBM = 1 /* BBMDynamicsKernel   (dynamics/src/include/BBMDynamicsKernel.hpp:18-44)  */
+};
+
+/* Named fields of DynamicsKernel::setData / getDG0Data / getDGData
+ * (dynamics/src/include/DynamicsKernel.hpp:92-156, core/src/include/gridNames.hpp:17-37). */
+enum nsdg_field {
+    NSDG_HICE = 0, /* "hice"      in/out, DG */
+    NSDG_CICE = 1, /* "cice"      in/out, DG */
+    NSDG_DAMAGE = 2, /* "damage"    in/out, DG (BBM only) */
+    NSDG_U = 3, /* "u"         in (cell means -> CG via DG2CG), out (CG -> DG0) */
+    NSDG_V = 4, /* "v" */
+    NSDG_UWIND = 5, /* "uwind"     in */
+    NSDG_VWIND = 6, /* "vwind"     in */
+    NSDG_UOCEAN = 7, /* "uocean"    in */
+    NSDG_VOCEAN = 8, /* "vocean"    in */
+    NSDG_SSH = 9, /* "ssh"       in, DG0 */
+    NSDG_TAUX = 10, /* "uiostress" out: ice-ocean stress, x */
+    NSDG_TAUY = 11, /* "viostress" out: ice-ocean stress, y */
+    NSDG_NFIELDS = 12
+};
+
+/* Neighbour sides of a partition box (partition.cdl connectivity: core/test/partition_metadata_3.cdl:28-66) */
+enum nsdg_side { NSDG_BOTTOM = 0, NSDG_RIGHT = 1, NSDG_TOP = 2, NSDG_LEFT = 3 };
+
+/*
+ * Construction parameters.  Zero-initialise, then set what differs from the defaults
+ * (nsdg_config_default does both).  dgadv / cgdegree are the reference's compile-time
+ * DGCOMP and CGDEGREE (CMakeLists.txt:12-16,112-118); nsteps is DynamicsKernel::nSteps
+ * (DynamicsKernel.hpp:187, hard-coded 100 upstream).
+ */
+typedef struct nsdg_config {
+    int rheology; /* enum nsdg_rheology */
+    int dgadv; /* DGCOMP: 6 (DG2, default), 3 (DG1) */
+    int cgdegree; /* CGDEGREE: 2 (default), 1 */
+    int nsteps; /* subcycles per update(); default 100 */
+    int device; /* CUDA device ordinal; -1 = current device */
+    int use_cuda_graph; /* 1 = capture the subcycle loop in a CUDA graph (default 1) */
+    int force_general; /* 1 = never use the uniform-rectangular-mesh fast path (default 0) */
+    int pin_host_buffers; /* 1 = nsdg_update page-locks the caller's arrays on first use (cudaHostRegister) so
+                             the per-step copies are asynchronous DMA; the arrays must then stay allocated
+                             until nsdg_destroy (true for the model's ModelArrays). default 0 */
+    /* mEVP relaxation parameters (MEVPStressUpdateStep.hpp:126-127, VPCGDynamicsKernel.hpp:125-126) */
+    double alpha, beta; /* default 1500, 1500 */
+    /* Partition of the global grid handled by this handle (ModelMetadata.cpp:42-62, run/partition.cdl).
+     * Single-domain use: leave all zero. */
+    int global_nx, global_ny; /* extent of the whole domain in elements (0 = not partitioned) */
+    int box_x0, box_y0; /* first owned element of this box in the global grid */
+    int rank, nranks; /* rank of this box, number of boxes */
+    int neighbour[4]; /* rank of the box across each side, -1 = domain edge */
+} nsdg_config;
+
+void nsdg_config_default(nsdg_config* cfg);
+
+/* Replaces: construction of the kernel member in MEVPDynamics::MEVPDynamics / BBMDynamics::BBMDynamics
+ * (core/src/modules/DynamicsModule/MEVPDynamics.cpp:29-35, BBMDynamics.cpp:24-30). */
+int nsdg_create(const nsdg_config* cfg, nsdg_handle* out);
+
+/* Replaces: Module::finalize<IDynamics> destroying the kernel (core/src/include/Module.hpp:171-175). */
+int nsdg_destroy(nsdg_handle h);
+
+/* Replaces: DynamicsKernel::initialise(coords, isSpherical, mask)
+ * (DynamicsKernel.hpp:44-75, CGDynamicsKernel.cpp:24-51, BrittleCGDynamicsKernel.hpp:72-86).
+ *   coords_xy : (nx+1)*(ny+1) interleaved (x,y) pairs, vertex index x-fastest; metres, or
+ *               lon/lat in RADIANS when spherical != 0 (the module multiplies degrees by
+ *               pi/180 first, MEVPDynamics.cpp:43-46)
+ *   mask      : nx*ny doubles, 1.0 = ocean/ice element (ParametricMesh.cpp:221)
+ * With a partition in the config, nx, ny, coords and mask describe the box INCLUDING its
+ * one-element overlap ring where a neighbour exists. */
+int nsdg_set_mesh(nsdg_handle h, int nx, int ny, const double* coords_xy, const double* mask, int spherical);
+
+/* Replaces: DynamicsKernel::setData(name, ModelArray) (DynamicsKernel.hpp:92-112,
+ * CGDynamicsKernel.cpp:53-90, BrittleCGDynamicsKernel.hpp:138-145) with DGModelArray::ma2dg
+ * semantics (DGModelArray.hpp:20-32): ncomp == 1 sets component 0 and ZEROES the higher
+ * moments; ncomp == dgadv copies all components. */
+int nsdg_set_field(nsdg_handle h, int field, const double* host, int ncomp);
+
+/* Replaces: kernel.update(tst) -- VPCGDynamicsKernel::update (VPCGDynamicsKernel.hpp:63-94) or
+ * BrittleCGDynamicsKernel::update (BrittleCGDynamicsKernel.hpp:91-136): advection + limiters,
+ * prepareIteration, nsteps subcycles.  dt_seconds = tst.step.seconds(). */
+int nsdg_step(nsdg_handle h, double dt_seconds);
+
+/* Replaces: getDG0Data(name) (ncomp == 1; DynamicsKernel.hpp:114-126, CGDynamicsKernel.cpp:92-118)
+ * and getDGData(name) (ncomp == dgadv; DynamicsKernel.hpp:134-156). */
+int nsdg_get_field(nsdg_handle h, int field, double* host, int ncomp);
+
+/* The whole of MEVPDynamics::update / BBMDynamics::update in ONE call (MEVPDynamics.cpp:59-87,
+ * BBMDynamics.cpp:66-101): uploads the 7 (8) input HFields from pinned staging with async copies,
+ * steps, downloads the 6 (7) outputs.  Any pointer may be NULL to skip that field.
+ * in/out arrays are nx*ny doubles each. */
+typedef struct nsdg_update_io {
+    const double *hice_in, *cice_in, *damage_in, *uwind, *vwind, *uocean, *vocean, *ssh;
+    double *hice_out, *cice_out, *damage_out, *u_out, *v_out, *taux_out, *tauy_out;
+} nsdg_update_io;
+int nsdg_update(nsdg_handle h, const nsdg_update_io* io, double dt_seconds);
+
+/* ---- mesh-derived integer state (bit-exact against ParametricMesh, ParametricMesh.cpp:217-292) ---- */
+int nsdg_get_landmask(nsdg_handle h, unsigned char* out /* nx*ny */);
+int nsdg_get_dirichlet(nsdg_handle h, int edge /* 0 bottom,1 right,2 top,3 left */, long* out, size_t capacity,
+    size_t* count);
+
+/* ---- test / diagnostic access to internal state, converted to the reference's layouts ----
+ * names: "cg_u","cg_v","cgH","cgA","uGradSSH","vGradSSH","uOcean","vOcean","uAtmos","vAtmos","avgU","avgV",
+ *        "lumpedcgmass" (flat CG vectors, cgVector.hpp:21-31);
+ *        "hice","cice","damage","s11","s12","s22" (row-major N x comps, dgVector.hpp:89-91);
+ *        "divS1","divS2","iMgradX","iMgradY","iMJwPSI","iMJwPSI_dam","divM","iMM" (N x rows x cols,
+ *        ParametricMap.hpp:72-113), "AdvX","AdvY","iMass" (ParametricMap.hpp:22-27). */
+int nsdg_get_internal(nsdg_handle h, const char* name, double* host, size_t capacity, size_t* count);
+int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_t count);
+
+/* Run n bare subcycles on the current device state (no advection / prepare); the unit the
+ * throughput metric counts.  Returns device milliseconds of the loop through *ms (CUDA events). */
+int nsdg_subcycles(nsdg_handle h, int n, float* ms);
+
+/* Timing of the last nsdg_step, measured with CUDA events on the handle's stream. */
+typedef struct nsdg_timing {
+    float advection_ms, prepare_ms, subcycle_ms, total_ms;
+    long kernel_launches; /* kernels launched by this library during the last nsdg_step/nsdg_subcycles */
+    int uniform_path; /* 1 if the uniform-rectangular operator path is active */
+} nsdg_timing;
+int nsdg_get_timing(nsdg_handle h, nsdg_timing* t);
+
+/* ---- multi-GPU halo plumbing (no reference counterpart: the reference dynamics has no halo
+ * exchange; semantics follow the 2-D box decomposition of run/partition.cdl) ----
+ * Each box exports one device buffer per side that neighbours write into over NVLink; the
+ * handles are CUDA IPC handles exchanged by the launcher (any transport).                    */
+#define NSDG_IPC_HANDLE_BYTES 64
+int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handles /* 2 * NSDG_IPC_HANDLE_BYTES */);
+int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handles);
+int nsdg_halo_ready(nsdg_handle h);
+
+const char* nsdg_last_error(void);
+const char* nsdg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSDG_H */

@@ -1,0 +1,1028 @@
+/*
+ * nsdg_cuda.cu -- libnsdg_cuda.so: handle, host orchestration and the C ABI of include/nsdg.h.
+ *
+ * The per-timestep sequence is that of the reference kernels
+ *   VPCGDynamicsKernel::update       dynamics/src/include/VPCGDynamicsKernel.hpp:63-94
+ *   BrittleCGDynamicsKernel::update  dynamics/src/include/BrittleCGDynamicsKernel.hpp:91-136
+ *   DynamicsKernel::advectionAndLimits dynamics/src/include/DynamicsKernel.hpp:160-172
+ *   CGDynamicsKernel::prepareIteration dynamics/src/CGDynamicsKernel.cpp:260-276
+ * with all state resident on the device between calls.  Mesh-derived integer state (land mask,
+ * sorted Dirichlet lists) is built on the host exactly as ParametricMesh does
+ * (dynamics/src/ParametricMesh.cpp:217-292) and is bit-exact by construction.
+ *
+ * There is no CPU fallback: without a usable CUDA device every entry point fails.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <utility>
+
+#include "nsdg_momentum.cuh"
+#include "nsdg_prepare.cuh"
+
+namespace nsdg {
+
+static thread_local std::string g_lastError;
+
+static inline unsigned blocksFor(size_t n, unsigned bs = 128) { return unsigned((n + bs - 1) / bs); }
+static inline size_t alignUp(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
+//! type-erased handle
+class HandleBase {
+public:
+    virtual ~HandleBase() = default;
+    virtual void setMesh(int nx, int ny, const double* coords, const double* mask, int spherical) = 0;
+    virtual void setField(int field, const double* host, int ncomp) = 0;
+    virtual void getField(int field, double* host, int ncomp) = 0;
+    virtual void step(double dt) = 0;
+    virtual void update(const nsdg_update_io* io, double dt) = 0;
+    virtual void subcycles(int n, float* ms) = 0;
+    virtual void getInternal(const std::string& name, double* host, size_t cap, size_t* count) = 0;
+    virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
+    nsdg_config cfg {};
+    nsdg_timing timing {};
+    std::vector<uint8_t> landmask;
+    std::vector<long> dirichlet[4];
+    bool meshSet = false;
+};
+
+template <int CG, int DGA> class Handle : public HandleBase {
+public:
+    static constexpr int DGs = cg2dgstress(CG), GS = gp1d(DGs), Q = GS * GS, NR = CG + 1, ND = NR * NR;
+    static constexpr int EDA = edgedofs(DGA), EDS = edgedofs(DGs);
+    static constexpr int QA = gp1d(DGA) * gp1d(DGA), QS = Q;
+
+    PhysParams p;
+    GridDims g {};
+    bool uniform = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] {};
+    int cg1s = 0; //!< CG1 row stride
+    size_t ncg = 0, ncg1 = 0; //!< allocated CG / CG1 doubles
+
+    // mesh
+    std::vector<double> hvx, hvy;
+    std::vector<uint8_t> hdirmask;
+    DevBuf<double> vx, vy;
+    DevBuf<uint8_t> d_landmask, d_dirmask, d_nodemask;
+    // element fields
+    DevBuf<double> hice, cice, damage, ssh, s11, s12, s22, gaussA, gaussB, helem;
+    DevBuf<double> velx, vely, tmp1, tmp2, nvX, nvY; // DGA transport
+    DevBuf<double> velxS, velyS, tmp1S, tmp2S, nvXS, nvYS; // DGs transport (BBM)
+    DevBuf<double> scratchDG; // DGA planes scratch (set/get via DG2CG / CG2DG)
+    // operators
+    DevBuf<double> tAdvX, tAdvY, tiMass, sAdvX, sAdvY, siMass;
+    DevBuf<double> oGx, oGy, oGM, oB, oBd, oD1, oD2, oDM, odX, odY;
+    TransportOpPtrs topA {}, topS {};
+    MomentumOpPtrs mop {};
+    // CG fields
+    DevBuf<double> u, v, u0, v0, cgH, cgA, gradX, gradY, uO, vO, uA, vA, lmass, avgU, avgV, taux, tauy;
+    DevBuf<double> cgSSH, mass1, gu1, gv1;
+    DevBuf<double> hbuf, vbuf;
+    // staging
+    DevBuf<double> staging;
+    std::vector<std::pair<const void*, size_t>> registered;
+    // strips
+    int R = 16, nsx = 0, nsy = 0;
+    // graph cache
+    cudaGraphExec_t graphExec = nullptr;
+    int graphN = 0;
+    double graphDeltaT = 0;
+    long launches = 0;
+
+    explicit Handle(const nsdg_config& c)
+    {
+        cfg = c;
+        if (cfg.device >= 0)
+            NSDG_CUDA_CHECK(cudaSetDevice(cfg.device));
+        int dev = 0;
+        NSDG_CUDA_CHECK(cudaGetDevice(&dev)); // fails loudly when there is no GPU: no CPU fallback
+        cfg.device = dev;
+        NSDG_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& e : ev)
+            NSDG_CUDA_CHECK(cudaEventCreate(&e));
+        p.alpha = cfg.alpha;
+        p.beta = cfg.beta;
+    }
+    ~Handle() override
+    {
+        if (graphExec)
+            cudaGraphExecDestroy(graphExec);
+        for (auto& r : registered)
+            cudaHostUnregister(const_cast<void*>(r.first));
+        for (auto& e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+
+    // ------------------------------------------------------------------------------------
+    // mesh
+    // ------------------------------------------------------------------------------------
+    void buildDirichlet()
+    {
+        const size_t nx = g.nx, ny = g.ny, N = g.N;
+        for (auto& d : dirichlet)
+            d.clear();
+        // dirichletFromMask, ParametricMesh.cpp:228-252
+        const size_t startX[4] = { 0, 0, 0, 1 }, stopX[4] = { nx, nx - 1, nx, nx };
+        const size_t startY[4] = { 1, 0, 0, 0 }, stopY[4] = { ny, ny, ny - 1, ny };
+        const long delta[4] = { -long(nx), 1, long(nx), -1 };
+        for (int edge = 0; edge < 4; ++edge) {
+            for (size_t j = startY[edge]; j < stopY[edge]; ++j)
+                for (size_t i = startX[edge]; i < stopX[edge]; ++i) {
+                    const size_t idx = i + nx * j;
+                    if (landmask[idx] && !landmask[idx + delta[edge]])
+                        dirichlet[edge].push_back(long(idx));
+                }
+            std::sort(dirichlet[edge].begin(), dirichlet[edge].end());
+        }
+        // dirichletFromEdge for BOTTOM, RIGHT, TOP, LEFT, ParametricMesh.cpp:259-272.  With a partition,
+        // only sides on the edge of the GLOBAL domain are closed.
+        const size_t start[4] = { 0, nx - 1, N - nx, 0 }, stop[4] = { nx, N, N, N }, stride[4] = { 1, nx, 1, nx };
+        for (int edge = 0; edge < 4; ++edge) {
+            if (cfg.global_nx > 0 && cfg.neighbour[edge] >= 0)
+                continue;
+            for (size_t idx = start[edge]; idx < stop[edge]; idx += stride[edge])
+                if (landmask[idx])
+                    dirichlet[edge].push_back(long(idx));
+            std::sort(dirichlet[edge].begin(), dirichlet[edge].end());
+        }
+        hdirmask.assign(N, 0);
+        for (int edge = 0; edge < 4; ++edge)
+            for (long e : dirichlet[edge])
+                hdirmask[e] |= uint8_t(1 << edge);
+    }
+
+    //! all elements are congruent axis-aligned rectangles (Cartesian): one operator set suffices
+    bool detectUniform() const
+    {
+        if (g.spherical || cfg.force_general)
+            return false;
+        const int nx = g.nx, ny = g.ny;
+        const double dx = hvx[1] - hvx[0], dy = hvy[nx + 1] - hvy[0];
+        if (!(dx > 0) || !(dy > 0))
+            return false;
+        const double tolx = 1e-9 * dx, toly = 1e-9 * dy;
+        for (int j = 0; j <= ny; ++j)
+            for (int i = 0; i <= nx; ++i) {
+                const size_t n = size_t(j) * (nx + 1) + i;
+                if (std::fabs(hvx[n] - (hvx[0] + i * dx)) > tolx * (1 + i) || std::fabs(hvy[n] - (hvy[0] + j * dy)) > toly * (1 + j))
+                    return false;
+            }
+        return true;
+    }
+
+    void setMesh(int nx, int ny, const double* coords, const double* mask, int spherical) override
+    {
+        if (nx < 2 || ny < 2)
+            throw std::runtime_error("nsdg_set_mesh: nx and ny must be >= 2");
+        meshSet = false;
+        if (graphExec) {
+            cudaGraphExecDestroy(graphExec);
+            graphExec = nullptr;
+        }
+        g.nx = nx;
+        g.ny = ny;
+        g.N = nx * ny;
+        g.Npad = int(alignUp(size_t(g.N), 32));
+        g.CG = CG;
+        g.cgnx = CG * nx + 1;
+        g.cgny = CG * ny + 1;
+        g.cgs = int(alignUp(size_t(g.cgnx), 16));
+        g.spherical = spherical ? 1 : 0;
+        cg1s = int(alignUp(size_t(nx + 1), 16));
+        ncg = size_t(g.cgs) * g.cgny;
+        ncg1 = size_t(cg1s) * (ny + 1);
+        const size_t N = g.N, Npad = g.Npad, nnodes = size_t(nx + 1) * (ny + 1);
+
+        // ---- host mesh: coordinates, pole rotation, land mask, Dirichlet lists ----
+        hvx.resize(nnodes);
+        hvy.resize(nnodes);
+        for (size_t i = 0; i < nnodes; ++i) { // coordinatesFromModelArray, ParametricMesh.cpp:198-210
+            hvx[i] = coords[2 * i];
+            hvy[i] = coords[2 * i + 1];
+        }
+        if (spherical) // RotatePoleToGreenland, ParametricMesh.hpp:137-157
+            for (size_t i = 0; i < nnodes; ++i) {
+                const double x = cos(hvy[i]) * cos(hvx[i]), y = cos(hvy[i]) * sin(hvx[i]), z = sin(hvy[i]);
+                const double aw = 40.0 * M_PI / 180.0, bw = 15.0 * M_PI / 180.0;
+                const double x1 = cos(aw) * x - sin(aw) * y, y1 = sin(aw) * x + cos(aw) * y, z1 = z;
+                const double x2 = cos(bw) * x1 - sin(bw) * z1, y2 = y1, z2 = sin(bw) * x1 + cos(bw) * z1;
+                hvy[i] = asin(z2);
+                hvx[i] = atan2(y2, x2);
+            }
+        landmask.resize(N);
+        for (size_t i = 0; i < N; ++i) // landmaskFromModelArray, ParametricMesh.cpp:217-223 (quirk Q10)
+            landmask[i] = (mask[i] == 1.) ? 1 : 0;
+        buildDirichlet();
+        uniform = detectUniform();
+
+        vx.alloc(nnodes);
+        vy.alloc(nnodes);
+        NSDG_CUDA_CHECK(cudaMemcpy(vx, hvx.data(), nnodes * 8, cudaMemcpyHostToDevice));
+        NSDG_CUDA_CHECK(cudaMemcpy(vy, hvy.data(), nnodes * 8, cudaMemcpyHostToDevice));
+        d_landmask.alloc(Npad);
+        d_dirmask.alloc(Npad);
+        NSDG_CUDA_CHECK(cudaMemcpy(d_landmask, landmask.data(), N, cudaMemcpyHostToDevice));
+        NSDG_CUDA_CHECK(cudaMemcpy(d_dirmask, hdirmask.data(), N, cudaMemcpyHostToDevice));
+        d_nodemask.alloc(ncg);
+        nodemask_kernel<CG><<<blocksFor(N), 128, 0, stream>>>(g, d_dirmask, d_nodemask);
+
+        // ---- state (zero-initialised; the reference relies on fresh pages being zero, quirk Q9) ----
+        const bool bbm = cfg.rheology == NSDG_BBM;
+        for (auto* f : { &hice, &cice, &velx, &vely, &tmp1, &tmp2, &scratchDG })
+            f->alloc(size_t(DGA) * Npad);
+        damage.alloc(bbm ? size_t(DGA) * Npad : 0);
+        ssh.alloc(Npad);
+        for (auto* f : { &s11, &s12, &s22 })
+            f->alloc(size_t(DGs) * Npad);
+        gaussA.alloc(size_t(Q) * Npad);
+        gaussB.alloc(bbm ? size_t(Q) * Npad : 0);
+        helem.alloc(bbm ? Npad : 0);
+        const size_t pX = alignUp(size_t(nx) * (ny + 1), 32), pY = alignUp(size_t(nx + 1) * ny, 32);
+        nvX.alloc(EDA * pX);
+        nvY.alloc(EDA * pY);
+        if (bbm) {
+            for (auto* f : { &velxS, &velyS, &tmp1S, &tmp2S })
+                f->alloc(size_t(DGs) * Npad);
+            nvXS.alloc(EDS * pX);
+            nvYS.alloc(EDS * pY);
+        }
+        for (auto* f : { &u, &v, &u0, &v0, &cgH, &cgA, &gradX, &gradY, &uO, &vO, &uA, &vA, &lmass, &taux, &tauy })
+            f->alloc(ncg);
+        avgU.alloc(bbm ? ncg : 0);
+        avgV.alloc(bbm ? ncg : 0);
+        for (auto* f : { &cgSSH, &mass1, &gu1, &gv1 })
+            f->alloc(ncg1);
+        staging.alloc(size_t(std::max(DGA, DGs)) * Npad, false);
+
+        // ---- operators ----
+        const size_t opN = uniform ? 1 : Npad;
+        const int nel = uniform ? 1 : g.N;
+        tAdvX.alloc(size_t(DGA) * QA * opN);
+        tAdvY.alloc(size_t(DGA) * QA * opN);
+        tiMass.alloc(size_t(DGA) * DGA * opN);
+        topA = { tAdvX, tAdvY, tiMass, opN, uniform ? 0 : 1 };
+        setup_transport_kernel<DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, topA, nel);
+        if (bbm) {
+            sAdvX.alloc(size_t(DGs) * QS * opN);
+            sAdvY.alloc(size_t(DGs) * QS * opN);
+            siMass.alloc(size_t(DGs) * DGs * opN);
+            topS = { sAdvX, sAdvY, siMass, opN, uniform ? 0 : 1 };
+            setup_transport_kernel<DGs><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, topS, nel);
+            helem_kernel<<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, helem);
+        }
+        oGx.alloc(size_t(DGs) * ND * opN);
+        oGy.alloc(size_t(DGs) * ND * opN);
+        oB.alloc(size_t(DGs) * Q * opN);
+        oBd.alloc(size_t(DGA) * Q * opN);
+        oD1.alloc(size_t(ND) * DGs * opN);
+        oD2.alloc(size_t(ND) * DGs * opN);
+        odX.alloc(16 * opN);
+        odY.alloc(16 * opN);
+        oGM.alloc(spherical ? size_t(DGs) * ND * opN : 0);
+        oDM.alloc(spherical ? size_t(ND) * DGs * opN : 0);
+        mop = { oGx, oGy, oGM, oB, oBd, oD1, oD2, oDM, odX, odY, opN, uniform ? 0 : 1 };
+        setup_momentum_kernel<CG, DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, mop, nel);
+        constexpr int CGGP = (CG == 1 ? 1 : 4);
+        lumpedmass_kernel<CG, CGGP><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(g, g.cgnx, g.cgny, g.cgs, vx, vy, lmass);
+        lumpedmass_kernel<1, 2><<<blocksFor(size_t(nx + 1) * (ny + 1)), 128, 0, stream>>>(g, nx + 1, ny + 1, cg1s, vx, vy, mass1);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (uniform) { // the single operator set goes to __constant__ memory for the subcycle kernels
+            MomentumOps h {};
+            auto pull = [&](double* dst, const DevBuf<double>& src, size_t n) {
+                NSDG_CUDA_CHECK(cudaMemcpy(dst, src.p, n * 8, cudaMemcpyDeviceToHost));
+            };
+            pull(h.Gx, oGx, DGs * ND);
+            pull(h.Gy, oGy, DGs * ND);
+            pull(h.B, oB, DGs * Q);
+            pull(h.Bd, oBd, DGA * Q);
+            pull(h.D1, oD1, ND * DGs);
+            pull(h.D2, oD2, ND * DGs);
+            NSDG_CUDA_CHECK(cudaMemcpyToSymbol(c_mops, &h, sizeof(h)));
+        }
+
+        // ---- strips and deferred-line buffers ----
+        R = 16;
+        nsx = (nx + 31) / 32;
+        nsy = (ny + R - 1) / R;
+        hbuf.alloc(size_t(nsy) * 2 * nx * NR * 2);
+        vbuf.alloc(size_t(nsx) * 2 * ny * NR * 2);
+        timing.uniform_path = uniform ? 1 : 0;
+        meshSet = true;
+    }
+
+    // ------------------------------------------------------------------------------------
+    // fields in / out
+    // ------------------------------------------------------------------------------------
+    void requireMesh() const
+    {
+        if (!meshSet)
+            throw std::runtime_error("nsdg: mesh not set (call nsdg_set_mesh first)");
+    }
+
+    //! host AoS (N x ncomp) -> device planes (nplanes), DGModelArray::ma2dg semantics (quirk Q4)
+    void uploadPlanes(const double* host, int ncomp, int nplanes, double* planes)
+    {
+        if (ncomp != 1 && ncomp != nplanes)
+            throw std::runtime_error("nsdg_set_field: ncomp must be 1 or the DG component count");
+        const size_t N = g.N;
+        if (ncomp == 1) {
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(planes, host, N * 8, cudaMemcpyHostToDevice, stream));
+            if (nplanes > 1)
+                NSDG_CUDA_CHECK(cudaMemsetAsync(planes + g.Npad, 0, size_t(nplanes - 1) * g.Npad * 8, stream));
+        } else {
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(staging, host, N * ncomp * 8, cudaMemcpyHostToDevice, stream));
+            aos2planes_kernel<<<blocksFor(N), 128, 0, stream>>>(N, g.Npad, ncomp, nplanes, staging, planes);
+        }
+    }
+    void downloadPlanes(const double* planes, int ncomp, double* host)
+    {
+        const size_t N = g.N;
+        if (ncomp == 1) {
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(host, planes, N * 8, cudaMemcpyDeviceToHost, stream));
+        } else {
+            planes2aos_kernel<<<blocksFor(N), 128, 0, stream>>>(N, g.Npad, ncomp, planes, staging);
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(host, staging, N * ncomp * 8, cudaMemcpyDeviceToHost, stream));
+        }
+    }
+    //! ModelArray -> temp DG -> DG2CG (CGDynamicsKernel.cpp:56-86)
+    void uploadViaDG2CG(const double* host, int ncomp, double* cgDest)
+    {
+        uploadPlanes(host, ncomp, ncomp == 1 ? 1 : DGA, scratchDG);
+        const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
+        if (ncomp == 1)
+            dg2cg_kernel<CG, 1><<<nb, 128, 0, stream>>>(g, scratchDG, cgDest, -INFINITY, INFINITY);
+        else
+            dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, scratchDG, cgDest, -INFINITY, INFINITY);
+    }
+    void setFieldAsync(int field, const double* host, int ncomp)
+    {
+        requireMesh();
+        switch (field) {
+        case NSDG_HICE:
+            uploadPlanes(host, ncomp, DGA, hice);
+            break;
+        case NSDG_CICE:
+            uploadPlanes(host, ncomp, DGA, cice);
+            break;
+        case NSDG_DAMAGE:
+            if (cfg.rheology != NSDG_BBM)
+                return; // the mEVP kernel just buckets unknown fields (DynamicsKernel.hpp:104-109): no effect on the path
+            uploadPlanes(host, ncomp, DGA, damage);
+            break;
+        case NSDG_U:
+            uploadViaDG2CG(host, ncomp, u);
+            break;
+        case NSDG_V:
+            uploadViaDG2CG(host, ncomp, v);
+            break;
+        case NSDG_UWIND:
+            uploadViaDG2CG(host, ncomp, uA);
+            break;
+        case NSDG_VWIND:
+            uploadViaDG2CG(host, ncomp, vA);
+            break;
+        case NSDG_UOCEAN:
+            uploadViaDG2CG(host, ncomp, uO);
+            break;
+        case NSDG_VOCEAN:
+            uploadViaDG2CG(host, ncomp, vO);
+            break;
+        case NSDG_SSH:
+            if (ncomp != 1)
+                throw std::runtime_error("nsdg_set_field: ssh is a DG0 field (ncomp must be 1)");
+            uploadPlanes(host, 1, 1, ssh);
+            break;
+        default:
+            throw std::runtime_error("nsdg_set_field: field cannot be set");
+        }
+    }
+    void setField(int field, const double* host, int ncomp) override
+    {
+        setFieldAsync(field, host, ncomp);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    void cgToDG0(const double* cgSrc, double* host)
+    {
+        cg2dg_kernel<CG, DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgSrc, topA, scratchDG);
+        downloadPlanes(scratchDG, 1, host);
+    }
+    void getFieldAsync(int field, double* host, int ncomp)
+    {
+        requireMesh();
+        const bool bbm = cfg.rheology == NSDG_BBM;
+        if (ncomp != 1 && ncomp != DGA)
+            throw std::runtime_error("nsdg_get_field: ncomp must be 1 or the DG component count");
+        switch (field) {
+        case NSDG_HICE:
+            downloadPlanes(hice, ncomp, host);
+            break;
+        case NSDG_CICE:
+            downloadPlanes(cice, ncomp, host);
+            break;
+        case NSDG_DAMAGE:
+            if (!bbm)
+                throw std::runtime_error("nsdg_get_field: damage exists for BBM only");
+            downloadPlanes(damage, ncomp, host);
+            break;
+        case NSDG_U:
+        case NSDG_V:
+            if (ncomp != 1)
+                throw std::runtime_error("nsdg_get_field: u, v are exported as DG0 cell means");
+            cgToDG0(field == NSDG_U ? u : v, host);
+            break;
+        case NSDG_TAUX:
+        case NSDG_TAUY: {
+            if (ncomp != 1)
+                throw std::runtime_error("nsdg_get_field: ice-ocean stress is exported as DG0 cell means");
+            const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
+            if (bbm)
+                iostress_kernel<NSDG_BBM><<<nb, 128, 0, stream>>>(g, p, avgU, avgV, uO, vO, taux, tauy);
+            else
+                iostress_kernel<NSDG_MEVP><<<nb, 128, 0, stream>>>(g, p, u, v, uO, vO, taux, tauy);
+            cgToDG0(field == NSDG_TAUX ? taux : tauy, host);
+            break;
+        }
+        default:
+            throw std::runtime_error("nsdg_get_field: field cannot be read");
+        }
+    }
+    void getField(int field, double* host, int ncomp) override
+    {
+        getFieldAsync(field, host, ncomp);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    // ------------------------------------------------------------------------------------
+    // advection
+    // ------------------------------------------------------------------------------------
+    template <int DG>
+    void prepareAdvection(const double* cgU, const double* cgV, TransportOpPtrs op, double* vxd, double* vyd, double* nX, double* nY)
+    {
+        const size_t pX = alignUp(size_t(g.nx) * (g.ny + 1), 32), pY = alignUp(size_t(g.nx + 1) * g.ny, 32);
+        cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgU, op, vxd);
+        cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgV, op, vyd);
+        const size_t nEdges = size_t(g.nx) * (g.ny + 1) + size_t(g.nx + 1) * g.ny;
+        normalvel_kernel<DG><<<blocksFor(nEdges), 128, 0, stream>>>(g, vx, vy, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY);
+        launches += 3;
+    }
+    //! DGTransport::step_rk2, DGTransport.cpp:521-532
+    template <int DG>
+    void transportStep(double dt, TransportOpPtrs op, const double* vxd, const double* vyd, const double* nX, const double* nY,
+        double* phi, double* t1, double* t2)
+    {
+        const size_t pX = alignUp(size_t(g.nx) * (g.ny + 1), 32), pY = alignUp(size_t(g.nx + 1) * g.ny, 32);
+        const size_t n = size_t(DG) * g.Npad;
+        const unsigned nb = blocksFor(g.N);
+        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t1);
+        add_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t1);
+        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t2);
+        heun_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t2, t1);
+        launches += 4;
+    }
+    void limit(double* f, int mode, double maxv, double minv)
+    {
+        limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, mode, maxv, minv);
+        launches += 1;
+    }
+
+    // ------------------------------------------------------------------------------------
+    // prepareIteration (CGDynamicsKernel.cpp:260-276)
+    // ------------------------------------------------------------------------------------
+    void prepareIteration()
+    {
+        const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
+        dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, hice, cgH, 1.e-4, INFINITY);
+        dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, cice, cgA, 1.e-4, 1.0);
+        // ComputeGradientOfSeaSurfaceHeight
+        GridDims g1 = g;
+        g1.CG = 1;
+        g1.cgnx = g.nx + 1;
+        g1.cgny = g.ny + 1;
+        g1.cgs = cg1s;
+        const unsigned nb1 = blocksFor(size_t(g1.cgnx) * g1.cgny);
+        dg2cg_kernel<1, 1><<<nb1, 128, 0, stream>>>(g1, ssh, cgSSH, -INFINITY, INFINITY);
+        sshgrad_cg1_kernel<<<nb1, 128, 0, stream>>>(g, cg1s, cgSSH, mop, mass1, gu1, gv1);
+        sshgrad_cg_kernel<CG><<<nb, 128, 0, stream>>>(g, cg1s, gu1, gv1, gradX, gradY);
+        launches += 5;
+    }
+
+    // ------------------------------------------------------------------------------------
+    // subcycles
+    // ------------------------------------------------------------------------------------
+    SubcycleArgs makeArgs(double deltaT) const
+    {
+        SubcycleArgs a {};
+        a.g = g;
+        a.R = R;
+        a.nsx = nsx;
+        a.nsy = nsy;
+        a.s11 = s11;
+        a.s12 = s12;
+        a.s22 = s22;
+        a.damage = damage;
+        a.gaussA = gaussA;
+        a.gaussB = gaussB;
+        a.helem = helem;
+        a.landmask = d_landmask;
+        a.Gx = oGx;
+        a.Gy = oGy;
+        a.GM = oGM;
+        a.B = oB;
+        a.Bd = oBd;
+        a.D1 = oD1;
+        a.D2 = oD2;
+        a.DM = oDM;
+        a.u = u;
+        a.v = v;
+        a.avgU = avgU;
+        a.avgV = avgV;
+        a.u0 = u0;
+        a.v0 = v0;
+        a.cgH = cgH;
+        a.cgA = cgA;
+        a.uAtm = uA;
+        a.vAtm = vA;
+        a.uOcn = uO;
+        a.vOcn = vO;
+        a.gradX = gradX;
+        a.gradY = gradY;
+        a.lmass = lmass;
+        a.nodemask = d_nodemask;
+        a.hbuf = hbuf;
+        a.vbuf = vbuf;
+        a.deltaT = deltaT;
+        a.nSteps = double(cfg.nsteps);
+        a.p = p;
+        return a;
+    }
+
+    template <int RHEO> void launchSubcycle(const SubcycleArgs& a)
+    {
+        const unsigned nwarps = unsigned(nsx) * nsy;
+        const unsigned nbStrip = (nwarps + 3) / 4;
+        const size_t nLine = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
+        if (uniform)
+            subcycle_strip<CG, DGA, RHEO, true, false><<<nbStrip, 128, 0, stream>>>(a);
+        else if (g.spherical)
+            subcycle_strip<CG, DGA, RHEO, false, true><<<nbStrip, 128, 0, stream>>>(a);
+        else
+            subcycle_strip<CG, DGA, RHEO, false, false><<<nbStrip, 128, 0, stream>>>(a);
+        subcycle_lines<CG, RHEO><<<blocksFor(nLine), 128, 0, stream>>>(a);
+    }
+
+    void runSubcycles(int n, double deltaT)
+    {
+        const SubcycleArgs a = makeArgs(deltaT);
+        auto body = [&]() {
+            for (int i = 0; i < n; ++i) {
+                if (cfg.rheology == NSDG_BBM)
+                    launchSubcycle<NSDG_BBM>(a);
+                else
+                    launchSubcycle<NSDG_MEVP>(a);
+            }
+        };
+        if (cfg.use_cuda_graph && n > 1) {
+            if (!graphExec || graphN != n || graphDeltaT != deltaT) {
+                if (graphExec) {
+                    cudaGraphExecDestroy(graphExec);
+                    graphExec = nullptr;
+                }
+                cudaGraph_t graph;
+                NSDG_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                body();
+                NSDG_CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+                NSDG_CUDA_CHECK(cudaGraphInstantiate(&graphExec, graph, 0));
+                cudaGraphDestroy(graph);
+                graphN = n;
+                graphDeltaT = deltaT;
+            }
+            NSDG_CUDA_CHECK(cudaGraphLaunch(graphExec, stream));
+        } else {
+            body();
+        }
+        NSDG_CUDA_CHECK(cudaGetLastError());
+        launches += 2L * n;
+    }
+
+    void subcycles(int n, float* ms) override
+    {
+        requireMesh();
+        launches = 0;
+        const double deltaT = graphDeltaT != 0 ? graphDeltaT : lastDeltaT;
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+        runSubcycles(n, deltaT);
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        float t = 0;
+        NSDG_CUDA_CHECK(cudaEventElapsedTime(&t, ev[0], ev[1]));
+        if (ms)
+            *ms = t;
+        timing.subcycle_ms = t;
+        timing.kernel_launches = launches;
+    }
+
+    double lastDeltaT = 1.0;
+
+    // ------------------------------------------------------------------------------------
+    // one timestep
+    // ------------------------------------------------------------------------------------
+    void stepAsync(double dt)
+    {
+        requireMesh();
+        launches = 0;
+        const bool bbm = cfg.rheology == NSDG_BBM;
+        const size_t cgBytes = ncg * 8;
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+        // ---- advection + limiters (DynamicsKernel.hpp:160-172) ----
+        prepareAdvection<DGA>(bbm ? avgU : u, bbm ? avgV : v, topA, velx, vely, nvX, nvY);
+        transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, cice, tmp1, tmp2);
+        transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, hice, tmp1, tmp2);
+        limit(cice, 3, 1.0, 0.0);
+        limit(hice, 2, 0.0, 0.0);
+        if (bbm) { // BrittleCGDynamicsKernel.hpp:97-106
+            prepareAdvection<DGs>(avgU, avgV, topS, velxS, velyS, nvXS, nvYS);
+            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s11, tmp1S, tmp2S);
+            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s12, tmp1S, tmp2S);
+            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s22, tmp1S, tmp2S);
+            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, damage, tmp1, tmp2);
+            limit(damage, 3, 1.0, 1e-12);
+        }
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+        // ---- prepareIteration ----
+        prepareIteration();
+        double deltaT;
+        if (!bbm) { // VPCGDynamicsKernel.hpp:70-74
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(u0, u, cgBytes, cudaMemcpyDeviceToDevice, stream));
+            NSDG_CUDA_CHECK(cudaMemcpyAsync(v0, v, cgBytes, cudaMemcpyDeviceToDevice, stream));
+            deltaT = dt;
+            gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB);
+        } else { // BrittleCGDynamicsKernel.hpp:110-114
+            deltaT = dt / double(cfg.nsteps);
+            NSDG_CUDA_CHECK(cudaMemsetAsync(avgU, 0, cgBytes, stream));
+            NSDG_CUDA_CHECK(cudaMemsetAsync(avgV, 0, cgBytes, stream));
+            gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB);
+        }
+        launches += 1;
+        lastDeltaT = deltaT;
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+        // ---- the subcycle loop ----
+        const long before = launches;
+        runSubcycles(cfg.nsteps, deltaT);
+        (void)before;
+        NSDG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
+    }
+    void finishTiming()
+    {
+        NSDG_CUDA_CHECK(cudaEventElapsedTime(&timing.advection_ms, ev[0], ev[1]));
+        NSDG_CUDA_CHECK(cudaEventElapsedTime(&timing.prepare_ms, ev[1], ev[2]));
+        NSDG_CUDA_CHECK(cudaEventElapsedTime(&timing.subcycle_ms, ev[2], ev[3]));
+        NSDG_CUDA_CHECK(cudaEventElapsedTime(&timing.total_ms, ev[0], ev[3]));
+        timing.kernel_launches = launches;
+    }
+    void step(double dt) override
+    {
+        stepAsync(dt);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        finishTiming();
+    }
+
+    //! pin the model's buffers once so that the per-step copies run at PCIe speed and asynchronously
+    void pin(const void* ptr, size_t bytes)
+    {
+        if (!ptr || !cfg.pin_host_buffers)
+            return;
+        for (auto& r : registered)
+            if (r.first == ptr && r.second >= bytes)
+                return;
+        if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess)
+            registered.emplace_back(ptr, bytes);
+        else
+            cudaGetLastError(); // already pinned by the caller or not pinnable: copies still work
+    }
+
+    //! MEVPDynamics::update / BBMDynamics::update in one call
+    void update(const nsdg_update_io* io, double dt) override
+    {
+        requireMesh();
+        const size_t bytes = size_t(g.N) * 8;
+        const double* ins[] = { io->hice_in, io->cice_in, io->damage_in, io->uwind, io->vwind, io->uocean, io->vocean, io->ssh };
+        const int inField[] = { NSDG_HICE, NSDG_CICE, NSDG_DAMAGE, NSDG_UWIND, NSDG_VWIND, NSDG_UOCEAN, NSDG_VOCEAN, NSDG_SSH };
+        double* outs[] = { io->hice_out, io->cice_out, io->damage_out, io->u_out, io->v_out, io->taux_out, io->tauy_out };
+        const int outField[] = { NSDG_HICE, NSDG_CICE, NSDG_DAMAGE, NSDG_U, NSDG_V, NSDG_TAUX, NSDG_TAUY };
+        for (const double* ptr : ins)
+            pin(ptr, bytes);
+        for (double* ptr : outs)
+            pin(ptr, bytes);
+        for (int i = 0; i < 8; ++i)
+            if (ins[i])
+                setFieldAsync(inField[i], ins[i], 1);
+        stepAsync(dt);
+        for (int i = 0; i < 7; ++i)
+            if (outs[i] && !(outField[i] == NSDG_DAMAGE && cfg.rheology != NSDG_BBM))
+                getFieldAsync(outField[i], outs[i], 1);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        finishTiming();
+    }
+
+    // ------------------------------------------------------------------------------------
+    // test access in the reference layouts
+    // ------------------------------------------------------------------------------------
+    struct Internal {
+        enum Kind { CGF, CG1F, DGF, OPF, EDGEX, EDGEY } kind;
+        double* ptr;
+        int comps; //!< DGF: planes; OPF: entries
+    };
+    bool lookup(const std::string& n, Internal& out)
+    {
+        const std::map<std::string, Internal> t = {
+            { "cg_u", { Internal::CGF, u, 1 } }, { "cg_v", { Internal::CGF, v, 1 } }, { "cgH", { Internal::CGF, cgH, 1 } },
+            { "cgA", { Internal::CGF, cgA, 1 } }, { "uGradSSH", { Internal::CGF, gradX, 1 } },
+            { "vGradSSH", { Internal::CGF, gradY, 1 } }, { "uOcean", { Internal::CGF, uO, 1 } },
+            { "vOcean", { Internal::CGF, vO, 1 } }, { "uAtmos", { Internal::CGF, uA, 1 } }, { "vAtmos", { Internal::CGF, vA, 1 } },
+            { "avgU", { Internal::CGF, avgU, 1 } }, { "avgV", { Internal::CGF, avgV, 1 } }, { "u0", { Internal::CGF, u0, 1 } },
+            { "v0", { Internal::CGF, v0, 1 } }, { "lumpedcgmass", { Internal::CGF, lmass, 1 } },
+            { "lumpedcg1mass", { Internal::CG1F, mass1, 1 } }, { "hice", { Internal::DGF, hice, DGA } },
+            { "cice", { Internal::DGF, cice, DGA } }, { "damage", { Internal::DGF, damage, DGA } },
+            { "s11", { Internal::DGF, s11, DGs } }, { "s12", { Internal::DGF, s12, DGs } }, { "s22", { Internal::DGF, s22, DGs } },
+            { "velx", { Internal::DGF, velx, DGA } }, { "vely", { Internal::DGF, vely, DGA } },
+            { "ssh", { Internal::DGF, ssh, 1 } }, { "divS1", { Internal::OPF, oD1, ND * DGs } },
+            { "divS2", { Internal::OPF, oD2, ND * DGs } }, { "divM", { Internal::OPF, oDM, ND * DGs } },
+            { "iMgradX", { Internal::OPF, oGx, DGs * ND } }, { "iMgradY", { Internal::OPF, oGy, DGs * ND } },
+            { "iMM", { Internal::OPF, oGM, DGs * ND } }, { "iMJwPSI", { Internal::OPF, oB, DGs * Q } },
+            { "iMJwPSI_dam", { Internal::OPF, oBd, DGA * Q } }, { "dX_SSH", { Internal::OPF, odX, 16 } },
+            { "dY_SSH", { Internal::OPF, odY, 16 } }, { "AdvX", { Internal::OPF, tAdvX, DGA * QA } },
+            { "AdvY", { Internal::OPF, tAdvY, DGA * QA } }, { "iMass", { Internal::OPF, tiMass, DGA * DGA } },
+            { "normalvel_X", { Internal::EDGEX, nvX, EDA } }, { "normalvel_Y", { Internal::EDGEY, nvY, EDA } },
+        };
+        auto it = t.find(n);
+        if (it == t.end() || it->second.ptr == nullptr)
+            return false;
+        out = it->second;
+        return true;
+    }
+    void getInternal(const std::string& name, double* host, size_t cap, size_t* count) override
+    {
+        requireMesh();
+        Internal in;
+        if (!lookup(name, in))
+            throw std::runtime_error("nsdg_get_internal: unknown or unallocated array " + name);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const size_t N = g.N;
+        size_t n = 0;
+        std::vector<double> tmp;
+        auto pull = [&](size_t cnt) {
+            tmp.resize(cnt);
+            NSDG_CUDA_CHECK(cudaMemcpy(tmp.data(), in.ptr, cnt * 8, cudaMemcpyDeviceToHost));
+        };
+        if (in.kind == Internal::CGF || in.kind == Internal::CG1F) {
+            const int nxn = in.kind == Internal::CGF ? g.cgnx : g.nx + 1, nyn = in.kind == Internal::CGF ? g.cgny : g.ny + 1;
+            const int st = in.kind == Internal::CGF ? g.cgs : cg1s;
+            n = size_t(nxn) * nyn;
+            if (count)
+                *count = n;
+            if (!host || cap < n)
+                return;
+            pull(size_t(st) * nyn);
+            for (int r = 0; r < nyn; ++r)
+                std::copy(tmp.begin() + size_t(r) * st, tmp.begin() + size_t(r) * st + nxn, host + size_t(r) * nxn);
+        } else if (in.kind == Internal::DGF) {
+            n = N * in.comps;
+            if (count)
+                *count = n;
+            if (!host || cap < n)
+                return;
+            pull(size_t(in.comps) * g.Npad);
+            for (size_t e = 0; e < N; ++e)
+                for (int c = 0; c < in.comps; ++c)
+                    host[e * in.comps + c] = tmp[size_t(c) * g.Npad + e];
+        } else if (in.kind == Internal::OPF) {
+            n = N * in.comps;
+            if (count)
+                *count = n;
+            if (!host || cap < n)
+                return;
+            const size_t opN = uniform ? 1 : g.Npad;
+            pull(size_t(in.comps) * opN);
+            for (size_t e = 0; e < N; ++e)
+                for (int k = 0; k < in.comps; ++k)
+                    host[e * in.comps + k] = tmp[size_t(k) * opN + (uniform ? 0 : e)];
+        } else {
+            const size_t ne = in.kind == Internal::EDGEX ? size_t(g.nx) * (g.ny + 1) : size_t(g.nx + 1) * g.ny;
+            const size_t pitch = alignUp(ne, 32);
+            n = ne * in.comps;
+            if (count)
+                *count = n;
+            if (!host || cap < n)
+                return;
+            pull(pitch * in.comps);
+            for (size_t e = 0; e < ne; ++e)
+                for (int c = 0; c < in.comps; ++c)
+                    host[e * in.comps + c] = tmp[size_t(c) * pitch + e];
+        }
+    }
+    void setInternal(const std::string& name, const double* host, size_t count) override
+    {
+        requireMesh();
+        Internal in;
+        if (!lookup(name, in))
+            throw std::runtime_error("nsdg_set_internal: unknown or unallocated array " + name);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const size_t N = g.N;
+        std::vector<double> tmp;
+        if (in.kind == Internal::CGF) {
+            if (count != size_t(g.cgnx) * g.cgny)
+                throw std::runtime_error("nsdg_set_internal: wrong size for " + name);
+            tmp.assign(ncg, 0.0);
+            for (int r = 0; r < g.cgny; ++r)
+                std::copy(host + size_t(r) * g.cgnx, host + size_t(r + 1) * g.cgnx, tmp.begin() + size_t(r) * g.cgs);
+            NSDG_CUDA_CHECK(cudaMemcpy(in.ptr, tmp.data(), ncg * 8, cudaMemcpyHostToDevice));
+        } else if (in.kind == Internal::DGF) {
+            if (count != N * in.comps)
+                throw std::runtime_error("nsdg_set_internal: wrong size for " + name);
+            tmp.assign(size_t(in.comps) * g.Npad, 0.0);
+            for (size_t e = 0; e < N; ++e)
+                for (int c = 0; c < in.comps; ++c)
+                    tmp[size_t(c) * g.Npad + e] = host[e * in.comps + c];
+            NSDG_CUDA_CHECK(cudaMemcpy(in.ptr, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
+        } else
+            throw std::runtime_error("nsdg_set_internal: array is read-only: " + name);
+    }
+};
+
+static HandleBase* makeHandle(const nsdg_config& c)
+{
+    if (c.rheology != NSDG_MEVP && c.rheology != NSDG_BBM)
+        throw std::runtime_error("nsdg_create: unknown rheology");
+    if (c.nsteps < 1)
+        throw std::runtime_error("nsdg_create: nsteps must be >= 1");
+    if (c.dgadv == 6 && c.cgdegree == 2)
+        return new Handle<2, 6>(c);
+    if (c.dgadv == 3 && c.cgdegree == 1)
+        return new Handle<1, 3>(c);
+    throw std::runtime_error("nsdg_create: supported (dgadv, cgdegree) builds are (6,2) and (3,1)");
+}
+
+} // namespace nsdg
+
+using namespace nsdg;
+
+#define NSDG_TRY try {
+#define NSDG_CATCH                                                                                                   \
+    }                                                                                                                \
+    catch (const std::exception& ex)                                                                                 \
+    {                                                                                                                \
+        g_lastError = ex.what();                                                                                     \
+        return 1;                                                                                                    \
+    }                                                                                                                \
+    return 0;
+
+static HandleBase* H(nsdg_handle h)
+{
+    if (!h)
+        throw std::runtime_error("nsdg: null handle");
+    return reinterpret_cast<HandleBase*>(h);
+}
+
+extern "C" {
+
+void nsdg_config_default(nsdg_config* cfg)
+{
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->rheology = NSDG_MEVP;
+    cfg->dgadv = 6;
+    cfg->cgdegree = 2;
+    cfg->nsteps = 100;
+    cfg->device = -1;
+    cfg->use_cuda_graph = 1;
+    cfg->force_general = 0;
+    cfg->pin_host_buffers = 0;
+    cfg->alpha = 1500.0;
+    cfg->beta = 1500.0;
+    cfg->rank = 0;
+    cfg->nranks = 1;
+    for (int& n : cfg->neighbour)
+        n = -1;
+}
+
+int nsdg_create(const nsdg_config* cfg, nsdg_handle* out)
+{
+    NSDG_TRY
+    if (!cfg || !out)
+        throw std::runtime_error("nsdg_create: null argument");
+    *out = reinterpret_cast<nsdg_handle>(makeHandle(*cfg));
+    NSDG_CATCH
+}
+int nsdg_destroy(nsdg_handle h)
+{
+    NSDG_TRY
+    delete H(h);
+    NSDG_CATCH
+}
+int nsdg_set_mesh(nsdg_handle h, int nx, int ny, const double* coords_xy, const double* mask, int spherical)
+{
+    NSDG_TRY
+    if (!coords_xy || !mask)
+        throw std::runtime_error("nsdg_set_mesh: coords and mask are required (IDynamics.hpp:107-120 throws likewise)");
+    H(h)->setMesh(nx, ny, coords_xy, mask, spherical);
+    NSDG_CATCH
+}
+int nsdg_set_field(nsdg_handle h, int field, const double* host, int ncomp)
+{
+    NSDG_TRY
+    if (!host)
+        throw std::runtime_error("nsdg_set_field: null data");
+    H(h)->setField(field, host, ncomp);
+    NSDG_CATCH
+}
+int nsdg_get_field(nsdg_handle h, int field, double* host, int ncomp)
+{
+    NSDG_TRY
+    if (!host)
+        throw std::runtime_error("nsdg_get_field: null data");
+    H(h)->getField(field, host, ncomp);
+    NSDG_CATCH
+}
+int nsdg_step(nsdg_handle h, double dt_seconds)
+{
+    NSDG_TRY
+    H(h)->step(dt_seconds);
+    NSDG_CATCH
+}
+int nsdg_update(nsdg_handle h, const nsdg_update_io* io, double dt_seconds)
+{
+    NSDG_TRY
+    if (!io)
+        throw std::runtime_error("nsdg_update: null io");
+    H(h)->update(io, dt_seconds);
+    NSDG_CATCH
+}
+int nsdg_subcycles(nsdg_handle h, int n, float* ms)
+{
+    NSDG_TRY
+    H(h)->subcycles(n, ms);
+    NSDG_CATCH
+}
+int nsdg_get_timing(nsdg_handle h, nsdg_timing* t)
+{
+    NSDG_TRY
+    *t = H(h)->timing;
+    NSDG_CATCH
+}
+int nsdg_get_landmask(nsdg_handle h, unsigned char* out)
+{
+    NSDG_TRY
+    HandleBase* b = H(h);
+    if (!b->meshSet)
+        throw std::runtime_error("nsdg_get_landmask: mesh not set");
+    std::copy(b->landmask.begin(), b->landmask.end(), out);
+    NSDG_CATCH
+}
+int nsdg_get_dirichlet(nsdg_handle h, int edge, long* out, size_t capacity, size_t* count)
+{
+    NSDG_TRY
+    HandleBase* b = H(h);
+    if (!b->meshSet || edge < 0 || edge > 3)
+        throw std::runtime_error("nsdg_get_dirichlet: mesh not set or bad edge");
+    const auto& d = b->dirichlet[edge];
+    if (count)
+        *count = d.size();
+    if (out && capacity >= d.size())
+        std::copy(d.begin(), d.end(), out);
+    NSDG_CATCH
+}
+int nsdg_get_internal(nsdg_handle h, const char* name, double* host, size_t capacity, size_t* count)
+{
+    NSDG_TRY
+    H(h)->getInternal(name, host, capacity, count);
+    NSDG_CATCH
+}
+int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_t count)
+{
+    NSDG_TRY
+    H(h)->setInternal(name, host, count);
+    NSDG_CATCH
+}
+int nsdg_halo_export(nsdg_handle, unsigned char*)
+{
+    g_lastError = "nsdg_halo_export: multi-GPU halo exchange is not built yet";
+    return 1;
+}
+int nsdg_halo_connect(nsdg_handle, int, const unsigned char*)
+{
+    g_lastError = "nsdg_halo_connect: multi-GPU halo exchange is not built yet";
+    return 1;
+}
+int nsdg_halo_ready(nsdg_handle)
+{
+    g_lastError = "nsdg_halo_ready: multi-GPU halo exchange is not built yet";
+    return 1;
+}
+const char* nsdg_last_error(void) { return g_lastError.c_str(); }
+const char* nsdg_version(void) { return "nsdg-cuda 0.1 (sm_100a)"; }
+}

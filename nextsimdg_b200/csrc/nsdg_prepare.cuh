@@ -1,0 +1,281 @@
+/*
+ * nsdg_prepare.cuh -- once-per-mesh and once-per-step kernels around the subcycle loop.
+ *
+ *   setup_*_kernel         operator planes per element      dynamics/src/ParametricMap.cpp:13-87, :209-356
+ *   lumpedmass_kernel      lumpedcgmass / lumpedcg1mass     dynamics/src/ParametricMap.cpp:94-206
+ *   nodemask_kernel        node set of dirichletZero        dynamics/src/CGDynamicsKernel.cpp:401-437
+ *   sshgrad_*_kernel       ComputeGradientOfSeaSurfaceHeight dynamics/src/CGDynamicsKernel.cpp:126-258
+ *   gaussconst_kernel      the h,a-dependent factors of the stress update, constant over a step:
+ *                          mEVP P = P* h exp(-20(1-a))       MEVPStressUpdateStep.hpp:53-56,74-76
+ *                          BBM  h, exp(C(1-a))               BBMStressUpdateStep.hpp:54-57,76-78
+ *   iostress_kernel        getIceOceanStress                VPCGDynamicsKernel.hpp:96-110,
+ *                                                           BrittleCGDynamicsKernel.hpp:168-182
+ */
+#pragma once
+#include "nsdg_transport.cuh"
+
+namespace nsdg {
+
+template <int DG>
+__global__ void setup_transport_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
+    TransportOpPtrs op, int nelem)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(nelem))
+        return;
+    double c[4][2];
+    elementCorners(vx, vy, g.nx, int(e % g.nx), int(e / g.nx), g.spherical, c);
+    transportOpsOfElement<DG>(c, g.spherical, op, e);
+}
+
+template <int CG, int DGA>
+__global__ void setup_momentum_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
+    MomentumOpPtrs op, int nelem)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(nelem))
+        return;
+    double c[4][2];
+    elementCorners(vx, vy, g.nx, int(e % g.nx), int(e / g.nx), g.spherical, c);
+    momentumOpsOfElement<CG, DGA>(c, g.spherical, op, e);
+}
+
+//! element size h = sqrt(area) (ParametricMesh.hpp:276-299), used by the BBM stress update
+__global__ void helem_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy, double* __restrict__ h)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    h[e] = sqrt(elementArea(vx, vy, g.nx, int(e % g.nx), int(e / g.nx)));
+}
+
+//! lumped mass per node of the CG(CGM) space, CGGP Gauss points per direction; gather in the
+//! reference's scatter order (even element rows first, then odd; x ascending).
+template <int CGM, int CGGP>
+__global__ void lumpedmass_kernel(GridDims g, int cgnx, int cgny, int cgs, const double* __restrict__ vx,
+    const double* __restrict__ vy, double* __restrict__ mass)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(cgnx) * cgny)
+        return;
+    const int c = int(t % cgnx), r = int(t / cgnx);
+    const int jx = c % CGM, jy = r % CGM;
+    double sum = 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int a = 0; a < 2; ++a) {
+            // a = 0: element row below the node row (local row CGM), a = 1: element row containing it
+            int ey, ly;
+            if (a == 0) {
+                if (!(jy == 0 && r > 0))
+                    continue;
+                ey = r / CGM - 1;
+                ly = CGM;
+            } else {
+                if (r >= CGM * g.ny)
+                    continue;
+                ey = r / CGM;
+                ly = jy;
+            }
+            if ((ey % 2) != pass)
+                continue;
+            for (int b = 0; b < 2; ++b) {
+                int ex, lx;
+                if (b == 0) {
+                    if (!(jx == 0 && c > 0))
+                        continue;
+                    ex = c / CGM - 1;
+                    lx = CGM;
+                } else {
+                    if (c >= CGM * g.nx)
+                        continue;
+                    ex = c / CGM;
+                    lx = jx;
+                }
+                double crn[4][2];
+                elementCorners(vx, vy, g.nx, ex, ey, g.spherical, crn);
+                sum += lumpedMassShare<CGM, CGGP>(crn, g.spherical, ly * (CGM + 1) + lx);
+            }
+        }
+    mass[size_t(r) * cgs + c] = sum;
+}
+
+//! marks the CG nodes of every listed Dirichlet element edge (CGDynamicsKernel.cpp:401-437)
+template <int CG>
+__global__ void nodemask_kernel(GridDims g, const uint8_t* __restrict__ dirmask, uint8_t* __restrict__ nodemask)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    const uint8_t dm = dirmask[e];
+    if (!dm)
+        return;
+    const int ix = int(e % g.nx), iy = int(e / g.nx);
+    for (int j = 0; j <= CG; ++j) {
+        if (dm & 1)
+            nodemask[size_t(CG * iy) * g.cgs + CG * ix + j] = 1;
+        if (dm & 2)
+            nodemask[size_t(CG * iy + j) * g.cgs + CG * ix + CG] = 1;
+        if (dm & 4)
+            nodemask[size_t(CG * iy + CG) * g.cgs + CG * ix + j] = 1;
+        if (dm & 8)
+            nodemask[size_t(CG * iy + j) * g.cgs + CG * ix] = 1;
+    }
+}
+
+//! raw CG1 gradient of the CG1 sea-surface height: per CG1 node gather, even element rows first
+//! (CGDynamicsKernel.cpp:138-175).  g1 = CG1 node grid (cgnx = nx+1).
+__global__ void sshgrad_cg1_kernel(GridDims g, int cg1s, const double* __restrict__ cgSSH, MomentumOpPtrs op,
+    const double* __restrict__ mass1, double* __restrict__ gu, double* __restrict__ gv)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int n1x = g.nx + 1, n1y = g.ny + 1;
+    if (t >= long(n1x) * n1y)
+        return;
+    const int c = int(t % n1x), r = int(t / n1x);
+    double sx = 0.0, sy = 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int a = 0; a < 2; ++a) {
+            const int ey = r - 1 + a, ly = 1 - a;
+            if (ey < 0 || ey >= g.ny || (ey % 2) != pass)
+                continue;
+            for (int b = 0; b < 2; ++b) {
+                const int ex = c - 1 + b, lx = 1 - b;
+                if (ex < 0 || ex >= g.nx)
+                    continue;
+                const size_t e = size_t(ey) * g.nx + ex;
+                const size_t n0 = size_t(ey) * cg1s + ex;
+                const double loc[4] = { cgSSH[n0], cgSSH[n0 + 1], cgSSH[n0 + cg1s], cgSSH[n0 + cg1s + 1] };
+                const int i = ly * 2 + lx;
+                double tx = 0, ty = 0;
+                for (int j = 0; j < 4; ++j) {
+                    tx += op.dXssh[(i * 4 + j) * op.pitch + e * op.estride] * loc[j];
+                    ty += op.dYssh[(i * 4 + j) * op.pitch + e * op.estride] * loc[j];
+                }
+                sx -= tx;
+                sy -= ty;
+            }
+        }
+    const size_t n = size_t(r) * cg1s + c;
+    gu[n] = sx / mass1[n];
+    gv[n] = sy / mass1[n];
+}
+
+//! boundary extension + CG1 -> CG interpolation of the SSH gradient (CGDynamicsKernel.cpp:177-257).
+//! The boundary copies of the reference only ever read interior CG1 nodes, so the corrected CG1
+//! value at (i,j) is the raw value at (clamp(i,1,nx-1), clamp(j,1,ny-1)).
+template <int CG>
+__global__ void sshgrad_cg_kernel(GridDims g, int cg1s, const double* __restrict__ gu1, const double* __restrict__ gv1,
+    double* __restrict__ gu, double* __restrict__ gv)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const int c = int(t % g.cgnx), r = int(t / g.cgnx);
+    auto at = [&](const double* f, int i, int j) {
+        i = min(max(i, 1), g.nx - 1);
+        j = min(max(j, 1), g.ny - 1);
+        return f[size_t(j) * cg1s + i];
+    };
+    double u, v;
+    if (CG == 1) {
+        u = at(gu1, c, r);
+        v = at(gv1, c, r);
+    } else {
+        const int i = c / 2, j = r / 2, mx = c % 2, my = r % 2;
+        if (!mx && !my) {
+            u = at(gu1, i, j);
+            v = at(gv1, i, j);
+        } else if (mx && !my) {
+            u = 0.5 * (at(gu1, i, j) + at(gu1, i + 1, j));
+            v = 0.5 * (at(gv1, i, j) + at(gv1, i + 1, j));
+        } else if (!mx && my) {
+            u = 0.5 * (at(gu1, i, j) + at(gu1, i, j + 1));
+            v = 0.5 * (at(gv1, i, j) + at(gv1, i, j + 1));
+        } else {
+            u = 0.25 * (at(gu1, i, j) + at(gu1, i + 1, j) + at(gu1, i, j + 1) + at(gu1, i + 1, j + 1));
+            v = 0.25 * (at(gv1, i, j) + at(gv1, i + 1, j) + at(gv1, i, j + 1) + at(gv1, i + 1, j + 1));
+        }
+    }
+    gu[size_t(r) * g.cgs + c] = u;
+    gv[size_t(r) * g.cgs + c] = v;
+}
+
+//! per-step Gauss-point constants of the stress update
+template <int DGA, int GS, int RHEO>
+__global__ void gaussconst_kernel(GridDims g, PhysParams p, const double* __restrict__ hice, const double* __restrict__ cice,
+    double* __restrict__ outA, double* __restrict__ outB)
+{
+    constexpr int Q = GS * GS;
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    double h[DGA], a[DGA];
+#pragma unroll
+    for (int j = 0; j < DGA; ++j) {
+        h[j] = hice[size_t(j) * g.Npad + e];
+        a[j] = cice[size_t(j) * g.Npad + e];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double hq = 0, aq = 0;
+#pragma unroll
+        for (int j = 0; j < DGA; ++j) {
+            const double w = PSI(GS, j, q);
+            if (w != 0.0) {
+                hq = (j == 0) ? h[0] * w : fma(h[j], w, hq);
+                aq = (j == 0) ? a[0] * w : fma(a[j], w, aq);
+            }
+        }
+        hq = fmax(hq, 0.0);
+        aq = fmin(fmax(aq, 0.0), 1.0);
+        if constexpr (RHEO == NSDG_MEVP) {
+            outA[size_t(q) * g.Npad + e] = p.Pstar * hq * exp(-20.0 * (1.0 - aq));
+        } else {
+            outA[size_t(q) * g.Npad + e] = hq;
+            outB[size_t(q) * g.Npad + e] = exp(p.compaction_param * (1.0 - aq));
+        }
+    }
+}
+
+//! ice-ocean stress on the CG nodes (quirk Q14)
+template <int RHEO>
+__global__ void iostress_kernel(GridDims g, PhysParams p, const double* __restrict__ u, const double* __restrict__ v,
+    const double* __restrict__ uO, const double* __restrict__ vO, double* __restrict__ taux, double* __restrict__ tauy)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
+    if constexpr (RHEO == NSDG_MEVP) {
+        const double uR = u[n] - uO[n], vR = v[n] - vO[n];
+        const double absocn = sqrt(uR * uR + vR * vR);
+        taux[n] = p.F_ocean * absocn * uR;
+        tauy[n] = p.F_ocean * absocn * vR;
+    } else { // u, v = avgU, avgV
+        const double uR = uO[n] - u[n], vR = vO[n] - v[n];
+        const double cPrime = p.F_ocean * hypot(uR, vR);
+        taux[n] = cPrime * (uR * p.cosOceanAngle - vR * p.sinOceanAngle);
+        tauy[n] = cPrime * (vR * p.cosOceanAngle + uR * p.sinOceanAngle);
+    }
+}
+
+//! AoS (row-major N x ncomp, the ModelArray layout) <-> planes
+__global__ void aos2planes_kernel(size_t N, size_t Npad, int ncomp, int nplanes, const double* __restrict__ aos,
+    double* __restrict__ planes)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= N)
+        return;
+    for (int c = 0; c < nplanes; ++c)
+        planes[size_t(c) * Npad + e] = (c < ncomp) ? aos[e * ncomp + c] : 0.0;
+}
+__global__ void planes2aos_kernel(size_t N, size_t Npad, int ncomp, const double* __restrict__ planes, double* __restrict__ aos)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= N)
+        return;
+    for (int c = 0; c < ncomp; ++c)
+        aos[e * ncomp + c] = planes[size_t(c) * Npad + e];
+}
+
+} // namespace nsdg

@@ -1,0 +1,455 @@
+/*
+ * nsdg_transport.cuh -- DG advection on the parametric mesh and the DG<->CG transfers, as
+ * one-thread-per-element (or per node / per edge) gather kernels on the plane layout.
+ *
+ *   cg2dg_kernel          Interpolations::CG2DG             dynamics/src/Interpolations.cpp:74-122
+ *   dg2cg_kernel          Interpolations::DG2CG             dynamics/src/Interpolations.cpp:129-204
+ *   normalvel_kernel      DGTransport::reinitnormalvelocity dynamics/src/DGTransport.cpp:158-252
+ *   transport_kernel      DGTransport::DGTransportOperator  dynamics/src/DGTransport.cpp:272-512
+ *                         (cell_term + edge_term_X/Y + boundary_* + inverse mass)
+ *   axpy kernels          DGTransport::step_rk2             dynamics/src/DGTransport.cpp:521-532
+ *   limit_kernel          LimitMax / LimitMin               dynamics/src/include/dgLimit.hpp:16-84
+ *
+ * The reference scatters edge fluxes into both neighbours; here every element gathers the flux
+ * through its own four edges (each interior edge flux is evaluated twice, identically), in the
+ * reference's accumulation order: cell, left, right, bottom, top, then Dirichlet sides 0..3.
+ * Periodic edges are not reachable through IDynamics (DynamicsKernel.hpp:54 leaves them TODO),
+ * so they are not implemented on the device.
+ */
+#pragma once
+#include "nsdg_setup.cuh"
+
+namespace nsdg {
+
+//! element Dirichlet side bits (bit s set: element is in smesh.dirichlet[s]); bit 4: ice element
+__device__ __forceinline__ bool isIce(const uint8_t* landmask, size_t e) { return __ldg(landmask + e) != 0; }
+
+// ------------------------------------------------------------------------------------------
+// CG -> DG L2 projection (per element).  Uses the stored inverse DG mass matrix of the transport
+// map (Cartesian: exactly massMatrix<DG>().inverse(); spherical: that / EarthRadius, undone here).
+// ------------------------------------------------------------------------------------------
+template <int CG, int DG>
+__global__ void cg2dg_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
+    const double* __restrict__ cg, TransportOpPtrs op, double* __restrict__ dg)
+{
+    constexpr int G = gp1d(DG), Q = G * G, NR = CG + 1, ND = NR * NR;
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    const int ix = int(e % g.nx), iy = int(e / g.nx);
+    double loc[ND];
+    for (int r = 0; r < NR; ++r)
+        for (int c = 0; c < NR; ++c)
+            loc[r * NR + c] = cg[size_t(CG * iy + r) * g.cgs + CG * ix + c];
+    double crn[4][2], dx[2][Q], dy[2][Q], J[Q], lat[Q], gq[Q];
+    elementCorners(vx, vy, g.nx, ix, iy, g.spherical, crn);
+    elementMap<G>(crn, dx, dy, J, lat);
+    for (int q = 0; q < Q; ++q) {
+        double s = 0;
+        for (int i = 0; i < ND; ++i)
+            s += PHI(CG, G, i, q) * loc[i];
+        double wj = J[q] * gaussweight2(G, q);
+        if (g.spherical)
+            wj *= cos(lat[q]);
+        gq[q] = wj * s;
+    }
+    double rhs[DG];
+    for (int j = 0; j < DG; ++j) {
+        double s = 0;
+        for (int q = 0; q < Q; ++q)
+            s += PSI(G, j, q) * gq[q];
+        rhs[j] = s;
+    }
+    const size_t eo = e * op.estride;
+    for (int i = 0; i < DG; ++i) {
+        double s = 0;
+        for (int j = 0; j < DG; ++j)
+            s += op.iMass[(i * DG + j) * op.pitch + eo] * rhs[j];
+        dg[size_t(i) * g.Npad + e] = g.spherical ? s * EarthRadius : s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DG -> CG nodal averaging (per node gather over <= 4 elements, reference order: odd element
+// rows first, quirk Q7; weights 1/4 corner, 1/2 edge, 1 centre; domain-boundary nodes x2).
+// Optional clamp [lo,hi] fuses prepareIteration's limits (CGDynamicsKernel.cpp:272-275).
+// ------------------------------------------------------------------------------------------
+template <int CG, int DG>
+__global__ void dg2cg_kernel(GridDims g, const double* __restrict__ src, double* __restrict__ dest, double lo, double hi)
+{
+    constexpr int L = CG + 1;
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const int c = int(t % g.cgnx), r = int(t / g.cgnx);
+    // elements touching the node: columns exA..exB, rows eyA..eyB, with local node index
+    const int jx = c % CG, jy = r % CG;
+    int exs[2], lxs[2], nxs = 0, eys[2], lys[2], nys = 0;
+    if (jx == 0 && c > 0) {
+        exs[nxs] = c / CG - 1;
+        lxs[nxs++] = CG;
+    }
+    if (c < CG * g.nx) {
+        exs[nxs] = c / CG;
+        lxs[nxs++] = jx;
+    }
+    if (jy == 0 && r > 0) {
+        eys[nys] = r / CG - 1;
+        lys[nys++] = CG;
+    }
+    if (r < CG * g.ny) {
+        eys[nys] = r / CG;
+        lys[nys++] = jy;
+    }
+    double sum = 0.0;
+    for (int pass = 0; pass < 2; ++pass) // pass 0: odd element rows, pass 1: even rows
+        for (int a = 0; a < nys; ++a) {
+            if ((eys[a] % 2 == 1) != (pass == 0))
+                continue;
+            for (int b = 0; b < nxs; ++b) {
+                const size_t e = size_t(eys[a]) * g.nx + exs[b];
+                const int q = lys[a] * L + lxs[b];
+                double At = 0;
+                for (int j = 0; j < DG; ++j)
+                    At += src[size_t(j) * g.Npad + e] * PSILag(L, j, q);
+                double wt = 1.0;
+                if (CG == 1)
+                    wt = 0.25;
+                else
+                    wt = ((lxs[b] == 1) ? 1.0 : 0.5) * ((lys[a] == 1) ? 1.0 : 0.5);
+                sum += wt * At;
+            }
+        }
+    // DG2CGBoundary, Interpolations.cpp:165-180: rows first, then columns (corners x4)
+    if (r == 0 || r == g.cgny - 1)
+        sum *= 2.0;
+    if (c == 0 || c == g.cgnx - 1)
+        sum *= 2.0;
+    sum = fmin(fmax(sum, lo), hi);
+    dest[size_t(r) * g.cgs + c] = sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// Normal velocity on the edges (per edge gather).  X-edges: nx*(ny+1), Y-edges: (nx+1)*ny.
+// dirmask: per element, bit s = element has a Dirichlet edge on side s.
+// Output planes: nvX[k*pitchX + edge], nvY[k*pitchY + edge].
+// ------------------------------------------------------------------------------------------
+template <int DG>
+__global__ void normalvel_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
+    const uint8_t* __restrict__ landmask, const uint8_t* __restrict__ dirmask, const double* __restrict__ velx,
+    const double* __restrict__ vely, double* __restrict__ nvX, size_t pitchX, double* __restrict__ nvY, size_t pitchY)
+{
+    constexpr int ED = edgedofs(DG);
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long nXe = long(g.nx) * (g.ny + 1), nYe = long(g.nx + 1) * g.ny;
+    if (t >= nXe + nYe)
+        return;
+    auto tangent = [&](size_t n1, size_t n2, double& tx, double& ty) { // ParametricMesh.hpp:381-397
+        tx = vx[n2] - vx[n1];
+        ty = vy[n2] - vy[n1];
+        if (g.spherical) {
+            if (tx > 0.5 * M_PI)
+                tx -= 2.0 * M_PI;
+            if (tx < -0.5 * M_PI)
+                tx += 2.0 * M_PI;
+        }
+    };
+    double acc[ED];
+    for (int k = 0; k < ED; ++k)
+        acc[k] = 0.0;
+    bool twice = false;
+    if (t < nXe) { // X-edge (ix, jy): between element rows jy-1 (below) and jy (above)
+        const int ix = int(t % g.nx), jy = int(t / g.nx);
+        double tx, ty;
+        const size_t n = size_t(jy) * (g.nx + 1) + ix;
+        tangent(n, n + 1, tx, ty);
+        for (int side = 0; side < 2; ++side) { // 0: element below (its top edge), 1: element above (its bottom edge)
+            const int ey = jy - 1 + side;
+            if (ey < 0 || ey >= g.ny)
+                continue;
+            const size_t e = size_t(ey) * g.nx + ix;
+            if (!isIce(landmask, e))
+                continue;
+            double ex[ED], eyv[ED];
+            edgeofcell<DG>([&](int k) { return velx[size_t(k) * g.Npad + e]; }, side == 0 ? 2 : 0, ex);
+            edgeofcell<DG>([&](int k) { return vely[size_t(k) * g.Npad + e]; }, side == 0 ? 2 : 0, eyv);
+            for (int k = 0; k < ED; ++k)
+                acc[k] += 0.5 * (-ty * ex[k] + tx * eyv[k]);
+            twice = twice || (dirmask[e] & (side == 0 ? 4 : 1));
+        }
+        for (int k = 0; k < ED; ++k)
+            nvX[size_t(k) * pitchX + t] = twice ? acc[k] * 2.0 : acc[k];
+    } else { // Y-edge (jx, iy): between element columns jx-1 (left) and jx (right)
+        const long ty_ = t - nXe;
+        const int jx = int(ty_ % (g.nx + 1)), iy = int(ty_ / (g.nx + 1));
+        double tx, ty;
+        const size_t n = size_t(iy) * (g.nx + 1) + jx;
+        tangent(n, n + g.nx + 1, tx, ty);
+        for (int side = 0; side < 2; ++side) { // 0: element on the left (its right edge), 1: on the right (its left edge)
+            const int ex_ = jx - 1 + side;
+            if (ex_ < 0 || ex_ >= g.nx)
+                continue;
+            const size_t e = size_t(iy) * g.nx + ex_;
+            if (!isIce(landmask, e))
+                continue;
+            double ex[ED], eyv[ED];
+            edgeofcell<DG>([&](int k) { return velx[size_t(k) * g.Npad + e]; }, side == 0 ? 1 : 3, ex);
+            edgeofcell<DG>([&](int k) { return vely[size_t(k) * g.Npad + e]; }, side == 0 ? 1 : 3, eyv);
+            for (int k = 0; k < ED; ++k)
+                acc[k] += 0.5 * (ty * ex[k] - tx * eyv[k]);
+            twice = twice || (dirmask[e] & (side == 0 ? 2 : 8));
+        }
+        for (int k = 0; k < ED; ++k)
+            nvY[size_t(k) * pitchY + ty_] = twice ? acc[k] * 2.0 : acc[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// The transport operator: phiup = M^-1 [ dt * cell term - dt * sum over edges of upwind flux ]
+// ------------------------------------------------------------------------------------------
+template <int DG>
+__global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, const uint8_t* __restrict__ landmask,
+    const uint8_t* __restrict__ dirmask, const double* __restrict__ velx, const double* __restrict__ vely,
+    const double* __restrict__ nvX, size_t pitchX, const double* __restrict__ nvY, size_t pitchY, TransportOpPtrs op,
+    const double* __restrict__ phi, double* __restrict__ phiup)
+{
+    constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    const int ix = int(e % g.nx), iy = int(e / g.nx);
+    const size_t Npad = g.Npad;
+    const bool ice = isIce(landmask, e);
+    double up[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        up[j] = 0.0;
+    double ph[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        ph[j] = phi[size_t(j) * Npad + e];
+
+    const size_t eo = e * op.estride;
+    // ---- cell term (DGTransport.cpp:278-303) ----
+    if (DG > 1 && ice) {
+        double vxg[Q], vyg[Q], pg[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            vxg[q] = vyg[q] = pg[q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            const double a = velx[size_t(j) * Npad + e], b = vely[size_t(j) * Npad + e];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double w = PSI(G, j, q);
+                if (w != 0.0) {
+                    vxg[q] = fma(a, w, vxg[q]);
+                    vyg[q] = fma(b, w, vyg[q]);
+                    pg[q] = fma(ph[j], w, pg[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            double s = 0;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double ax = __ldg(op.AdvX + (j * Q + q) * op.pitch + eo);
+                const double ay = __ldg(op.AdvY + (j * Q + q) * op.pitch + eo);
+                s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
+            }
+            up[j] += s;
+        }
+    }
+    // ---- interior edges (DGTransport.cpp:390-433) ----
+    // side: 0 bottom, 1 right, 2 top, 3 left.  Order of the reference accumulation: left, right, bottom, top.
+    auto edgeFlux = [&](int side) {
+        const int nix = ix + (side == 1 ? 1 : (side == 3 ? -1 : 0));
+        const int niy = iy + (side == 2 ? 1 : (side == 0 ? -1 : 0));
+        if (nix < 0 || nix >= g.nx || niy < 0 || niy >= g.ny)
+            return;
+        const size_t en = size_t(niy) * g.nx + nix;
+        if (!ice || !isIce(landmask, en))
+            return;
+        // c1 = left/bottom element, c2 = right/top element of the edge
+        const bool meFirst = (side == 1 || side == 2);
+        double nv[ED];
+        if (side == 0 || side == 2) {
+            const size_t ie = size_t(side == 2 ? iy + 1 : iy) * g.nx + ix;
+            for (int k = 0; k < ED; ++k)
+                nv[k] = nvX[size_t(k) * pitchX + ie];
+        } else {
+            const size_t ie = size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix);
+            for (int k = 0; k < ED; ++k)
+                nv[k] = nvY[size_t(k) * pitchY + ie];
+        }
+        double tme[ED], tnb[ED];
+        edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
+        edgeofcell<DG>([&](int k) { return phi[size_t(k) * Npad + en]; }, (side + 2) & 3, tnb);
+        double tmp[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            double vg = 0, g1 = 0, g2 = 0;
+#pragma unroll
+            for (int k = 0; k < ED; ++k) {
+                vg += nv[k] * PSIe(G, k, q);
+                g1 += (meFirst ? tme[k] : tnb[k]) * PSIe(G, k, q);
+                g2 += (meFirst ? tnb[k] : tme[k]) * PSIe(G, k, q);
+            }
+            tmp[q] = fmax(vg, 0.) * g1 + fmin(vg, 0.) * g2;
+        }
+        const double sdt = meFirst ? -dt : dt;
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            double s = 0;
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                s += (sdt * tmp[q]) * PSIew(G, side, q, j);
+            up[j] += s;
+        }
+    };
+    edgeFlux(3);
+    edgeFlux(1);
+    edgeFlux(0);
+    edgeFlux(2);
+    // ---- Dirichlet edges: outflow only (DGTransport.cpp:306-351), sides in list order 0,1,2,3 ----
+    const uint8_t dm = dirmask[e];
+    if (dm)
+        for (int side = 0; side < 4; ++side) {
+            if (!(dm & (1 << side)))
+                continue;
+            double nv[ED];
+            if (side == 0 || side == 2) {
+                const size_t ie = size_t(side == 2 ? iy + 1 : iy) * g.nx + ix;
+                for (int k = 0; k < ED; ++k)
+                    nv[k] = nvX[size_t(k) * pitchX + ie];
+            } else {
+                const size_t ie = size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix);
+                for (int k = 0; k < ED; ++k)
+                    nv[k] = nvY[size_t(k) * pitchY + ie];
+            }
+            double tme[ED];
+            edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
+            const double sg = (side == 0 || side == 3) ? -1.0 : 1.0;
+            double tmp[G];
+            for (int q = 0; q < G; ++q) {
+                double vg = 0, g1 = 0;
+                for (int k = 0; k < ED; ++k) {
+                    vg += nv[k] * PSIe(G, k, q);
+                    g1 += tme[k] * PSIe(G, k, q);
+                }
+                tmp[q] = g1 * fmax(sg * vg, 0.);
+            }
+            for (int j = 0; j < DG; ++j) {
+                double s = 0;
+                for (int q = 0; q < G; ++q) {
+                    const double w = side == 0 ? PSIew(G, 0, q, j)
+                        : side == 1            ? PSIew(G, 1, q, j)
+                        : side == 2            ? PSIew(G, 2, q, j)
+                                               : PSIew(G, 3, q, j);
+                    s += (-dt * tmp[q]) * w;
+                }
+                up[j] += s;
+            }
+        }
+    // ---- inverse mass (DGTransport.cpp:509-511) ----
+#pragma unroll
+    for (int i = 0; i < DG; ++i) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < DG; ++j)
+            s += __ldg(op.iMass + (i * DG + j) * op.pitch + eo) * up[j];
+        phiup[size_t(i) * Npad + e] = s;
+    }
+}
+
+//! y += x        (step_rk2: phi += tmp1)
+__global__ void add_kernel(size_t n, double* __restrict__ y, const double* __restrict__ x)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        y[i] += x[i];
+}
+//! y += 0.5*(b - a)  (step_rk2: phi += 0.5*(tmp2 - tmp1))
+__global__ void heun_kernel(size_t n, double* __restrict__ y, const double* __restrict__ b, const double* __restrict__ a)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        y[i] += 0.5 * (b[i] - a[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Limiters (dgLimit.hpp:16-84).  mode bits: 1 = LimitMax(maxv) then 2 = LimitMin(minv), in this
+// order (the reference always calls LimitMax before LimitMin on the same field).
+// ------------------------------------------------------------------------------------------
+template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ f, int mode, double maxv, double minv)
+{
+    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= size_t(g.N))
+        return;
+    double d[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        d[j] = f[size_t(j) * g.Npad + e];
+    if (mode & 1) {
+        d[0] = fmin(maxv, d[0]);
+        if constexpr (DG == 3) {
+            const double l0 = 2.0 * fmax(fabs(d[1] + d[2]), fabs(d[1] - d[2]));
+            if (l0 != 0 && d[0] + l0 - maxv > 0) {
+                const double a = d[1] * ((maxv - d[0]) / l0), b = d[2] * ((maxv - d[0]) / l0);
+                d[1] = a;
+                d[2] = b;
+            }
+        } else if constexpr (DG == 6) {
+            double mx = -1e300;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                double v = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    v += d[j] * PSI(3, j, q);
+                mx = fmax(mx, v);
+            }
+            const double l0 = mx - d[0];
+            if (mx > maxv) {
+                const double s = (maxv - d[0]) / l0;
+#pragma unroll
+                for (int j = 1; j < 6; ++j)
+                    d[j] *= s;
+            }
+        }
+    }
+    if (mode & 2) {
+        d[0] = fmax(minv, d[0]);
+        if constexpr (DG == 3) {
+            const double l0 = 2.0 * fmax(fabs(d[1] + d[2]), fabs(d[1] - d[2]));
+            if (l0 != 0 && d[0] - l0 - minv < 0) {
+                const double a = d[1] * ((d[0] - minv) / l0), b = d[2] * ((d[0] - minv) / l0);
+                d[1] = a;
+                d[2] = b;
+            }
+        } else if constexpr (DG == 6) {
+            double mn = 1e300;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                double v = 0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    v += d[j] * PSI(3, j, q);
+                mn = fmin(mn, v);
+            }
+            const double l0 = mn - d[0];
+            if (mn < minv) {
+                const double s = (d[0] - minv) / l0;
+#pragma unroll
+                for (int j = 1; j < 6; ++j)
+                    d[j] *= s;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        f[size_t(j) * g.Npad + e] = d[j];
+}
+
+} // namespace nsdg

@@ -269,6 +269,8 @@ public:
     virtual Vec* rawMutable(const std::string& name) = 0;
     virtual const Mesh& mesh() const = 0;
     virtual void subcycle() = 0;
+    virtual void sweep(const std::string& which) = 0;
+    virtual void setDeltaT(double) = 0;
     size_t nSteps = 100; //!< DynamicsKernel.hpp:187 (hard-coded 100 in the reference, quirk Q5)
     Params params;
     double subcycleSeconds = 0; //!< wall time spent in the subcycle loop of the last update()
@@ -796,6 +798,28 @@ public:
             updateMomentumBrittle();
         dirichletZero(u); // applyBoundaries, CGDynamicsKernel.cpp:439-444
         dirichletZero(v);
+    }
+
+    void setDeltaT(double d) override { deltaT = d; }
+
+    //! a single sweep of the subcycle (or prepareIteration), for the analytic tests
+    void sweep(const std::string& which) override
+    {
+        if (which == "strain")
+            projectVelocityToStrain();
+        else if (which == "stress")
+            rheology == MEVP ? stressUpdateMEVP() : stressUpdateBBM();
+        else if (which == "divergence")
+            stressDivergence();
+        else if (which == "momentum")
+            rheology == MEVP ? updateMomentumVP() : updateMomentumBrittle();
+        else if (which == "boundaries") {
+            dirichletZero(u);
+            dirichletZero(v);
+        } else if (which == "prepare")
+            prepareIteration();
+        else
+            throw std::runtime_error("unknown sweep " + which);
     }
 
     //! VPCGDynamicsKernel.hpp:63-94 / BrittleCGDynamicsKernel.hpp:91-136

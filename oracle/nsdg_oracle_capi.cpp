@@ -87,6 +87,13 @@ double nso_subcycles(void* h, int n)
         d->subcycle();
     return omp_get_wtime() - t0;
 }
+int nso_sweep(void* h, const char* which)
+{
+    NSO_TRY static_cast<IDynOracle*>(h)->sweep(which);
+    return 0;
+    NSO_CATCH
+}
+int nso_set_delta_t(void* h, double deltaT);
 double nso_last_subcycle_seconds(void* h) { return static_cast<IDynOracle*>(h)->subcycleSeconds; }
 int nso_get_dg0(void* h, const char* name, double* out)
 {
@@ -145,6 +152,12 @@ int nso_set_param(void* h, const char* name, double value)
         lastError = "unknown parameter " + n;
         return -1;
     }
+    return 0;
+}
+
+int nso_set_delta_t(void* h, double deltaT)
+{
+    static_cast<IDynOracle*>(h)->setDeltaT(deltaT);
     return 0;
 }
 

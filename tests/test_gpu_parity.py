@@ -1,0 +1,283 @@
+"""GPU parity: libnsdg_cuda.so (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (FP64): integer state bit-exact; operators and single sweeps <= 1e-12; a full timestep
+(advection + 100 subcycles) <= 1e-10, all measured norm-wise, max|gpu - ref| / max|ref| over the field,
+as BASELINE.json's north_star states ("about 1e-10 per step and bounded drift over N steps").
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_SWEEP = 1e-12
+TOL_STEP = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    assert a.shape == b.shape
+    assert np.isfinite(a).all(), "GPU result has non-finite values"
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def pair(rheo, ms, nsteps=100, dgadv=6, cg=2, **kw):
+    import oracle
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics
+
+    gpu = (CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics)(dgadv=dgadv, cgdegree=cg, nsteps=nsteps, **kw)
+    ref = oracle.OracleDynamics(rheo, dgadv, cg, nsteps)
+    gpu.setData(ms)
+    ref.setData(ms)
+    return gpu, ref
+
+
+def run_steps(gpu, ref, ms, forcings, dt):
+    sh = {"hice": np.ascontiguousarray(np.asarray(ms["hice"]).reshape(gpu.ny, gpu.nx, -1)[..., 0]),
+          "cice": np.ascontiguousarray(np.asarray(ms["cice"]).reshape(gpu.ny, gpu.nx, -1)[..., 0])}
+    for d in (gpu, ref):
+        d.shared = {k: v.copy() for k, v in sh.items()}
+    for f in forcings:
+        for d in (gpu, ref):
+            d.shared.update({k: v.copy() for k, v in f.items()})
+            d.update(dt)
+
+
+def cases():
+    from nextsimdg_b200 import synthetic
+
+    return {
+        "box32": (synthetic.benchmark_box(32), [synthetic.benchmark_forcing(32, 0.0)], 120.0),
+        "para_distorted_land": (synthetic.para_state(30, 24, distort=0.05, irregular_mask=True),
+                                [synthetic.smooth_forcing(30, 24)], 900.0),
+        "para_uniform_land": (synthetic.para_state(37, 21, irregular_mask=True), [synthetic.smooth_forcing(37, 21)], 900.0),
+        "spherical": (synthetic.topaz_like_spherical(32), [synthetic.smooth_forcing(32, 32)], 600.0),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def test_mesh_lists_bit_exact_against_reference_fixture():
+    """dynamics/test/ParametricMesh_test.cpp:89-131 through the C ABI."""
+    from nextsimdg_b200 import CUDAMEVPDynamics
+    from test_oracle_mesh import golden_mesh
+
+    nx, ny, coords, mask, lists = golden_mesh()
+    z = np.zeros((ny, nx))
+    gpu = CUDAMEVPDynamics(nsteps=1)
+    gpu.setData({"coords": coords, "mask": mask, "x": z, "y": z, "hice": z, "cice": z, "u": z, "v": z})
+    assert np.array_equal(gpu.landmask(), mask.ravel().astype(np.uint8))
+    for e in range(4):
+        assert np.array_equal(gpu.dirichlet(e), lists[e])
+
+
+@pytest.mark.parametrize("case", ["box32", "para_distorted_land", "spherical"])
+def test_operators_match_oracle(case):
+    ms, _, _ = cases()[case]
+    gpu, ref = pair("bbm", ms, nsteps=1)
+    names = ["lumpedcgmass", "lumpedcg1mass", "divS1", "divS2", "iMgradX", "iMgradY", "iMJwPSI", "iMJwPSI_dam", "dX_SSH",
+             "dY_SSH", "AdvX", "AdvY", "iMass"]
+    if case == "spherical":
+        names += ["divM", "iMM"]
+    for n in names:
+        assert rel(gpu.internal(n), ref.internal(n)) < TOL_SWEEP, n
+    for e in range(4):
+        assert np.array_equal(gpu.dirichlet(e), ref.dirichlet(e))
+    assert np.array_equal(gpu.landmask(), ref.landmask())
+
+
+@pytest.mark.parametrize("case", ["box32", "para_distorted_land", "spherical"])
+def test_setdata_and_prepare_match_oracle(case):
+    """setData (ma2dg + DG2CG), prepareIteration (DG2CG + clamps + SSH gradient)."""
+    ms, forcings, dt = cases()[case]
+    gpu, ref = pair("mevp", ms, nsteps=1)
+    run_steps(gpu, ref, ms, forcings, dt)
+    for n in ("uAtmos", "vAtmos", "uOcean", "vOcean", "cgH", "cgA"):
+        assert rel(gpu.internal(n), ref.internal(n)) < 1e-13, n
+    scale = max(np.abs(ref.internal("uGradSSH")).max(), np.abs(ref.internal("vGradSSH")).max(), 1e-300)
+    for n in ("uGradSSH", "vGradSSH"):
+        assert np.abs(gpu.internal(n) - ref.internal(n)).max() / scale < TOL_SWEEP, n
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+@pytest.mark.parametrize("case", ["box32", "para_distorted_land", "para_uniform_land", "spherical"])
+def test_single_subcycle(rheo, case):
+    """One timestep with nSteps = 1: advection + prepare + exactly one pass of the five sweeps."""
+    ms, forcings, dt = cases()[case]
+    gpu, ref = pair(rheo, ms, nsteps=1)
+    run_steps(gpu, ref, ms, forcings, dt)
+    ice = ref.landmask().astype(bool)
+    for n in ("s11", "s12", "s22"):
+        g, r = gpu.internal(n).reshape(ice.size, -1), ref.internal(n).reshape(ice.size, -1)
+        assert rel(g[ice], r[ice]) < TOL_SWEEP, n
+    for n in ("cg_u", "cg_v"):
+        assert rel(gpu.internal(n), ref.internal(n)) < TOL_SWEEP, n
+    for n in ("hice", "cice") + (("damage",) if rheo == "bbm" else ()):
+        g, r = gpu.internal(n).reshape(ice.size, -1), ref.internal(n).reshape(ice.size, -1)
+        assert rel(g[ice], r[ice]) < TOL_SWEEP, n
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+@pytest.mark.parametrize("case", ["box32", "para_distorted_land", "para_uniform_land", "spherical"])
+def test_full_timestep(rheo, case):
+    """IDynamics::update with the reference's 100 subcycles, outputs as the module exports them."""
+    ms, forcings, dt = cases()[case]
+    gpu, ref = pair(rheo, ms, nsteps=100)
+    run_steps(gpu, ref, ms, forcings, dt)
+    ice = ms["mask"].astype(bool)
+    for n, g, r in (("uice", gpu.uice, ref.uice), ("vice", gpu.vice, ref.vice), ("taux", gpu.taux, ref.taux),
+                    ("tauy", gpu.tauy, ref.tauy), ("hice", gpu.shared["hice"], ref.shared["hice"]),
+                    ("cice", gpu.shared["cice"], ref.shared["cice"])):
+        assert rel(g[ice], r[ice]) < TOL_STEP, n
+    if rheo == "bbm":
+        assert rel(gpu.damage[ice], ref.damage[ice]) < TOL_STEP
+    for n in ("s11", "s12", "s22"):
+        g, r = gpu.internal(n).reshape(ice.size, -1), ref.internal(n).reshape(ice.size, -1)
+        assert rel(g[ice.ravel()], r[ice.ravel()]) < 1e-8, n  # stress is ill-conditioned in rigid ice (P/Delta)
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_dg1_cg1_build(rheo):
+    """The reference's alternative compile-time build DGCOMP=3 / CGDEGREE=1 (CMakeLists.txt:112-118)."""
+    from nextsimdg_b200 import synthetic
+
+    ms = synthetic.para_state(30, 24, distort=0.05, irregular_mask=True)
+    ms["hice"] = np.ascontiguousarray(ms["hice"][..., :3])
+    ms["cice"] = np.ascontiguousarray(ms["cice"][..., :3])
+    gpu, ref = pair(rheo, ms, nsteps=100, dgadv=3, cg=1)
+    run_steps(gpu, ref, ms, [synthetic.smooth_forcing(30, 24)], 900.0)
+    ice = ms["mask"].astype(bool)
+    for n, g, r in (("uice", gpu.uice, ref.uice), ("vice", gpu.vice, ref.vice), ("hice", gpu.shared["hice"], ref.shared["hice"])):
+        assert rel(g[ice], r[ice]) < TOL_STEP, n
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_drift_over_steps(rheo):
+    """Bounded drift: 5 consecutive timesteps of the cyclone box with moving forcing."""
+    from nextsimdg_b200 import synthetic
+
+    n, dt = 64, 120.0
+    ms = synthetic.benchmark_box(n)
+    gpu, ref = pair(rheo, ms, nsteps=100)
+    sh = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
+    for d in (gpu, ref):
+        d.shared = {k: v.copy() for k, v in sh.items()}
+    errs = []
+    for k in range(5):
+        f = synthetic.benchmark_forcing(n, k * dt)
+        for d in (gpu, ref):
+            d.shared.update({a: b.copy() for a, b in f.items()})
+            d.update(dt)
+        errs.append(max(rel(gpu.uice, ref.uice), rel(gpu.vice, ref.vice), rel(gpu.shared["hice"], ref.shared["hice"])))
+    print("drift", rheo, errs)
+    assert max(errs) < 10 * TOL_STEP
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_uniform_fast_path_equals_general_path(rheo):
+    """(vii) on a rectangular mesh the shared-operator path and the per-element-operator path agree."""
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, synthetic
+
+    n, dt = 48, 120.0
+    ms = synthetic.benchmark_box(n)
+    f = synthetic.benchmark_forcing(n, 0.0)
+    out = []
+    for force_general in (False, True):
+        d = (CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics)(nsteps=100, force_general=force_general)
+        d.setData(ms)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{a: b.copy() for a, b in f.items()}}
+        d.update(dt)
+        assert d.timing().uniform_path == (0 if force_general else 1)
+        out.append((d.uice.copy(), d.vice.copy(), d.internal("s11")))
+    assert rel(out[0][0], out[1][0]) < TOL_STEP and rel(out[0][1], out[1][1]) < TOL_STEP
+    assert rel(out[0][2], out[1][2]) < 1e-8
+
+
+def test_cuda_graph_and_plain_launches_identical():
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, dt = 40, 120.0
+    ms = synthetic.benchmark_box(n)
+    f = synthetic.benchmark_forcing(n, 0.0)
+    res = []
+    for graph in (True, False):
+        d = CUDAMEVPDynamics(nsteps=50, use_cuda_graph=graph)
+        d.setData(ms)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{a: b.copy() for a, b in f.items()}}
+        d.update(dt)
+        d.update(dt)
+        res.append((d.uice.copy(), d.internal("s12")))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("shape", [(33, 17), (64, 16), (65, 35), (2, 2), (31, 50)])
+def test_ragged_sizes(shape):
+    """Strip logic at sizes that are not multiples of the 32 x R strip (and the minimum 2 x 2 mesh)."""
+    from nextsimdg_b200 import synthetic
+
+    nx, ny = shape
+    ms = synthetic.para_state(nx, ny, distort=0.03 if min(nx, ny) > 2 else 0.0, irregular_mask=min(nx, ny) > 8)
+    gpu, ref = pair("mevp", ms, nsteps=7)
+    run_steps(gpu, ref, ms, [synthetic.smooth_forcing(nx, ny)], 600.0)
+    assert rel(gpu.internal("cg_u"), ref.internal("cg_u")) < 1e-11
+    assert rel(gpu.internal("cg_v"), ref.internal("cg_v")) < 1e-11
+
+
+def test_error_behaviour():
+    from nextsimdg_b200 import CUDAMEVPDynamics, NsdgError, synthetic
+
+    d = CUDAMEVPDynamics(nsteps=1)
+    ms = synthetic.benchmark_box(8)
+    bad = dict(ms)
+    del bad["x"]
+    with pytest.raises(RuntimeError):  # IDynamics::checkSpherical, IDynamics.hpp:107-120
+        d.setData(bad)
+    bad = dict(ms)
+    del bad["coords"]
+    with pytest.raises(KeyError):  # ms.at(coordsName) -> std::out_of_range
+        d.setData(bad)
+    with pytest.raises(NsdgError):  # update before setData
+        d.step(120.0)
+    d.setData(ms)
+    with pytest.raises(NsdgError):
+        d._set("hice", np.zeros((8, 8, 4)))  # neither 1 nor DGCOMP components
+
+
+def test_locality_and_determinism_at_full_size():
+    """BASELINE size (2048 x 2048, mEVP, uniform path): (a) two runs are bitwise identical;
+    (b) information travels one element per subcycle, so after k subcycles a window far from the crop
+    edge equals the same window computed on a small cropped domain -- checked against the ORACLE run on
+    the crop, which ties the full-size run to the oracle without running the oracle at full size."""
+    import oracle
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, crop, k, dt = 2048, 96, 6, 120.0
+    L = 250.0 * n
+    ms = synthetic.benchmark_box(n, L=L, ring_mask=False)
+    f = synthetic.benchmark_forcing(n, 0.0, L=L)
+    runs = []
+    for _ in range(2):
+        d = CUDAMEVPDynamics(nsteps=k)
+        d.setData(ms)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{a: b.copy() for a, b in f.items()}}
+        d.update(dt)
+        runs.append((d.uice.copy(), d.vice.copy()))
+        d.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    # crop window [j0:j0+crop, i0:i0+crop] of the big domain, translated to the origin
+    i0, j0 = 1000, 700
+    sl = (slice(j0, j0 + crop), slice(i0, i0 + crop))
+    msc = {"coords": np.ascontiguousarray(ms["coords"][j0:j0 + crop + 1, i0:i0 + crop + 1] - ms["coords"][j0, i0]),
+           "mask": np.ones((crop, crop)), "x": np.zeros((crop, crop)), "y": np.zeros((crop, crop)),
+           "hice": np.ascontiguousarray(ms["hice"][sl]), "cice": np.ascontiguousarray(ms["cice"][sl]),
+           "u": np.zeros((crop, crop)), "v": np.zeros((crop, crop))}
+    ref = oracle.OracleDynamics("mevp", 6, 2, k)
+    ref.setData(msc)
+    ref.shared = {"hice": msc["hice"].copy(), "cice": msc["cice"].copy(), **{a: np.ascontiguousarray(b[sl]) for a, b in f.items()}}
+    ref.update(dt)
+    m = k + 6  # margin in elements: k subcycles + advection/DG2CG stencils
+    inner = (slice(m, crop - m), slice(m, crop - m))
+    big_u = runs[0][0][sl][inner]
+    big_v = runs[0][1][sl][inner]
+    assert rel(big_u, ref.uice[inner]) < TOL_STEP
+    assert rel(big_v, ref.vice[inner]) < TOL_STEP
