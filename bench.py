@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the dynamics hot path on N B200s, one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--rheology mevp|bbm] [--n 2048]
+
+metric  : dynamics element-subcycle updates/s (FP64)  (BASELINE.json)
+step    : one IDynamics::update (advection + limiters + prepareIteration + 100 subcycles) on the
+          synthetic 2048 x 2048 DG2/CG2 rectangular grid (BASELINE.json configs[4]); per GPU for N > 1
+          (weak scaling, 2-D boxes with NVLink halo exchange).
+value   : N_elements * nSteps * K / (device time of K steps), inputs resident in HBM.
+e2e     : same metric through the module-level call nsdg_update with HOST buffers: every step uploads
+          the 7 input HFields and downloads the 6 output HFields inside the timed region.
+roofline: the subcycle kernel pair (strip + lines) of one subcycle against the measured HBM peak.
+cpu_baseline / --impl reference: the CPU oracle port (the reference itself needs Eigen 3.4, absent here)
+          timed on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dynamics element-subcycle updates/s (FP64)"
+UNIT = "element-subcycles/s"
+DT = 120.0  # run/config_benchmark.cfg:5
+NSTEPS = 100  # DynamicsKernel.hpp:187
+# algorithmic bytes per element-subcycle, SURVEY.md 8(d) / BASELINE.md 3
+B_ALG = {("mevp", True): 960, ("mevp", False): 3840, ("bbm", True): 1120, ("bbm", False): 4432}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # the samples under load are the upper half
+            out = {"sm_mhz": statistics.median(top), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def make_inputs(n: int, rheo: str):
+    from nextsimdg_b200 import synthetic
+
+    # 4 km cells: with the reference's hard-coded alpha = beta = 1500 and dt = 120 s the mEVP iteration
+    # amplifies rounding noise ~100x per subcycle below ~2 km cells, so results there are
+    # not reproducible by ANY implementation; the arithmetic per element is the same at every cell size.
+    L = 4000.0 * n
+    ms = synthetic.benchmark_box(n, L=L)
+    forcing = synthetic.benchmark_forcing(n, 0.0, L=L)
+    return ms, forcing
+
+
+def cpu_oracle_run(n: int, rheo: str, nsteps: int, steps: int, warmup: int):
+    """Times the CPU oracle port (all host threads) on an n x n sample of the workload."""
+    import oracle
+
+    L = oracle.load()
+    cores = os.cpu_count() or 1
+    L.nso_set_threads(cores)
+    ms, forcing = make_inputs(n, rheo)
+    o = oracle.OracleDynamics(rheo, 6, 2, nsteps)
+    o.setData(ms)
+    o.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{k: v.copy() for k, v in forcing.items()}}
+    for _ in range(warmup):
+        o.update(DT)
+    t0 = time.perf_counter()
+    sub = 0.0
+    for _ in range(steps):
+        o.update(DT)
+        sub += o.last_subcycle_seconds()
+    el = time.perf_counter() - t0
+    units = float(n) * n * nsteps * steps
+    return {"value": units / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{rheo} {n}x{n} DG2/CG2 benchmark box, {steps} update(s) of {nsteps} subcycles through the module-level "
+                      f"update (setData + advection + subcycles + getDG0Data), OpenMP on {cores} threads; the reference "
+                      "itself cannot be built here (needs Eigen 3.4)",
+            "subcycle_loop_only": units / max(sub, 1e-12), "seconds": el}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path = the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n
+    t0 = time.perf_counter()
+    r = cpu_oracle_run(n, args.rheology, NSTEPS, args.steps, args.warmup)
+    ms_per_step = r["seconds"] / args.steps * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_grid": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
+                   "note": "each step is a bounded sample (smaller grid) of the workload; throughput per element-subcycle is size-independent on the CPU"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return f"{args.rheology}_rect{args.n}x{args.n}_dg2cg2_nsteps{NSTEPS}"
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+
+        torch.cuda.set_device(local_rank)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_
+
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, capi
+    from nextsimdg_b200 import partition as part
+
+    n, rheo = args.n, args.rheology
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    if world == 1:
+        ms, forcing = make_inputs(n, rheo)
+        dyn = cls(nsteps=NSTEPS, device=local_rank, pin_host_buffers=True)
+        dyn.setData(ms)
+    else:
+        dyn, ms, forcing = part.make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=NSTEPS,
+                                                      make_inputs=make_inputs)
+    N_owned = dyn.owned_elements() if hasattr(dyn, "owned_elements") else n * n
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ----
+    dyn.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{k: v.copy() for k, v in forcing.items()}}
+    dyn.update(DT)  # uploads every input once; state is resident from here on
+    for _ in range(args.warmup):
+        dyn.step(DT)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    dev_ms, adv_ms, prep_ms, sub_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dyn.step(DT)
+        t = dyn.timing()
+        dev_ms += t.total_ms
+        adv_ms += t.advection_ms
+        prep_ms += t.prepare_ms
+        sub_ms += t.subcycle_ms
+        launches += t.kernel_launches
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    units = float(N_owned) * NSTEPS * args.steps * world
+    value = units / (dev_ms * 1e-3)
+    uniform = bool(dyn.timing().uniform_path)
+
+    # ---- roofline of the subcycle kernel pair, timed live with CUDA events on the launching stream ----
+    strip_ms = ctypes.c_float()
+    lines_ms = ctypes.c_float()
+    capi.check(dyn._lib.nsdg_time_kernels(dyn._h, 20, ctypes.byref(strip_ms), ctypes.byref(lines_ms)))
+    peak, peak_src = peaks()
+    b_alg = B_ALG[(rheo, uniform)]
+    local_elems = dyn.nx * dyn.ny
+    pair_ms = strip_ms.value + lines_ms.value
+    achieved = b_alg * local_elems / (pair_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
+                "lines_ms": lines_ms.value, "alg_bytes_per_element_subcycle": b_alg, "peak_source": peak_src}
+
+    # ---- end-to-end arm: host buffers in, host buffers out, every step ----
+    for _ in range(min(args.warmup, 2)):
+        dyn.update(DT)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        dyn.update(DT)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = float(N_owned) * NSTEPS * args.e2e_steps * world / e2e_s
+    nin = 8 if rheo == "bbm" else 7
+    nout = 7 if rheo == "bbm" else 6
+    field_bytes = dyn.nx * dyn.ny * 8
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_oracle_run(args.cpu_n, rheo, args.cpu_nsteps, 1, 0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "subcycle_loop_only")}
+    ms_per_step = dev_ms / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "grid_per_gpu": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
+                   "operators": "uniform rectangular (shared, __constant__)" if uniform else "per-element (streamed)",
+                   "l2": "working set (~3 GB) is larger than the 126 MB L2; no flush needed",
+                   "parallelism": "single domain" if world == 1 else f"2-D boxes x{world}, NVLink halo exchange"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nin * field_bytes, "d2h_bytes_per_step": nout * field_bytes,
+                "steps": args.e2e_steps, "ms_per_step": e2e_s / args.e2e_steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "phases_ms_per_step": {"advection": adv_ms / args.steps, "prepare": prep_ms / args.steps, "subcycles": sub_ms / args.steps},
+        "subcycle_loop_only": float(N_owned) * NSTEPS * args.steps * world / (sub_ms * 1e-3),
+        "model_days_per_wall_hour": 3600.0 / (ms_per_step * 1e-3 * (86400.0 / DT)),
+        "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rheology", default="mevp", choices=["mevp", "bbm"])
+    ap.add_argument("--n", type=int, default=2048, help="grid size per GPU (elements per side)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-n", type=int, default=512, help="grid size of the bounded CPU baseline sample")
+    ap.add_argument("--cpu-nsteps", type=int, default=100)
+    ap.add_argument("--ref-n", type=int, default=512, help="grid size of the --impl reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

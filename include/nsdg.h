@@ -145,6 +145,10 @@ int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_
  * throughput metric counts.  Returns device milliseconds of the loop through *ms (CUDA events). */
 int nsdg_subcycles(nsdg_handle h, int n, float* ms);
 
+/* Average device time of the two kernels of one subcycle (subcycle_strip, subcycle_lines) over n
+ * subcycles, each launch bracketed by CUDA events on the handle's stream (state advances by n subcycles). */
+int nsdg_time_kernels(nsdg_handle h, int n, float* strip_ms, float* lines_ms);
+
 /* Timing of the last nsdg_step, measured with CUDA events on the handle's stream. */
 typedef struct nsdg_timing {
     float advection_ms, prepare_ms, subcycle_ms, total_ms;

@@ -19,6 +19,7 @@
 #include <utility>
 
 #include "nsdg_momentum.cuh"
+#include "nsdg_momentum_uniform.cuh"
 #include "nsdg_prepare.cuh"
 
 namespace nsdg {
@@ -38,6 +39,7 @@ public:
     virtual void step(double dt) = 0;
     virtual void update(const nsdg_update_io* io, double dt) = 0;
     virtual void subcycles(int n, float* ms) = 0;
+    virtual void timeKernels(int n, float* stripMs, float* linesMs) = 0;
     virtual void getInternal(const std::string& name, double* host, size_t cap, size_t* count) = 0;
     virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
     nsdg_config cfg {};
@@ -80,6 +82,8 @@ public:
     DevBuf<double> u, v, u0, v0, cgH, cgA, gradX, gradY, uO, vO, uA, vA, lmass, avgU, avgV, taux, tauy;
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
+    DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
+    bool fastUniformMEVP = false;
     // staging
     DevBuf<double> staging;
     std::vector<std::pair<const void*, size_t>> registered;
@@ -311,6 +315,10 @@ public:
         nsy = (ny + R - 1) / R;
         hbuf.alloc(size_t(nsy) * 2 * nx * NR * 2);
         vbuf.alloc(size_t(nsx) * 2 * ny * NR * 2);
+        fastUniformMEVP = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6;
+        if (fastUniformMEVP)
+            for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
+                f->alloc(ncg);
         timing.uniform_path = uniform ? 1 : 0;
         meshSet = true;
     }
@@ -562,6 +570,56 @@ public:
         return a;
     }
 
+    UniformArgs makeUniformArgs(double deltaT) const
+    {
+        UniformArgs a {};
+        a.g = g;
+        a.R = R;
+        a.nsx = nsx;
+        a.nsy = nsy;
+        a.s11 = s11;
+        a.s12 = s12;
+        a.s22 = s22;
+        a.Pa = gaussA;
+        a.landmask = d_landmask;
+        a.u = u;
+        a.v = v;
+        a.c1 = ncC1;
+        a.cA = ncCA;
+        a.rx = ncRx;
+        a.ry = ncRy;
+        a.uO = uO;
+        a.vO = vO;
+        a.ilm = ncIlm;
+        a.nodemask = d_nodemask;
+        a.hbuf = hbuf;
+        a.vbuf = vbuf;
+        a.dx = hvx[1] - hvx[0];
+        a.dy = hvy[g.nx + 1] - hvy[0];
+        a.keep = 1.0 - 1.0 / p.alpha;
+        a.beta = p.beta;
+        a.dtfc = deltaT * p.fc;
+        a.DeltaMin2 = p.DeltaMin * p.DeltaMin;
+        return a;
+    }
+    void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
+    {
+        if constexpr (CG == 2 && DGA == 6)
+            subcycle_strip_umevp<0><<<nbStrip, 128, 0, stream>>>(ua);
+    }
+    void launchLinesFast(const UniformArgs& ua, size_t nLine)
+    {
+        subcycle_lines_umevp<<<blocksFor(nLine), 128, 0, stream>>>(ua);
+    }
+    template <int RHEO> void launchStrip(const SubcycleArgs& a, unsigned nbStrip)
+    {
+        if (uniform)
+            subcycle_strip<CG, DGA, RHEO, true, false><<<nbStrip, 128, 0, stream>>>(a);
+        else if (g.spherical)
+            subcycle_strip<CG, DGA, RHEO, false, true><<<nbStrip, 128, 0, stream>>>(a);
+        else
+            subcycle_strip<CG, DGA, RHEO, false, false><<<nbStrip, 128, 0, stream>>>(a);
+    }
     template <int RHEO> void launchSubcycle(const SubcycleArgs& a)
     {
         const unsigned nwarps = unsigned(nsx) * nsy;
@@ -579,9 +637,15 @@ public:
     void runSubcycles(int n, double deltaT)
     {
         const SubcycleArgs a = makeArgs(deltaT);
+        const UniformArgs ua = makeUniformArgs(deltaT);
+        const unsigned nbStripF = (unsigned(nsx) * nsy + 3) / 4;
+        const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
         auto body = [&]() {
             for (int i = 0; i < n; ++i) {
-                if (cfg.rheology == NSDG_BBM)
+                if (fastUniformMEVP) {
+                    launchStripFast(ua, nbStripF);
+                    launchLinesFast(ua, nLineF);
+                } else if (cfg.rheology == NSDG_BBM)
                     launchSubcycle<NSDG_BBM>(a);
                 else
                     launchSubcycle<NSDG_MEVP>(a);
@@ -629,6 +693,42 @@ public:
 
     double lastDeltaT = 1.0;
 
+    //! per-kernel timing: events around every launch of the two subcycle kernels
+    void timeKernels(int n, float* stripMs, float* linesMs) override
+    {
+        requireMesh();
+        const SubcycleArgs a = makeArgs(lastDeltaT);
+        const UniformArgs ua = makeUniformArgs(lastDeltaT);
+        const unsigned nwarps = unsigned(nsx) * nsy, nbStrip = (nwarps + 3) / 4;
+        const size_t nLine = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
+        double ts = 0, tl = 0;
+        for (int i = 0; i < n; ++i) {
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+            if (fastUniformMEVP)
+                launchStripFast(ua, nbStrip);
+            else if (cfg.rheology == NSDG_BBM)
+                launchStrip<NSDG_BBM>(a, nbStrip);
+            else
+                launchStrip<NSDG_MEVP>(a, nbStrip);
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+            if (fastUniformMEVP)
+                launchLinesFast(ua, nLine);
+            else if (cfg.rheology == NSDG_BBM)
+                subcycle_lines<CG, NSDG_BBM><<<blocksFor(nLine), 128, 0, stream>>>(a);
+            else
+                subcycle_lines<CG, NSDG_MEVP><<<blocksFor(nLine), 128, 0, stream>>>(a);
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+            NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+            float x = 0, y = 0;
+            NSDG_CUDA_CHECK(cudaEventElapsedTime(&x, ev[0], ev[1]));
+            NSDG_CUDA_CHECK(cudaEventElapsedTime(&y, ev[1], ev[2]));
+            ts += x;
+            tl += y;
+        }
+        *stripMs = float(ts / n);
+        *linesMs = float(tl / n);
+    }
+
     // ------------------------------------------------------------------------------------
     // one timestep
     // ------------------------------------------------------------------------------------
@@ -661,12 +761,18 @@ public:
             NSDG_CUDA_CHECK(cudaMemcpyAsync(u0, u, cgBytes, cudaMemcpyDeviceToDevice, stream));
             NSDG_CUDA_CHECK(cudaMemcpyAsync(v0, v, cgBytes, cudaMemcpyDeviceToDevice, stream));
             deltaT = dt;
-            gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB);
+            gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(
+                g, p, hice, cice, gaussA, gaussB, fastUniformMEVP ? 1.0 / p.alpha : 1.0);
+            if (fastUniformMEVP) {
+                nodeconst_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
+                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
+                launches += 1;
+            }
         } else { // BrittleCGDynamicsKernel.hpp:110-114
             deltaT = dt / double(cfg.nsteps);
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgU, 0, cgBytes, stream));
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgV, 0, cgBytes, stream));
-            gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB);
+            gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, 1.0);
         }
         launches += 1;
         lastDeltaT = deltaT;
@@ -966,6 +1072,14 @@ int nsdg_subcycles(nsdg_handle h, int n, float* ms)
 {
     NSDG_TRY
     H(h)->subcycles(n, ms);
+    NSDG_CATCH
+}
+int nsdg_time_kernels(nsdg_handle h, int n, float* strip_ms, float* lines_ms)
+{
+    NSDG_TRY
+    if (n < 1 || !strip_ms || !lines_ms)
+        throw std::runtime_error("nsdg_time_kernels: bad arguments");
+    H(h)->timeKernels(n, strip_ms, lines_ms);
     NSDG_CATCH
 }
 int nsdg_get_timing(nsdg_handle h, nsdg_timing* t)

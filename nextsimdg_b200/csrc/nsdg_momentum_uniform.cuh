@@ -1,0 +1,449 @@
+/*
+ * nsdg_momentum_uniform.cuh -- the mEVP subcycle on a UNIFORM RECTANGULAR mesh (CG2 / DG8), the
+ * configuration of BASELINE.json's headline metric, restructured around what is special there:
+ *
+ *  - all elements share one operator set, and on a rectangle dx x dy it factorises:
+ *      iMgradX = (1/dx) Gx^, iMgradY = (1/dy) Gy^, iMJwPSI = B^ (mesh independent),
+ *      divS1 = dy D1^, divS2 = dx D2^          (^ = unit-square matrices, compile-time constants)
+ *    so the matrices live in the instruction stream as immediates and their structural zeros
+ *    (32 of 72 entries in D1^/D2^, 17 of 72 in B^) cost nothing;
+ *  - d(u,v)/d(x,y) of the Q2 velocity lies in the DG8 space (that is what DG8 = "grad Q2" is for),
+ *    so the L2 projection of projectVelocityToStrain followed by the Gauss-point evaluation of
+ *    stressUpdateHighOrder equals evaluating the velocity gradient directly in the 9 Gauss points
+ *    (two 1-d contractions); the 3 x 8 strain coefficients are never formed;
+ *  - everything in updateMomentum that does not change during the subcycles is folded into
+ *    seven per-node constants once per timestep (nodeconst_kernel), which removes 4 of 13 node
+ *    reads and 3 of 4 divisions per node and subcycle.
+ *
+ * Same sweeps and same results up to rounding (re-association only; tests/test_gpu_parity.py):
+ *   projectVelocityToStrain  dynamics/src/CGDynamicsKernel.cpp:300-337
+ *   stressUpdateHighOrder    dynamics/src/include/MEVPStressUpdateStep.hpp:30-118
+ *   stressDivergence         dynamics/src/CGDynamicsKernel.cpp:340-398
+ *   updateMomentum           dynamics/src/include/VPCGDynamicsKernel.hpp:132-172 (quirks Q1, Q2 kept)
+ *   applyBoundaries          dynamics/src/CGDynamicsKernel.cpp:439-444
+ * The warp-strip / register-carry / deferred-line organisation is that of nsdg_momentum.cuh.
+ */
+#pragma once
+#include "nsdg_momentum.cuh"
+
+#include <utility>
+
+namespace nsdg {
+
+//! compile-time loop: f(std::integral_constant<int, 0>) ... f(<N-1>)
+template <int N, typename F> __device__ __forceinline__ void static_for(F&& f)
+{
+    [&]<int... I>(std::integer_sequence<int, I...>) { (f(std::integral_constant<int, I> {}), ...); }(
+        std::make_integer_sequence<int, N> {});
+}
+
+//! unit-square operator tables of the CG2 / DG8 pair, evaluated at compile time
+struct UnitOps {
+    double L[3][3], Lp[3][3]; //!< Q2 1-d basis / derivative, [j][q] at the 3 Gauss points
+    double B[8][9]; //!< psi_j(q) w_q / m_j           (= iMJwPSI on any rectangle)
+    double D1[9][8], D2[9][8]; //!< int phi_i,xi psi_j ; int phi_i,eta psi_j (= divS1/dy, divS2/dx)
+    constexpr UnitOps()
+        : L {}
+        , Lp {}
+        , B {}
+        , D1 {}
+        , D2 {}
+    {
+        const double minv[8] = { 1., 12., 12., 180., 180., 144., 2160., 2160. }; // 1 / int psi_j^2
+        for (int j = 0; j < 3; ++j)
+            for (int q = 0; q < 3; ++q) {
+                L[j][q] = cgbasis1d(2, j, gausspoint(3, q));
+                Lp[j][q] = cgbasis1d_dx(2, j, gausspoint(3, q));
+            }
+        for (int j = 0; j < 8; ++j)
+            for (int q = 0; q < 9; ++q)
+                B[j][q] = clean(PSI(3, j, q) * gaussweight2(3, q) * minv[j]);
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 8; ++j) {
+                double a = 0, b = 0;
+                for (int q = 0; q < 9; ++q) {
+                    a += gaussweight2(3, q) * PHIx(2, 3, i, q) * PSI(3, j, q);
+                    b += gaussweight2(3, q) * PHIy(2, 3, i, q) * PSI(3, j, q);
+                }
+                D1[i][j] = clean(a);
+                D2[i][j] = clean(b);
+            }
+    }
+    //! entries that are zero in exact arithmetic come out as O(1e-17) from the quadrature sums
+    static constexpr double clean(double x) { return (x < 1e-13 && x > -1e-13) ? 0.0 : x; }
+};
+inline constexpr UnitOps kUnitOps {};
+
+//! arguments of the uniform mEVP kernels
+struct UniformArgs {
+    GridDims g;
+    int R, nsx, nsy;
+    double *s11, *s12, *s22; //!< DG8 planes
+    const double* Pa; //!< Gauss-point planes of P/alpha, P = P* h exp(-20(1-a))
+    const uint8_t* landmask;
+    double *u, *v;
+    const double *c1, *cA, *rx, *ry, *uO, *vO, *ilm; //!< per-node constants (nodeconst_kernel)
+    const uint8_t* nodemask;
+    double *hbuf, *vbuf;
+    double dx, dy; //!< element size
+    double keep; //!< 1 - 1/alpha
+    double beta, dtfc; //!< beta ; deltaT * fc
+    double DeltaMin2;
+};
+
+/*
+ * Per-node constants of VPCGDynamicsKernel::updateMomentum (VPCGDynamicsKernel.hpp:147-170):
+ *   c1  = rho_ice cgH / deltaT
+ *   cA  = cgA F_ocean
+ *   rx  = c1 u0 + cgA F_atm |ua| ua - rho_ice cgH g dSSH/dx          (ry alike)
+ *   ilm = 1 / lumpedcgmass
+ * so that   u_new = ( c1 beta u + rx + cA |du_ocn| uO - c1 dt fc u + dStressX ilm ) / ( c1 (1+beta) + cA |du_ocn| ).
+ */
+__global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
+    const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
+    const double* __restrict__ gy, const double* __restrict__ u0, const double* __restrict__ v0, const double* __restrict__ lm,
+    double* __restrict__ c1, double* __restrict__ cA, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ ilm)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
+    const double H = cgH[n], A = cgA[n];
+    const double k1 = p.rho_ice * H / deltaT;
+    const double absatm = sqrt(uA[n] * uA[n] + vA[n] * vA[n]);
+    c1[n] = k1;
+    cA[n] = A * p.F_ocean;
+    rx[n] = k1 * u0[n] + A * (p.F_atm * absatm * uA[n]) - p.rho_ice * H * p.gravity * gx[n];
+    ry[n] = k1 * v0[n] + A * (p.F_atm * absatm * vA[n]) - p.rho_ice * H * p.gravity * gy[n];
+    ilm[n] = 1.0 / lm[n];
+}
+
+//! mEVP momentum update of one node from the per-node constants (+ Dirichlet)
+__device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double c1, double cA, double rx, double ry, double uO,
+    double vO, double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew)
+{
+    const double uOcnRel = uO - un;
+    const double vOcnRel = vn - vO;
+    const double absocn = sqrt(uOcnRel * uOcnRel + vOcnRel * vOcnRel);
+    const double drag = cA * absocn;
+    const double inv = 1.0 / (c1 * (1.0 + a.beta) + drag);
+    const double cf = c1 * a.dtfc;
+    unew = inv * (c1 * (a.beta * un) + rx + drag * uO - cf * un + dSx * ilm);
+    vnew = inv * (c1 * (a.beta * vn) + ry + drag * vO + cf * vn + dSy * ilm);
+    if (dirichlet) {
+        unew = 0.0;
+        vnew = 0.0;
+    }
+}
+
+template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_strip_umevp(const __grid_constant__ UniformArgs a)
+{
+    constexpr int CG = 2, NR = 3, DGs = 8;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
+        return;
+    const GridDims& g = a.g;
+    const int sx = w % a.nsx, sy = w / a.nsx;
+    const int exRaw = 32 * sx + lane;
+    const bool active = exRaw < g.nx;
+    const int ex = active ? exRaw : g.nx - 1;
+    const bool lastLane = active && (lane == 31 || exRaw == g.nx - 1);
+    const bool loadsRight = (lane == 31) || (exRaw >= g.nx - 1);
+    const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
+    const size_t Npad = g.Npad;
+    const int col0 = CG * ex;
+    const double idx = 1.0 / a.dx, idy = 1.0 / a.dy;
+
+    auto loadRow = [&](const double* f, int r, double* out) {
+        const double* ptr = f + size_t(r) * g.cgs + col0;
+        const double2 t = *reinterpret_cast<const double2*>(ptr);
+        out[0] = t.x;
+        out[1] = t.y;
+        double right = __shfl_down_sync(FULL, t.x, 1);
+        if (loadsRight)
+            right = ptr[CG];
+        out[2] = right;
+    };
+
+    double carryX[2] = { 0.0, 0.0 }, carryY[2] = { 0.0, 0.0 };
+    double ul[9], vl[9];
+    loadRow(a.u, CG * ey0, ul);
+    loadRow(a.v, CG * ey0, vl);
+
+    for (int ey = ey0; ey < ey1; ++ey) {
+        const size_t e = size_t(ey) * g.nx + ex;
+        loadRow(a.u, CG * ey + 1, ul + 3);
+        loadRow(a.v, CG * ey + 1, vl + 3);
+        loadRow(a.u, CG * ey + 2, ul + 6);
+        loadRow(a.v, CG * ey + 2, vl + 6);
+        const bool ice = active && (__ldg(a.landmask + e) != 0);
+
+        // ---- velocity gradient in the 9 Gauss points by two 1-d contractions ----
+        double e11[9], e12[9], e22[9];
+        {
+            double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3]; // [jy][qx]
+            static_for<3>([&](auto JY) {
+                static_for<3>([&](auto QX) {
+                    constexpr int jy = decltype(JY)::value, qx = decltype(QX)::value;
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    static_for<3>([&](auto JX) {
+                        constexpr int jx = decltype(JX)::value;
+                        constexpr double l = kUnitOps.L[jx][qx], lp = kUnitOps.Lp[jx][qx];
+                        if constexpr (l != 0.0) {
+                            s0 = fma(l, ul[jy * 3 + jx], s0);
+                            s2 = fma(l, vl[jy * 3 + jx], s2);
+                        }
+                        if constexpr (lp != 0.0) {
+                            s1 = fma(lp, ul[jy * 3 + jx], s1);
+                            s3 = fma(lp, vl[jy * 3 + jx], s3);
+                        }
+                    });
+                    Au[jy][qx] = s0;
+                    Adu[jy][qx] = s1;
+                    Av[jy][qx] = s2;
+                    Adv[jy][qx] = s3;
+                });
+            });
+            static_for<3>([&](auto QY) {
+                static_for<3>([&](auto QX) {
+                    constexpr int qy = decltype(QY)::value, qx = decltype(QX)::value, q = qy * 3 + qx;
+                    double ux = 0, uy = 0, vx = 0, vy = 0;
+                    static_for<3>([&](auto JY) {
+                        constexpr int jy = decltype(JY)::value;
+                        constexpr double l = kUnitOps.L[jy][qy], lp = kUnitOps.Lp[jy][qy];
+                        if constexpr (l != 0.0) {
+                            ux = fma(l, Adu[jy][qx], ux);
+                            vx = fma(l, Adv[jy][qx], vx);
+                        }
+                        if constexpr (lp != 0.0) {
+                            uy = fma(lp, Au[jy][qx], uy);
+                            vy = fma(lp, Av[jy][qx], vy);
+                        }
+                    });
+                    // land elements keep zero strain (quirk Q8)
+                    e11[q] = ice ? ux * idx : 0.0;
+                    e22[q] = ice ? vy * idy : 0.0;
+                    e12[q] = ice ? 0.5 * (uy * idy + vx * idx) : 0.0;
+                });
+            });
+        }
+
+        // ---- VP law in the Gauss points: e** become the integrands r** (MEVPStressUpdateStep.hpp:62-117) ----
+        static_for<9>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            const double Pa = __ldg(a.Pa + size_t(q) * Npad + e);
+            const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+            const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+            const double pd = 0.125 * Pa * iD;
+            e11[q] = fma(pd, 5.0 * g11 + 3.0 * g22, -0.5 * Pa);
+            e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);
+            e12[q] = 2.0 * pd * g12;
+        });
+
+        // ---- per stress component: project, relax, store, accumulate the divergence contributions ----
+        double Tx[9], Ty[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            Tx[k] = Ty[k] = 0.0;
+        auto component = [&](double* plane, const double (&r)[9], auto COMP) {
+            constexpr int comp = decltype(COMP)::value; // 0: s11, 1: s12, 2: s22
+            double s[DGs];
+            static_for<DGs>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                double acc = 0.0;
+                static_for<9>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    constexpr double b = kUnitOps.B[j][q];
+                    if constexpr (b != 0.0)
+                        acc = fma(b, r[q], acc);
+                });
+                s[j] = fma(plane[size_t(j) * Npad + e], a.keep, acc);
+                if (active)
+                    plane[size_t(j) * Npad + e] = s[j];
+            });
+            if (ice) {
+                static_for<9>([&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    double d1 = 0.0, d2 = 0.0;
+                    static_for<DGs>([&](auto J) {
+                        constexpr int j = decltype(J)::value;
+                        constexpr double c1 = kUnitOps.D1[k][j], c2 = kUnitOps.D2[k][j];
+                        if constexpr (c1 != 0.0 && comp != 2)
+                            d1 = fma(c1, s[j], d1);
+                        if constexpr (c2 != 0.0 && comp != 0)
+                            d2 = fma(c2, s[j], d2);
+                    });
+                    // tx = divS1 s11 + divS2 s12 ; ty = divS1 s12 + divS2 s22
+                    if constexpr (comp == 0)
+                        Tx[k] = fma(d1, a.dy, Tx[k]);
+                    if constexpr (comp == 1) {
+                        Tx[k] = fma(d2, a.dx, Tx[k]);
+                        Ty[k] = fma(d1, a.dy, Ty[k]);
+                    }
+                    if constexpr (comp == 2)
+                        Ty[k] = fma(d2, a.dx, Ty[k]);
+                });
+            }
+        };
+        component(a.s11, e11, std::integral_constant<int, 0> {});
+        component(a.s12, e12, std::integral_constant<int, 1> {});
+        component(a.s22, e22, std::integral_constant<int, 2> {});
+
+        // ---- raw contributions to the deferred lines ----
+        if (active && lane == 0 && sx > 0) {
+            double* vb = a.vbuf + ((size_t(sx - 1) * 2 + 1) * g.ny + ey) * (NR * 2);
+#pragma unroll
+            for (int jy = 0; jy < NR; ++jy) {
+                vb[jy * 2 + 0] = Tx[jy * NR];
+                vb[jy * 2 + 1] = Ty[jy * NR];
+            }
+        }
+        if (lastLane) {
+            double* vb = a.vbuf + ((size_t(sx) * 2 + 0) * g.ny + ey) * (NR * 2);
+#pragma unroll
+            for (int jy = 0; jy < NR; ++jy) {
+                vb[jy * 2 + 0] = Tx[jy * NR + CG];
+                vb[jy * 2 + 1] = Ty[jy * NR + CG];
+            }
+        }
+        const bool bottomDeferred = (ey == ey0) && (sy > 0);
+        if (active && bottomDeferred) {
+            double* hb = a.hbuf + ((size_t(sy - 1) * 2 + 1) * g.nx + ex) * (NR * 2);
+#pragma unroll
+            for (int jx = 0; jx < NR; ++jx) {
+                hb[jx * 2 + 0] = Tx[jx];
+                hb[jx * 2 + 1] = Ty[jx];
+            }
+        }
+        if (active && ey == ey1 - 1) {
+            double* hb = a.hbuf + ((size_t(sy) * 2 + 0) * g.nx + ex) * (NR * 2);
+#pragma unroll
+            for (int jx = 0; jx < NR; ++jx) {
+                hb[jx * 2 + 0] = Tx[CG * NR + jx];
+                hb[jx * 2 + 1] = Ty[CG * NR + jx];
+            }
+        }
+        // ---- left neighbour's right column by shuffle ----
+#pragma unroll
+        for (int jy = 0; jy < NR; ++jy) {
+            const double lx = __shfl_up_sync(FULL, Tx[jy * NR + CG], 1);
+            const double ly = __shfl_up_sync(FULL, Ty[jy * NR + CG], 1);
+            if (lane > 0) {
+                Tx[jy * NR] = lx + Tx[jy * NR];
+                Ty[jy * NR] = ly + Ty[jy * NR];
+            }
+        }
+        // ---- momentum update of the completed nodes (rows 2ey, 2ey+1; columns 2ex, 2ex+1) ----
+#pragma unroll
+        for (int jy = 0; jy < CG; ++jy) {
+            const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+            const double2 c1 = __ldg(reinterpret_cast<const double2*>(a.c1 + n0));
+            const double2 cA = __ldg(reinterpret_cast<const double2*>(a.cA + n0));
+            const double2 rx = __ldg(reinterpret_cast<const double2*>(a.rx + n0));
+            const double2 ry = __ldg(reinterpret_cast<const double2*>(a.ry + n0));
+            const double2 uO = __ldg(reinterpret_cast<const double2*>(a.uO + n0));
+            const double2 vO = __ldg(reinterpret_cast<const double2*>(a.vO + n0));
+            const double2 ilm = __ldg(reinterpret_cast<const double2*>(a.ilm + n0));
+            const uchar2 msk = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + n0));
+            double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
+            if (jy == 0) {
+                sx0 += carryX[0];
+                sy0 += carryY[0];
+                sx1 += carryX[1];
+                sy1 += carryY[1];
+            }
+            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            double2 un, vn;
+            momentumNodeUniform(a, c1.x, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+                d0 ? 0.0 : -sy0, un.x, vn.x);
+            momentumNodeUniform(a, c1.y, cA.y, rx.y, ry.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+                d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y);
+            const bool rowSkip = !active || (jy == 0 && bottomDeferred);
+            const bool skip0 = rowSkip || (lane == 0 && sx > 0);
+            if (!rowSkip) {
+                if (!skip0) {
+                    *reinterpret_cast<double2*>(a.u + n0) = un;
+                    *reinterpret_cast<double2*>(a.v + n0) = vn;
+                } else {
+                    a.u[n0 + 1] = un.y;
+                    a.v[n0 + 1] = vn.y;
+                }
+            }
+        }
+        carryX[0] = Tx[CG * NR];
+        carryX[1] = Tx[CG * NR + 1];
+        carryY[0] = Ty[CG * NR];
+        carryY[1] = Ty[CG * NR + 1];
+#pragma unroll
+        for (int jx = 0; jx < NR; ++jx) {
+            ul[jx] = ul[CG * NR + jx];
+            vl[jx] = vl[CG * NR + jx];
+        }
+    }
+}
+
+//! deferred-line nodes for the uniform mEVP path (see subcycle_lines in nsdg_momentum.cuh)
+__global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constant__ UniformArgs a)
+{
+    constexpr int CG = 2, NR = 3;
+    const GridDims& g = a.g;
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long nH = long(a.nsy) * g.cgnx;
+    const long nV = long(a.nsx) * g.cgny;
+    if (t >= nH + nV)
+        return;
+    int c, r;
+    double sumX = 0.0, sumY = 0.0;
+    if (t < nH) {
+        const int L = int(t / g.cgnx) + 1;
+        c = int(t % g.cgnx);
+        r = min(CG * a.R * L, CG * g.ny);
+        const int jx = c % CG, exr = c / CG;
+        const bool above = r < CG * g.ny;
+        auto add = [&](int side, int ex, int j) {
+            const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
+            sumX += hb[0];
+            sumY += hb[1];
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !above)
+                break;
+            if (jx == 0 && exr > 0)
+                add(side, exr - 1, CG);
+            if (exr < g.nx)
+                add(side, exr, jx);
+        }
+    } else {
+        const long tv = t - nH;
+        const int L = int(tv / g.cgny) + 1;
+        r = int(tv % g.cgny);
+        c = min(CG * 32 * L, CG * g.nx);
+        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
+            return;
+        const int jy = r % CG, eyr = r / CG;
+        const bool right = c < CG * g.nx;
+        auto add = [&](int side, int ey, int j) {
+            const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
+            sumX += vb[0];
+            sumY += vb[1];
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !right)
+                break;
+            if (jy == 0 && eyr > 0)
+                add(side, eyr - 1, CG);
+            add(side, eyr, jy);
+        }
+    }
+    const size_t n = size_t(r) * g.cgs + c;
+    const bool d = __ldg(a.nodemask + n) & 1;
+    double un, vn;
+    momentumNodeUniform(a, __ldg(a.c1 + n), __ldg(a.cA + n), __ldg(a.rx + n), __ldg(a.ry + n), __ldg(a.uO + n), __ldg(a.vO + n),
+        __ldg(a.ilm + n), d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
+    a.u[n] = un;
+    a.v[n] = vn;
+}
+
+} // namespace nsdg

@@ -203,7 +203,7 @@ __global__ void sshgrad_cg_kernel(GridDims g, int cg1s, const double* __restrict
 //! per-step Gauss-point constants of the stress update
 template <int DGA, int GS, int RHEO>
 __global__ void gaussconst_kernel(GridDims g, PhysParams p, const double* __restrict__ hice, const double* __restrict__ cice,
-    double* __restrict__ outA, double* __restrict__ outB)
+    double* __restrict__ outA, double* __restrict__ outB, double scaleA)
 {
     constexpr int Q = GS * GS;
     const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -229,7 +229,7 @@ __global__ void gaussconst_kernel(GridDims g, PhysParams p, const double* __rest
         hq = fmax(hq, 0.0);
         aq = fmin(fmax(aq, 0.0), 1.0);
         if constexpr (RHEO == NSDG_MEVP) {
-            outA[size_t(q) * g.Npad + e] = p.Pstar * hq * exp(-20.0 * (1.0 - aq));
+            outA[size_t(q) * g.Npad + e] = scaleA * (p.Pstar * hq * exp(-20.0 * (1.0 - aq)));
         } else {
             outA[size_t(q) * g.Npad + e] = hq;
             outB[size_t(q) * g.Npad + e] = exp(p.compaction_param * (1.0 - aq));

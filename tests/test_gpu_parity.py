@@ -122,9 +122,14 @@ def test_single_subcycle(rheo, case):
 def test_full_timestep(rheo, case):
     """IDynamics::update with the reference's 100 subcycles, outputs as the module exports them."""
     ms, forcings, dt = cases()[case]
-    gpu, ref = pair(rheo, ms, nsteps=100)
+    # BBM on a spherical mesh: the reference's damage time scale td uses smesh.h(i) in MESH units
+    # (radians), BBMStressUpdateStep.hpp:158, so dt/td ~ 1e5 and the reference itself blows up to NaN
+    # within a few subcycles whatever the forcing.  Parity there is checked while it is still finite.
+    nsteps = 2 if (rheo, case) == ("bbm", "spherical") else 100
+    gpu, ref = pair(rheo, ms, nsteps=nsteps)
     run_steps(gpu, ref, ms, forcings, dt)
     ice = ms["mask"].astype(bool)
+    assert np.isfinite(ref.uice[ice]).all(), "oracle went non-finite: the test case is not meaningful"
     for n, g, r in (("uice", gpu.uice, ref.uice), ("vice", gpu.vice, ref.vice), ("taux", gpu.taux, ref.taux),
                     ("tauy", gpu.tauy, ref.tauy), ("hice", gpu.shared["hice"], ref.shared["hice"]),
                     ("cice", gpu.shared["cice"], ref.shared["cice"])):
@@ -251,8 +256,8 @@ def test_locality_and_determinism_at_full_size():
     import oracle
     from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
 
-    n, crop, k, dt = 2048, 96, 6, 120.0
-    L = 250.0 * n
+    n, crop, k, dt = 2048, 96, 12, 120.0
+    L = 4000.0 * n  # stable mEVP regime (>= 2 km cells for alpha = beta = 1500, dt = 120 s)
     ms = synthetic.benchmark_box(n, L=L, ring_mask=False)
     f = synthetic.benchmark_forcing(n, 0.0, L=L)
     runs = []
