@@ -14,6 +14,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <utility>
@@ -191,7 +192,12 @@ public:
         g.nx = nx;
         g.ny = ny;
         g.N = nx * ny;
-        g.Npad = int(alignUp(size_t(g.N), 32));
+        // Plane pitch: a multiple of 32 elements (256 B), skewed by 8 KiB + 256 B so that the 33+ planes a
+        // warp streams never sit a power-of-two apart (2048^2 * 8 B = 32 MiB exactly would alias every plane
+        // onto the same L2 sets and DRAM banks).
+        g.Npad = int(alignUp(size_t(g.N), 32)) + (g.N >= 4096 ? 1056 : 0);
+        if (const char* env = std::getenv("NSDG_PLANE_SKEW")) // tuning knob (elements, multiple of 32)
+            g.Npad = int(alignUp(size_t(g.N), 32)) + std::atoi(env);
         g.CG = CG;
         g.cgnx = CG * nx + 1;
         g.cgny = CG * ny + 1;
@@ -311,14 +317,20 @@ public:
 
         // ---- strips and deferred-line buffers ----
         R = 16;
+        if (const char* env = std::getenv("NSDG_STRIP_ROWS")) // tuning knob: element rows per warp strip
+            R = std::max(1, std::atoi(env));
         nsx = (nx + 31) / 32;
         nsy = (ny + R - 1) / R;
         hbuf.alloc(size_t(nsy) * 2 * nx * NR * 2);
         vbuf.alloc(size_t(nsx) * 2 * ny * NR * 2);
         fastUniformMEVP = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6;
-        if (fastUniformMEVP)
+        if (fastUniformMEVP) {
             for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
+            if constexpr (CG == 2 && DGA == 6)
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_umevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmevpSmemBytes)));
+        }
         timing.uniform_path = uniform ? 1 : 0;
         meshSet = true;
     }
@@ -605,7 +617,7 @@ public:
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
         if constexpr (CG == 2 && DGA == 6)
-            subcycle_strip_umevp<0><<<nbStrip, 128, 0, stream>>>(ua);
+            subcycle_strip_umevp<0><<<nbStrip, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
     }
     void launchLinesFast(const UniformArgs& ua, size_t nLine)
     {

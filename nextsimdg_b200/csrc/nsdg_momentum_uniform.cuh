@@ -74,6 +74,9 @@ struct UnitOps {
 };
 inline constexpr UnitOps kUnitOps {};
 
+//! pull the line holding `p` into L2 (no register, no scoreboard): used one element row ahead
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 //! arguments of the uniform mEVP kernels
 struct UniformArgs {
     GridDims g;
@@ -136,14 +139,54 @@ __device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double
     }
 }
 
-template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_strip_umevp(const __grid_constant__ UniformArgs a)
+// ---- cp.async (LDGSTS): global -> shared without passing through registers ----
+__device__ __forceinline__ void cpAsync8(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/*
+ * Per-warp staging buffer in shared memory.  Every lane copies (cp.async) and later reads ONLY its own
+ * slots, so no cross-lane synchronisation is needed: shared memory acts as an asynchronous extension
+ * of the register file that is filled one element row ahead of use, region by region:
+ *   P   9 x 32 doubles      Gauss-point P/alpha of the row          refilled right after the VP law
+ *   S  24 x 32 doubles      the three DG8 stresses of the row       refilled after the projection
+ *   ND  2 x 7 x 32 double2  the seven node constants, 2 node rows   refilled after the momentum update
+ *   UV  2 x 2 x 32 double2  u, v of the two upper node rows         refilled at the top of the row
+ * Four groups are always in flight; cp.async groups retire in order, so "wait_group 3" before each
+ * region's first read is exactly "the group issued one row ago has landed".
+ */
+struct UmevpStage {
+    double P[9][32];
+    double S[24][32];
+    double2 ND[2][7][32];
+    double2 UV[2][2][32];
+    double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
+    double pad[2];
+};
+constexpr int kUmevpWarps = 4;
+constexpr size_t kUmevpSmemBytes = sizeof(UmevpStage) * kUmevpWarps;
+
+#ifndef NSDG_UMEVP_MINBLOCKS
+#define NSDG_UMEVP_MINBLOCKS 3
+#endif
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcycle_strip_umevp(const __grid_constant__ UniformArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8;
     constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
         return;
+    UmevpStage& st = reinterpret_cast<UmevpStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
     const int exRaw = 32 * sx + lane;
@@ -156,29 +199,104 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
     const int col0 = CG * ex;
     const double idx = 1.0 / a.dx, idy = 1.0 / a.dy;
 
-    auto loadRow = [&](const double* f, int r, double* out) {
-        const double* ptr = f + size_t(r) * g.cgs + col0;
-        const double2 t = *reinterpret_cast<const double2*>(ptr);
-        out[0] = t.x;
-        out[1] = t.y;
-        double right = __shfl_down_sync(FULL, t.x, 1);
-        if (loadsRight)
-            right = ptr[CG];
-        out[2] = right;
+    // ---- issue functions of the four staging groups for element row `row` (empty group past the strip) ----
+    auto issueUV = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
+                cpAsync16(&st.UV[0][k][lane], a.u + n);
+                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                if (loadsRight) {
+                    cpAsync8(&st.UVr[0][k], a.u + n + CG);
+                    cpAsync8(&st.UVr[1][k], a.v + n + CG);
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueP = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nx + ex;
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                cpAsync8(&st.P[q][lane], a.Pa + size_t(q) * Npad + en);
+        }
+        cpAsyncCommit();
+    };
+    auto issueS = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nx + ex;
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueND = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + k) * g.cgs + col0;
+                cpAsync16(&st.ND[k][0][lane], a.c1 + n);
+                cpAsync16(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16(&st.ND[k][2][lane], a.rx + n);
+                cpAsync16(&st.ND[k][3][lane], a.ry + n);
+                cpAsync16(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+            }
+        }
+        cpAsyncCommit();
     };
 
     double carryX[2] = { 0.0, 0.0 }, carryY[2] = { 0.0, 0.0 };
     double ul[9], vl[9];
-    loadRow(a.u, CG * ey0, ul);
-    loadRow(a.v, CG * ey0, vl);
+    // prologue: the four groups of the first row; the bottom node row comes by plain loads
+    issueUV(ey0);
+    issueP(ey0);
+    issueS(ey0);
+    issueND(ey0);
+    {
+        const size_t n = size_t(CG * ey0) * g.cgs + col0;
+        const double2 tu = *reinterpret_cast<const double2*>(a.u + n), tv = *reinterpret_cast<const double2*>(a.v + n);
+        ul[0] = tu.x;
+        ul[1] = tu.y;
+        vl[0] = tv.x;
+        vl[1] = tv.y;
+        double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+        if (loadsRight) {
+            ru = a.u[n + CG];
+            rv = a.v[n + CG];
+        }
+        ul[2] = ru;
+        vl[2] = rv;
+    }
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nx + ex;
-        loadRow(a.u, CG * ey + 1, ul + 3);
-        loadRow(a.v, CG * ey + 1, vl + 3);
-        loadRow(a.u, CG * ey + 2, ul + 6);
-        loadRow(a.v, CG * ey + 2, vl + 6);
         const bool ice = active && (__ldg(a.landmask + e) != 0);
+        // ---- the two upper node rows of u, v from the staging buffer ----
+        cpAsyncWait<3>();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
+            ul[3 * (k + 1)] = tu.x;
+            ul[3 * (k + 1) + 1] = tu.y;
+            vl[3 * (k + 1)] = tv.x;
+            vl[3 * (k + 1) + 1] = tv.y;
+            double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+            if (loadsRight) {
+                ru = st.UVr[0][k];
+                rv = st.UVr[1][k];
+            }
+            ul[3 * (k + 1) + 2] = ru;
+            vl[3 * (k + 1) + 2] = rv;
+        }
+        issueUV(ey + 1);
 
         // ---- velocity gradient in the 9 Gauss points by two 1-d contractions ----
         double e11[9], e12[9], e22[9];
@@ -231,9 +349,10 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
         }
 
         // ---- VP law in the Gauss points: e** become the integrands r** (MEVPStressUpdateStep.hpp:62-117) ----
+        cpAsyncWait<3>();
         static_for<9>([&](auto QQ) {
             constexpr int q = decltype(QQ)::value;
-            const double Pa = __ldg(a.Pa + size_t(q) * Npad + e);
+            const double Pa = st.P[q][lane];
             const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
             const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
             const double pd = 0.125 * Pa * iD;
@@ -241,12 +360,14 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
             e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);
             e12[q] = 2.0 * pd * g12;
         });
+        issueP(ey + 1);
 
         // ---- per stress component: project, relax, store, accumulate the divergence contributions ----
         double Tx[9], Ty[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k)
             Tx[k] = Ty[k] = 0.0;
+        cpAsyncWait<3>();
         auto component = [&](double* plane, const double (&r)[9], auto COMP) {
             constexpr int comp = decltype(COMP)::value; // 0: s11, 1: s12, 2: s22
             double s[DGs];
@@ -259,7 +380,7 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
                     if constexpr (b != 0.0)
                         acc = fma(b, r[q], acc);
                 });
-                s[j] = fma(plane[size_t(j) * Npad + e], a.keep, acc);
+                s[j] = fma(st.S[comp * 8 + j][lane], a.keep, acc);
                 if (active)
                     plane[size_t(j) * Npad + e] = s[j];
             });
@@ -290,6 +411,7 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
         component(a.s11, e11, std::integral_constant<int, 0> {});
         component(a.s12, e12, std::integral_constant<int, 1> {});
         component(a.s22, e22, std::integral_constant<int, 2> {});
+        issueS(ey + 1);
 
         // ---- raw contributions to the deferred lines ----
         if (active && lane == 0 && sx > 0) {
@@ -336,16 +458,12 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
             }
         }
         // ---- momentum update of the completed nodes (rows 2ey, 2ey+1; columns 2ex, 2ex+1) ----
+        cpAsyncWait<3>();
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 c1 = __ldg(reinterpret_cast<const double2*>(a.c1 + n0));
-            const double2 cA = __ldg(reinterpret_cast<const double2*>(a.cA + n0));
-            const double2 rx = __ldg(reinterpret_cast<const double2*>(a.rx + n0));
-            const double2 ry = __ldg(reinterpret_cast<const double2*>(a.ry + n0));
-            const double2 uO = __ldg(reinterpret_cast<const double2*>(a.uO + n0));
-            const double2 vO = __ldg(reinterpret_cast<const double2*>(a.vO + n0));
-            const double2 ilm = __ldg(reinterpret_cast<const double2*>(a.ilm + n0));
+            const double2 c1 = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], rx = st.ND[jy][2][lane], ry = st.ND[jy][3][lane];
+            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
             const uchar2 msk = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + n0));
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
@@ -372,6 +490,7 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
                 }
             }
         }
+        issueND(ey + 1);
         carryX[0] = Tx[CG * NR];
         carryX[1] = Tx[CG * NR + 1];
         carryY[0] = Ty[CG * NR];
@@ -382,6 +501,7 @@ template <int DUMMY = 0> __global__ void __launch_bounds__(128, 3) subcycle_stri
             vl[jx] = vl[CG * NR + jx];
         }
     }
+    cpAsyncWait<0>();
 }
 
 //! deferred-line nodes for the uniform mEVP path (see subcycle_lines in nsdg_momentum.cuh)
