@@ -162,8 +162,11 @@ int nsdg_get_timing(nsdg_handle h, nsdg_timing* t);
  * Each box exports one device buffer per side that neighbours write into over NVLink; the
  * handles are CUDA IPC handles exchanged by the launcher (any transport).                    */
 #define NSDG_IPC_HANDLE_BYTES 64
-int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handles /* 2 * NSDG_IPC_HANDLE_BYTES */);
-int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handles);
+/* after nsdg_set_mesh: the CUDA IPC handle of this box's halo arena */
+int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handle /* NSDG_IPC_HANDLE_BYTES */);
+/* map the arena of the neighbour across `side` (enum nsdg_side) */
+int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handle);
+/* all neighbour sides connected: from now on nsdg_step / nsdg_update / nsdg_subcycles exchange halos */
 int nsdg_halo_ready(nsdg_handle h);
 
 const char* nsdg_last_error(void);

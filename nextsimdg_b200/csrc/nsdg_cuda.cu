@@ -21,6 +21,7 @@
 
 #include "nsdg_momentum.cuh"
 #include "nsdg_momentum_uniform.cuh"
+#include "nsdg_halo.cuh"
 #include "nsdg_prepare.cuh"
 
 namespace nsdg {
@@ -43,6 +44,9 @@ public:
     virtual void timeKernels(int n, float* stripMs, float* linesMs) = 0;
     virtual void getInternal(const std::string& name, double* host, size_t cap, size_t* count) = 0;
     virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
+    virtual void haloExport(unsigned char* handle) = 0;
+    virtual void haloConnect(int side, const unsigned char* handle) = 0;
+    virtual void haloReady() = 0;
     nsdg_config cfg {};
     nsdg_timing timing {};
     std::vector<uint8_t> landmask;
@@ -85,6 +89,13 @@ public:
     DevBuf<double> hbuf, vbuf;
     DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
     bool fastUniformMEVP = false;
+    // halo exchange (partitioned domain)
+    DevBuf<unsigned char> arena; //!< my receive arena: [side][parity] payload slots + flags
+    HaloArenaLayout arenaLayout {};
+    unsigned char* peerArena[kHaloSides] = { nullptr, nullptr, nullptr, nullptr }; //!< IPC-mapped neighbour arenas
+    unsigned sideEpoch[kHaloSides] = { 0, 0, 0, 0 };
+    DevBuf<int> haloError;
+    bool haloActive = false;
     // staging
     DevBuf<double> staging;
     std::vector<std::pair<const void*, size_t>> registered;
@@ -114,6 +125,7 @@ public:
     {
         if (graphExec)
             cudaGraphExecDestroy(graphExec);
+        closePeers();
         for (auto& r : registered)
             cudaHostUnregister(const_cast<void*>(r.first));
         for (auto& e : ev)
@@ -203,6 +215,10 @@ public:
         g.cgny = CG * ny + 1;
         g.cgs = int(alignUp(size_t(g.cgnx), 16));
         g.spherical = spherical ? 1 : 0;
+        g.bnd = 0;
+        for (int s = 0; s < 4; ++s)
+            if (!(cfg.global_nx > 0 && cfg.neighbour[s] >= 0))
+                g.bnd |= 1 << s;
         cg1s = int(alignUp(size_t(nx + 1), 16));
         ncg = size_t(g.cgs) * g.cgny;
         ncg1 = size_t(cg1s) * (ny + 1);
@@ -332,6 +348,14 @@ public:
                     subcycle_strip_umevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmevpSmemBytes)));
         }
         timing.uniform_path = uniform ? 1 : 0;
+        haloActive = false;
+        if (cfg.global_nx > 0) {
+            arenaLayout.slotDoubles = alignUp(size_t(6) * std::max(g.cgnx, g.cgny) + 64, 64);
+            arena.alloc(arenaLayout.totalBytes());
+            haloError.alloc(1);
+            for (auto& e : sideEpoch)
+                e = 0;
+        }
         meshSet = true;
     }
 
@@ -479,6 +503,151 @@ public:
     }
 
     // ------------------------------------------------------------------------------------
+    // halo exchange between partition boxes (nsdg_halo.cuh)
+    // ------------------------------------------------------------------------------------
+    bool hasNeighbour(int side) const { return cfg.global_nx > 0 && cfg.neighbour[side] >= 0; }
+
+    void haloExport(unsigned char* handle) override
+    {
+        requireMesh();
+        if (cfg.global_nx <= 0)
+            throw std::runtime_error("nsdg_halo_export: the handle was created without a partition");
+        cudaIpcMemHandle_t hnd;
+        NSDG_CUDA_CHECK(cudaIpcGetMemHandle(&hnd, arena.p));
+        static_assert(sizeof(hnd) == NSDG_IPC_HANDLE_BYTES, "IPC handle size");
+        std::memcpy(handle, &hnd, sizeof(hnd));
+    }
+    void haloConnect(int side, const unsigned char* handle) override
+    {
+        requireMesh();
+        if (side < 0 || side >= kHaloSides || !hasNeighbour(side))
+            throw std::runtime_error("nsdg_halo_connect: no neighbour on that side");
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, handle, sizeof(hnd));
+        void* ptr = nullptr;
+        NSDG_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+        peerArena[side] = static_cast<unsigned char*>(ptr);
+    }
+    void haloReady() override
+    {
+        for (int s = 0; s < kHaloSides; ++s)
+            if (hasNeighbour(s) && !peerArena[s])
+                throw std::runtime_error("nsdg_halo_ready: a neighbour side is not connected");
+        haloActive = cfg.global_nx > 0;
+    }
+    void closePeers()
+    {
+        for (auto& pa : peerArena)
+            if (pa) {
+                cudaIpcCloseMemHandle(pa);
+                pa = nullptr;
+            }
+    }
+
+    //! lines of a node field (CG grid) that go to / come from the neighbour across `side`.
+    //! The right/top box owns the shared boundary line: a box receives CG lines from its left/bottom
+    //! neighbour and CG+1 from its right/top one, and sends the complementary sets.
+    HaloLineDesc nodeLines(int side, bool send, int nFields) const
+    {
+        HaloLineDesc d {};
+        d.nFields = nFields;
+        const bool vertical = (side == NSDG_LEFT || side == NSDG_RIGHT); // lines are node columns
+        const int last = vertical ? g.cgnx - 1 : g.cgny - 1;
+        int first, count;
+        if (side == NSDG_LEFT || side == NSDG_BOTTOM) {
+            first = send ? CG : 0;
+            count = send ? CG + 1 : CG;
+        } else {
+            first = send ? last - 2 * CG : last - CG;
+            count = send ? CG : CG + 1;
+        }
+        d.nLines = count;
+        d.lineLen = vertical ? g.cgny : g.cgnx;
+        d.stride = vertical ? g.cgs : 1;
+        for (int k = 0; k < count; ++k)
+            d.firstLine[k] = vertical ? long(first + k) : long(first + k) * g.cgs;
+        return d;
+    }
+    //! the ring column/row of an element (DG plane) field: send the first/last OWNED line, receive the ring line
+    HaloLineDesc elemLines(int side, bool send, int nFields) const
+    {
+        HaloLineDesc d {};
+        d.nFields = nFields;
+        const bool vertical = (side == NSDG_LEFT || side == NSDG_RIGHT);
+        const int last = vertical ? g.nx - 1 : g.ny - 1;
+        const int line = (side == NSDG_LEFT || side == NSDG_BOTTOM) ? (send ? 1 : 0) : (send ? last - 1 : last);
+        d.nLines = 1;
+        d.lineLen = vertical ? g.ny : g.nx;
+        d.stride = vertical ? g.nx : 1;
+        d.firstLine[0] = vertical ? long(line) : long(line) * g.nx;
+        return d;
+    }
+
+    //! one full exchange (x phase, then y phase) of node fields (pitch == 0) or of the planes of a DG field
+    void exchange(double* const* fields, int nFields, size_t pitch, bool nodes)
+    {
+        if (!haloActive)
+            return;
+        const int phases[2] = { (1 << NSDG_LEFT) | (1 << NSDG_RIGHT), (1 << NSDG_BOTTOM) | (1 << NSDG_TOP) };
+        const int opposite[4] = { NSDG_TOP, NSDG_LEFT, NSDG_BOTTOM, NSDG_RIGHT };
+        for (int ph = 0; ph < 2; ++ph) {
+            bool any = false;
+            for (int s = 0; s < kHaloSides; ++s)
+                any = any || ((phases[ph] & (1 << s)) && hasNeighbour(s));
+            if (!any)
+                continue;
+            HaloPushArgs pa {};
+            HaloUnpackArgs ua {};
+            for (int f = 0; f < nFields && f < 8; ++f) {
+                pa.fields[f] = pitch ? nullptr : fields[f];
+                ua.fields[f] = pitch ? nullptr : fields[f];
+            }
+            pa.fields[0] = ua.fields[0] = fields[0];
+            pa.fieldPitch = ua.fieldPitch = pitch;
+            pa.sideMask = ua.sideMask = phases[ph];
+            ua.errorFlag = haloError;
+            for (int s = 0; s < kHaloSides; ++s) {
+                if (!(phases[ph] & (1 << s)) || !hasNeighbour(s))
+                    continue;
+                const unsigned epoch = ++sideEpoch[s];
+                const int parity = int(epoch & 1u);
+                pa.send[s] = nodes ? nodeLines(s, true, nFields) : elemLines(s, true, nFields);
+                ua.recv[s] = nodes ? nodeLines(s, false, nFields) : elemLines(s, false, nFields);
+                // my message lands in the neighbour's slot for ITS side facing me
+                const int os = opposite[s];
+                pa.peerSlot[s] = reinterpret_cast<double*>(peerArena[s]) + arenaLayout.slotOffset(os, parity);
+                pa.peerFlag[s] = reinterpret_cast<unsigned*>(peerArena[s] + arenaLayout.flagsOffsetBytes()) + os;
+                pa.epoch[s] = epoch;
+                ua.mySlot[s] = reinterpret_cast<const double*>(arena.p) + arenaLayout.slotOffset(s, parity);
+                ua.myFlag[s] = reinterpret_cast<const unsigned*>(arena.p + arenaLayout.flagsOffsetBytes()) + s;
+                ua.epoch[s] = epoch;
+            }
+            halo_push_kernel<<<kHaloSides, 1024, 0, stream>>>(pa);
+            halo_unpack_kernel<<<kHaloSides, 1024, 0, stream>>>(ua);
+            launches += 2;
+        }
+    }
+    void exchangeNodes(double* a, double* b)
+    {
+        double* f[2] = { a, b };
+        exchange(f, 2, 0, true);
+    }
+    void exchangePlanes(double* planes, int ncomp)
+    {
+        double* f[1] = { planes };
+        exchange(f, ncomp, g.Npad, false);
+    }
+    void checkHaloError()
+    {
+        if (!haloActive)
+            return;
+        int e = 0;
+        NSDG_CUDA_CHECK(cudaMemcpy(&e, haloError.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e)
+            throw std::runtime_error("nsdg: halo exchange timed out waiting for a neighbour box");
+    }
+
+    // ------------------------------------------------------------------------------------
     // advection
     // ------------------------------------------------------------------------------------
     template <int DG>
@@ -501,8 +670,10 @@ public:
         const unsigned nb = blocksFor(g.N);
         transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t1);
         add_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t1);
+        exchangePlanes(phi, DG); // ring elements of the RK stage value come from their owners
         transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t2);
         heun_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t2, t1);
+        exchangePlanes(phi, DG);
         launches += 4;
     }
     void limit(double* f, int mode, double maxv, double minv)
@@ -661,9 +832,11 @@ public:
                     launchSubcycle<NSDG_BBM>(a);
                 else
                     launchSubcycle<NSDG_MEVP>(a);
+                exchangeNodes(u, v); // no-op for a single domain
             }
         };
-        if (cfg.use_cuda_graph && n > 1) {
+        // the exchange epochs are kernel arguments, so a partitioned box replays plain launches
+        if (cfg.use_cuda_graph && n > 1 && !haloActive) {
             if (!graphExec || graphN != n || graphDeltaT != deltaT) {
                 if (graphExec) {
                     cudaGraphExecDestroy(graphExec);
@@ -752,6 +925,9 @@ public:
         const size_t cgBytes = ncg * 8;
         NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
         // ---- advection + limiters (DynamicsKernel.hpp:160-172) ----
+        exchangeNodes(u, v); // partitioned: non-owned node lines come from their owners (no-op otherwise)
+        if (bbm)
+            exchangeNodes(avgU, avgV);
         prepareAdvection<DGA>(bbm ? avgU : u, bbm ? avgV : v, topA, velx, vely, nvX, nvY);
         transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, cice, tmp1, tmp2);
         transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, hice, tmp1, tmp2);
@@ -790,9 +966,7 @@ public:
         lastDeltaT = deltaT;
         NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
         // ---- the subcycle loop ----
-        const long before = launches;
         runSubcycles(cfg.nsteps, deltaT);
-        (void)before;
         NSDG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
     }
     void finishTiming()
@@ -1134,20 +1308,27 @@ int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_
     H(h)->setInternal(name, host, count);
     NSDG_CATCH
 }
-int nsdg_halo_export(nsdg_handle, unsigned char*)
+int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handle)
 {
-    g_lastError = "nsdg_halo_export: multi-GPU halo exchange is not built yet";
-    return 1;
+    NSDG_TRY
+    if (!ipc_handle)
+        throw std::runtime_error("nsdg_halo_export: null argument");
+    H(h)->haloExport(ipc_handle);
+    NSDG_CATCH
 }
-int nsdg_halo_connect(nsdg_handle, int, const unsigned char*)
+int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handle)
 {
-    g_lastError = "nsdg_halo_connect: multi-GPU halo exchange is not built yet";
-    return 1;
+    NSDG_TRY
+    if (!peer_ipc_handle)
+        throw std::runtime_error("nsdg_halo_connect: null argument");
+    H(h)->haloConnect(side, peer_ipc_handle);
+    NSDG_CATCH
 }
-int nsdg_halo_ready(nsdg_handle)
+int nsdg_halo_ready(nsdg_handle h)
 {
-    g_lastError = "nsdg_halo_ready: multi-GPU halo exchange is not built yet";
-    return 1;
+    NSDG_TRY
+    H(h)->haloReady();
+    NSDG_CATCH
 }
 const char* nsdg_last_error(void) { return g_lastError.c_str(); }
 const char* nsdg_version(void) { return "nsdg-cuda 0.1 (sm_100a)"; }

@@ -172,8 +172,14 @@ __global__ void sshgrad_cg_kernel(GridDims g, int cg1s, const double* __restrict
         return;
     const int c = int(t % g.cgnx), r = int(t / g.cgnx);
     auto at = [&](const double* f, int i, int j) {
-        i = min(max(i, 1), g.nx - 1);
-        j = min(max(j, 1), g.ny - 1);
+        if (g.bnd & 8)
+            i = max(i, 1);
+        if (g.bnd & 2)
+            i = min(i, g.nx - 1);
+        if (g.bnd & 1)
+            j = max(j, 1);
+        if (g.bnd & 4)
+            j = min(j, g.ny - 1);
         return f[size_t(j) * cg1s + i];
     };
     double u, v;

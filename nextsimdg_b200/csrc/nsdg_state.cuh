@@ -60,6 +60,7 @@ struct GridDims {
     int cgnx, cgny; //!< CG*nx+1, CG*ny+1
     int cgs; //!< padded CG row stride
     int spherical;
+    int bnd; //!< bit s set: side s (0 bottom,1 right,2 top,3 left) is an edge of the GLOBAL domain (15 = single domain)
 };
 
 //! simple owning device buffer

@@ -121,9 +121,10 @@ __global__ void dg2cg_kernel(GridDims g, const double* __restrict__ src, double*
             }
         }
     // DG2CGBoundary, Interpolations.cpp:165-180: rows first, then columns (corners x4)
-    if (r == 0 || r == g.cgny - 1)
+    // (only on edges of the global domain; a partition box's artificial edges are halo lines)
+    if ((r == 0 && (g.bnd & 1)) || (r == g.cgny - 1 && (g.bnd & 4)))
         sum *= 2.0;
-    if (c == 0 || c == g.cgnx - 1)
+    if ((c == 0 && (g.bnd & 8)) || (c == g.cgnx - 1 && (g.bnd & 2)))
         sum *= 2.0;
     sum = fmin(fmax(sum, lo), hi);
     dest[size_t(r) * g.cgs + c] = sum;

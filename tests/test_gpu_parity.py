@@ -286,3 +286,22 @@ def test_locality_and_determinism_at_full_size():
     big_v = runs[0][1][sl][inner]
     assert rel(big_u, ref.uice[inner]) < TOL_STEP
     assert rel(big_v, ref.vice[inner]) < TOL_STEP
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_halo_exchange_matches_single_domain(world):
+    """2-D boxes with NVLink halo exchange == the single-domain GPU result (tests/mgpu_parity.py).
+    Needs `world` GPUs on the box (gpurun --gpus N); skipped on the 1-GPU box."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29400 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(os.path.dirname(__file__), "mgpu_parity.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
