@@ -547,25 +547,27 @@ public:
     //! lines of a node field (CG grid) that go to / come from the neighbour across `side`.
     //! The right/top box owns the shared boundary line: a box receives CG lines from its left/bottom
     //! neighbour and CG+1 from its right/top one, and sends the complementary sets.
-    HaloLineDesc nodeLines(int side, bool send, int nFields) const
+    HaloLineDesc nodeLines(int side, bool send, int nFields, int deg) const
     {
+        // deg = CG for the velocity space, 1 for the CG1 sea-surface-height grid
+        const int nxn = deg * g.nx + 1, nyn = deg * g.ny + 1, stride = (deg == CG) ? g.cgs : cg1s;
         HaloLineDesc d {};
         d.nFields = nFields;
         const bool vertical = (side == NSDG_LEFT || side == NSDG_RIGHT); // lines are node columns
-        const int last = vertical ? g.cgnx - 1 : g.cgny - 1;
+        const int last = vertical ? nxn - 1 : nyn - 1;
         int first, count;
         if (side == NSDG_LEFT || side == NSDG_BOTTOM) {
-            first = send ? CG : 0;
-            count = send ? CG + 1 : CG;
+            first = send ? deg : 0;
+            count = send ? deg + 1 : deg;
         } else {
-            first = send ? last - 2 * CG : last - CG;
-            count = send ? CG : CG + 1;
+            first = send ? last - 2 * deg : last - deg;
+            count = send ? deg : deg + 1;
         }
         d.nLines = count;
-        d.lineLen = vertical ? g.cgny : g.cgnx;
-        d.stride = vertical ? g.cgs : 1;
+        d.lineLen = vertical ? nyn : nxn;
+        d.stride = vertical ? stride : 1;
         for (int k = 0; k < count; ++k)
-            d.firstLine[k] = vertical ? long(first + k) : long(first + k) * g.cgs;
+            d.firstLine[k] = vertical ? long(first + k) : long(first + k) * stride;
         return d;
     }
     //! the ring column/row of an element (DG plane) field: send the first/last OWNED line, receive the ring line
@@ -584,7 +586,7 @@ public:
     }
 
     //! one full exchange (x phase, then y phase) of node fields (pitch == 0) or of the planes of a DG field
-    void exchange(double* const* fields, int nFields, size_t pitch, bool nodes)
+    void exchange(double* const* fields, int nFields, size_t pitch, bool nodes, int deg = CG)
     {
         if (!haloActive)
             return;
@@ -611,8 +613,8 @@ public:
                     continue;
                 const unsigned epoch = ++sideEpoch[s];
                 const int parity = int(epoch & 1u);
-                pa.send[s] = nodes ? nodeLines(s, true, nFields) : elemLines(s, true, nFields);
-                ua.recv[s] = nodes ? nodeLines(s, false, nFields) : elemLines(s, false, nFields);
+                pa.send[s] = nodes ? nodeLines(s, true, nFields, deg) : elemLines(s, true, nFields);
+                ua.recv[s] = nodes ? nodeLines(s, false, nFields, deg) : elemLines(s, false, nFields);
                 // my message lands in the neighbour's slot for ITS side facing me
                 const int os = opposite[s];
                 pa.peerSlot[s] = reinterpret_cast<double*>(peerArena[s]) + arenaLayout.slotOffset(os, parity);
@@ -631,6 +633,12 @@ public:
     {
         double* f[2] = { a, b };
         exchange(f, 2, 0, true);
+    }
+    //! a single field on the CG1 node grid (the sea-surface height before its gradient is taken)
+    void exchangeNodesCG1(double* a)
+    {
+        double* f[1] = { a };
+        exchange(f, 1, 0, true, 1);
     }
     void exchangePlanes(double* planes, int ncomp)
     {
@@ -698,6 +706,7 @@ public:
         g1.cgs = cg1s;
         const unsigned nb1 = blocksFor(size_t(g1.cgnx) * g1.cgny);
         dg2cg_kernel<1, 1><<<nb1, 128, 0, stream>>>(g1, ssh, cgSSH, -INFINITY, INFINITY);
+        exchangeNodesCG1(cgSSH); // the gradient at the first owned CG1 line needs the complete outer line
         sshgrad_cg1_kernel<<<nb1, 128, 0, stream>>>(g, cg1s, cgSSH, mop, mass1, gu1, gv1);
         sshgrad_cg_kernel<CG><<<nb, 128, 0, stream>>>(g, cg1s, gu1, gv1, gradX, gradY);
         launches += 5;
