@@ -168,6 +168,8 @@ def run_gpu(args):
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     dist = None
+    json_fd = os.dup(1)  # the ONE JSON line goes here; everything else a library prints to stdout (NCCL's
+    os.dup2(2, 1)  # version banner ...) is diverted to stderr
     if world > 1:
         import torch
         import torch.distributed as dist_
@@ -243,7 +245,8 @@ def run_gpu(args):
     achieved = b_alg * local_elems / (pair_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
-                "lines_ms": lines_ms.value, "alg_bytes_per_element_subcycle": b_alg, "peak_source": peak_src}
+                "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_alg,
+                "peak_source": peak_src}
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step ----
     for _ in range(min(args.warmup, 2)):
@@ -285,7 +288,8 @@ def run_gpu(args):
         "model_days_per_wall_hour": 3600.0 / (ms_per_step * 1e-3 * (86400.0 / DT)),
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():

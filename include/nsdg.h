@@ -154,6 +154,7 @@ typedef struct nsdg_timing {
     float advection_ms, prepare_ms, subcycle_ms, total_ms;
     long kernel_launches; /* kernels launched by this library during the last nsdg_step/nsdg_subcycles */
     int uniform_path; /* 1 if the uniform-rectangular operator path is active */
+    float halo_ms; /* partitioned boxes: average device time of one u,v halo exchange (nsdg_time_kernels) */
 } nsdg_timing;
 int nsdg_get_timing(nsdg_handle h, nsdg_timing* t);
 

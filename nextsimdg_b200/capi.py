@@ -41,7 +41,7 @@ class UpdateIO(Structure):
 
 class Timing(Structure):
     _fields_ = [("advection_ms", c_float), ("prepare_ms", c_float), ("subcycle_ms", c_float),
-                ("total_ms", c_float), ("kernel_launches", c_long), ("uniform_path", c_int)]
+                ("total_ms", c_float), ("kernel_launches", c_long), ("uniform_path", c_int), ("halo_ms", c_float)]
 
 
 # name -> (restype, argtypes); must list EVERY function declared in include/nsdg.h

@@ -95,6 +95,7 @@ public:
     unsigned char* peerArena[kHaloSides] = { nullptr, nullptr, nullptr, nullptr }; //!< IPC-mapped neighbour arenas
     unsigned sideEpoch[kHaloSides] = { 0, 0, 0, 0 };
     DevBuf<int> haloError;
+    DevBuf<unsigned> haloDone;
     bool haloActive = false;
     // staging
     DevBuf<double> staging;
@@ -204,12 +205,13 @@ public:
         g.nx = nx;
         g.ny = ny;
         g.N = nx * ny;
+        g.nxs = int(alignUp(size_t(nx), 32));
         // Plane pitch: a multiple of 32 elements (256 B), skewed by 8 KiB + 256 B so that the 33+ planes a
         // warp streams never sit a power-of-two apart (2048^2 * 8 B = 32 MiB exactly would alias every plane
         // onto the same L2 sets and DRAM banks).
-        g.Npad = int(alignUp(size_t(g.N), 32)) + (g.N >= 4096 ? 1056 : 0);
+        g.Npad = g.nxs * ny + (g.N >= 4096 ? 1056 : 0);
         if (const char* env = std::getenv("NSDG_PLANE_SKEW")) // tuning knob (elements, multiple of 32)
-            g.Npad = int(alignUp(size_t(g.N), 32)) + std::atoi(env);
+            g.Npad = g.nxs * ny + std::atoi(env);
         g.CG = CG;
         g.cgnx = CG * nx + 1;
         g.cgny = CG * ny + 1;
@@ -252,8 +254,8 @@ public:
         NSDG_CUDA_CHECK(cudaMemcpy(vy, hvy.data(), nnodes * 8, cudaMemcpyHostToDevice));
         d_landmask.alloc(Npad);
         d_dirmask.alloc(Npad);
-        NSDG_CUDA_CHECK(cudaMemcpy(d_landmask, landmask.data(), N, cudaMemcpyHostToDevice));
-        NSDG_CUDA_CHECK(cudaMemcpy(d_dirmask, hdirmask.data(), N, cudaMemcpyHostToDevice));
+        NSDG_CUDA_CHECK(cudaMemcpy2D(d_landmask, g.nxs, landmask.data(), nx, nx, ny, cudaMemcpyHostToDevice));
+        NSDG_CUDA_CHECK(cudaMemcpy2D(d_dirmask, g.nxs, hdirmask.data(), nx, nx, ny, cudaMemcpyHostToDevice));
         d_nodemask.alloc(ncg);
         nodemask_kernel<CG><<<blocksFor(N), 128, 0, stream>>>(g, d_dirmask, d_nodemask);
 
@@ -353,6 +355,7 @@ public:
             arenaLayout.slotDoubles = alignUp(size_t(6) * std::max(g.cgnx, g.cgny) + 64, 64);
             arena.alloc(arenaLayout.totalBytes());
             haloError.alloc(1);
+            haloDone.alloc(kHaloSides);
             for (auto& e : sideEpoch)
                 e = 0;
         }
@@ -375,21 +378,23 @@ public:
             throw std::runtime_error("nsdg_set_field: ncomp must be 1 or the DG component count");
         const size_t N = g.N;
         if (ncomp == 1) {
-            NSDG_CUDA_CHECK(cudaMemcpyAsync(planes, host, N * 8, cudaMemcpyHostToDevice, stream));
+            NSDG_CUDA_CHECK(cudaMemcpy2DAsync(planes, size_t(g.nxs) * 8, host, size_t(g.nx) * 8, size_t(g.nx) * 8, g.ny,
+                cudaMemcpyHostToDevice, stream));
             if (nplanes > 1)
                 NSDG_CUDA_CHECK(cudaMemsetAsync(planes + g.Npad, 0, size_t(nplanes - 1) * g.Npad * 8, stream));
         } else {
             NSDG_CUDA_CHECK(cudaMemcpyAsync(staging, host, N * ncomp * 8, cudaMemcpyHostToDevice, stream));
-            aos2planes_kernel<<<blocksFor(N), 128, 0, stream>>>(N, g.Npad, ncomp, nplanes, staging, planes);
+            aos2planes_kernel<<<blocksFor(N), 128, 0, stream>>>(g, ncomp, nplanes, staging, planes);
         }
     }
     void downloadPlanes(const double* planes, int ncomp, double* host)
     {
         const size_t N = g.N;
         if (ncomp == 1) {
-            NSDG_CUDA_CHECK(cudaMemcpyAsync(host, planes, N * 8, cudaMemcpyDeviceToHost, stream));
+            NSDG_CUDA_CHECK(cudaMemcpy2DAsync(host, size_t(g.nx) * 8, planes, size_t(g.nxs) * 8, size_t(g.nx) * 8, g.ny,
+                cudaMemcpyDeviceToHost, stream));
         } else {
-            planes2aos_kernel<<<blocksFor(N), 128, 0, stream>>>(N, g.Npad, ncomp, planes, staging);
+            planes2aos_kernel<<<blocksFor(N), 128, 0, stream>>>(g, ncomp, planes, staging);
             NSDG_CUDA_CHECK(cudaMemcpyAsync(host, staging, N * ncomp * 8, cudaMemcpyDeviceToHost, stream));
         }
     }
@@ -580,8 +585,8 @@ public:
         const int line = (side == NSDG_LEFT || side == NSDG_BOTTOM) ? (send ? 1 : 0) : (send ? last - 1 : last);
         d.nLines = 1;
         d.lineLen = vertical ? g.ny : g.nx;
-        d.stride = vertical ? g.nx : 1;
-        d.firstLine[0] = vertical ? long(line) : long(line) * g.nx;
+        d.stride = vertical ? g.nxs : 1;
+        d.firstLine[0] = vertical ? long(line) : long(line) * g.nxs;
         return d;
     }
 
@@ -624,8 +629,9 @@ public:
                 ua.myFlag[s] = reinterpret_cast<const unsigned*>(arena.p + arenaLayout.flagsOffsetBytes()) + s;
                 ua.epoch[s] = epoch;
             }
-            halo_push_kernel<<<kHaloSides, 1024, 0, stream>>>(pa);
-            halo_unpack_kernel<<<kHaloSides, 1024, 0, stream>>>(ua);
+            pa.done = haloDone;
+            halo_push_kernel<<<dim3(kHaloBlocksPerSide, kHaloSides), 256, 0, stream>>>(pa);
+            halo_unpack_kernel<<<dim3(kHaloBlocksPerSide, kHaloSides), 256, 0, stream>>>(ua);
             launches += 2;
         }
     }
@@ -895,7 +901,7 @@ public:
         const UniformArgs ua = makeUniformArgs(lastDeltaT);
         const unsigned nwarps = unsigned(nsx) * nsy, nbStrip = (nwarps + 3) / 4;
         const size_t nLine = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
-        double ts = 0, tl = 0;
+        double ts = 0, tl = 0, th = 0;
         for (int i = 0; i < n; ++i) {
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
             if (fastUniformMEVP)
@@ -912,15 +918,20 @@ public:
             else
                 subcycle_lines<CG, NSDG_MEVP><<<blocksFor(nLine), 128, 0, stream>>>(a);
             NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+            exchangeNodes(u, v);
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
             NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
-            float x = 0, y = 0;
+            float x = 0, y = 0, z = 0;
             NSDG_CUDA_CHECK(cudaEventElapsedTime(&x, ev[0], ev[1]));
             NSDG_CUDA_CHECK(cudaEventElapsedTime(&y, ev[1], ev[2]));
+            NSDG_CUDA_CHECK(cudaEventElapsedTime(&z, ev[2], ev[3]));
             ts += x;
             tl += y;
+            th += z;
         }
         *stripMs = float(ts / n);
         *linesMs = float(tl / n);
+        timing.halo_ms = float(th / n);
     }
 
     // ------------------------------------------------------------------------------------
@@ -1099,9 +1110,9 @@ public:
             if (!host || cap < n)
                 return;
             pull(size_t(in.comps) * g.Npad);
-            for (size_t e = 0; e < N; ++e)
+            for (size_t d = 0; d < N; ++d)
                 for (int c = 0; c < in.comps; ++c)
-                    host[e * in.comps + c] = tmp[size_t(c) * g.Npad + e];
+                    host[d * in.comps + c] = tmp[size_t(c) * g.Npad + (d / g.nx) * g.nxs + d % g.nx];
         } else if (in.kind == Internal::OPF) {
             n = N * in.comps;
             if (count)
@@ -1110,9 +1121,9 @@ public:
                 return;
             const size_t opN = uniform ? 1 : g.Npad;
             pull(size_t(in.comps) * opN);
-            for (size_t e = 0; e < N; ++e)
+            for (size_t d = 0; d < N; ++d)
                 for (int k = 0; k < in.comps; ++k)
-                    host[e * in.comps + k] = tmp[size_t(k) * opN + (uniform ? 0 : e)];
+                    host[d * in.comps + k] = tmp[size_t(k) * opN + (uniform ? 0 : (d / g.nx) * g.nxs + d % g.nx)];
         } else {
             const size_t ne = in.kind == Internal::EDGEX ? size_t(g.nx) * (g.ny + 1) : size_t(g.nx + 1) * g.ny;
             const size_t pitch = alignUp(ne, 32);
@@ -1147,9 +1158,9 @@ public:
             if (count != N * in.comps)
                 throw std::runtime_error("nsdg_set_internal: wrong size for " + name);
             tmp.assign(size_t(in.comps) * g.Npad, 0.0);
-            for (size_t e = 0; e < N; ++e)
+            for (size_t d = 0; d < N; ++d)
                 for (int c = 0; c < in.comps; ++c)
-                    tmp[size_t(c) * g.Npad + e] = host[e * in.comps + c];
+                    tmp[size_t(c) * g.Npad + (d / g.nx) * g.nxs + d % g.nx] = host[d * in.comps + c];
             NSDG_CUDA_CHECK(cudaMemcpy(in.ptr, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
         } else
             throw std::runtime_error("nsdg_set_internal: array is read-only: " + name);

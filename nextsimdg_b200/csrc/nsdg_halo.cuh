@@ -58,19 +58,23 @@ struct HaloPushArgs {
     unsigned* peerFlag[kHaloSides];
     unsigned epoch[kHaloSides];
     int sideMask; //!< which sides take part in this phase (x: left|right, y: bottom|top)
+    unsigned* done; //!< [kHaloSides] block-completion counters in MY memory (zero between launches)
 };
 
-//! grid = 4 blocks (one per side).  Packs the lines into the neighbour's arena, then publishes the epoch.
-__global__ void __launch_bounds__(1024) halo_push_kernel(const __grid_constant__ HaloPushArgs a)
+constexpr int kHaloBlocksPerSide = 24;
+
+//! grid = (blocks per side, 4 sides).  Packs the lines into the neighbour's arena; the last block of a side
+//! to finish publishes the epoch.
+__global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ HaloPushArgs a)
 {
-    const int side = blockIdx.x;
+    const int side = blockIdx.y;
     if (!(a.sideMask & (1 << side)) || a.peerSlot[side] == nullptr)
         return;
     const HaloLineDesc& d = a.send[side];
     const long perField = long(d.nLines) * d.lineLen;
     const long total = perField * d.nFields;
     double* dst = a.peerSlot[side];
-    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+    for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
         const int f = int(i / perField);
         const long r = i % perField;
         const int line = int(r / d.lineLen);
@@ -78,10 +82,15 @@ __global__ void __launch_bounds__(1024) halo_push_kernel(const __grid_constant__
         const double* src = a.fieldPitch ? a.fields[0] + size_t(f) * a.fieldPitch : a.fields[f];
         dst[i] = src[d.firstLine[line] + k * d.stride];
     }
+    __threadfence_system(); // my peer stores are visible system-wide before I report completion
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
-        stReleaseSys(a.peerFlag[side], a.epoch[side]);
+        const unsigned prev = atomicAdd(a.done + side, 1u);
+        if (prev == gridDim.x - 1) { // every block of this side has fenced its stores
+            a.done[side] = 0;
+            __threadfence_system();
+            stReleaseSys(a.peerFlag[side], a.epoch[side]);
+        }
     }
 }
 
@@ -96,10 +105,10 @@ struct HaloUnpackArgs {
     int* errorFlag; //!< set to 1 if a neighbour never showed up (spin timeout)
 };
 
-//! grid = 4 blocks.  Waits until the neighbour's message of this epoch has landed, then scatters it.
-__global__ void __launch_bounds__(1024) halo_unpack_kernel(const __grid_constant__ HaloUnpackArgs a)
+//! grid = (blocks per side, 4 sides).  Waits until the neighbour's message of this epoch has landed, then scatters it.
+__global__ void __launch_bounds__(256) halo_unpack_kernel(const __grid_constant__ HaloUnpackArgs a)
 {
-    const int side = blockIdx.x;
+    const int side = blockIdx.y;
     if (!(a.sideMask & (1 << side)) || a.mySlot[side] == nullptr)
         return;
     __shared__ int ok;
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(1024) halo_unpack_kernel(const __grid_constant
     const long perField = long(d.nLines) * d.lineLen;
     const long total = perField * d.nFields;
     const double* src = a.mySlot[side];
-    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+    for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
         const int f = int(i / perField);
         const long r = i % perField;
         const int line = int(r / d.lineLen);

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(128) subcycle_strip(const __grid_constant__ Su
     loadRow(a.v, CG * ey0, vl);
 
     for (int ey = ey0; ey < ey1; ++ey) {
-        const size_t e = size_t(ey) * g.nx + ex;
+        const size_t e = size_t(ey) * g.nxs + ex;
 #pragma unroll
         for (int jy = 1; jy <= CG; ++jy) {
             loadRow(a.u, CG * ey + jy, ul + jy * NR);

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     };
     auto issueP = [&](int row) {
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nx + ex;
+            const size_t en = size_t(row) * g.nxs + ex;
 #pragma unroll
             for (int q = 0; q < 9; ++q)
                 cpAsync8(&st.P[q][lane], a.Pa + size_t(q) * Npad + en);
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     };
     auto issueS = [&](int row) {
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nx + ex;
+            const size_t en = size_t(row) * g.nxs + ex;
 #pragma unroll
             for (int j = 0; j < DGs; ++j) {
                 cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     }
 
     for (int ey = ey0; ey < ey1; ++ey) {
-        const size_t e = size_t(ey) * g.nx + ex;
+        const size_t e = size_t(ey) * g.nxs + ex;
         const bool ice = active && (__ldg(a.landmask + e) != 0);
         // ---- the two upper node rows of u, v from the staging buffer ----
         cpAsyncWait<3>();

@@ -20,11 +20,13 @@ template <int DG>
 __global__ void setup_transport_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
     TransportOpPtrs op, int nelem)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(nelem))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(nelem))
         return;
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
     double c[4][2];
-    elementCorners(vx, vy, g.nx, int(e % g.nx), int(e / g.nx), g.spherical, c);
+    elementCorners(vx, vy, g.nx, ix, iy, g.spherical, c);
     transportOpsOfElement<DG>(c, g.spherical, op, e);
 }
 
@@ -32,21 +34,24 @@ template <int CG, int DGA>
 __global__ void setup_momentum_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
     MomentumOpPtrs op, int nelem)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(nelem))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(nelem))
         return;
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
     double c[4][2];
-    elementCorners(vx, vy, g.nx, int(e % g.nx), int(e / g.nx), g.spherical, c);
+    elementCorners(vx, vy, g.nx, ix, iy, g.spherical, c);
     momentumOpsOfElement<CG, DGA>(c, g.spherical, op, e);
 }
 
 //! element size h = sqrt(area) (ParametricMesh.hpp:276-299), used by the BBM stress update
 __global__ void helem_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy, double* __restrict__ h)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
-    h[e] = sqrt(elementArea(vx, vy, g.nx, int(e % g.nx), int(e / g.nx)));
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    h[size_t(iy) * g.nxs + ix] = sqrt(elementArea(vx, vy, g.nx, ix, iy));
 }
 
 //! lumped mass per node of the CG(CGM) space, CGGP Gauss points per direction; gather in the
@@ -103,13 +108,13 @@ __global__ void lumpedmass_kernel(GridDims g, int cgnx, int cgny, int cgs, const
 template <int CG>
 __global__ void nodemask_kernel(GridDims g, const uint8_t* __restrict__ dirmask, uint8_t* __restrict__ nodemask)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
-    const uint8_t dm = dirmask[e];
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const uint8_t dm = dirmask[size_t(iy) * g.nxs + ix];
     if (!dm)
         return;
-    const int ix = int(e % g.nx), iy = int(e / g.nx);
     for (int j = 0; j <= CG; ++j) {
         if (dm & 1)
             nodemask[size_t(CG * iy) * g.cgs + CG * ix + j] = 1;
@@ -142,7 +147,7 @@ __global__ void sshgrad_cg1_kernel(GridDims g, int cg1s, const double* __restric
                 const int ex = c - 1 + b, lx = 1 - b;
                 if (ex < 0 || ex >= g.nx)
                     continue;
-                const size_t e = size_t(ey) * g.nx + ex;
+                const size_t e = size_t(ey) * g.nxs + ex;
                 const size_t n0 = size_t(ey) * cg1s + ex;
                 const double loc[4] = { cgSSH[n0], cgSSH[n0 + 1], cgSSH[n0 + cg1s], cgSSH[n0 + cg1s + 1] };
                 const int i = ly * 2 + lx;
@@ -212,9 +217,10 @@ __global__ void gaussconst_kernel(GridDims g, PhysParams p, const double* __rest
     double* __restrict__ outA, double* __restrict__ outB, double scaleA)
 {
     constexpr int Q = GS * GS;
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
+    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
     double h[DGA], a[DGA];
 #pragma unroll
     for (int j = 0; j < DGA; ++j) {
@@ -266,22 +272,23 @@ __global__ void iostress_kernel(GridDims g, PhysParams p, const double* __restri
 }
 
 //! AoS (row-major N x ncomp, the ModelArray layout) <-> planes
-__global__ void aos2planes_kernel(size_t N, size_t Npad, int ncomp, int nplanes, const double* __restrict__ aos,
-    double* __restrict__ planes)
+__global__ void aos2planes_kernel(GridDims g, int ncomp, int nplanes, const double* __restrict__ aos, double* __restrict__ planes)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= N)
+    const size_t d = size_t(blockIdx.x) * blockDim.x + threadIdx.x; // dense element index of the host array
+    if (d >= size_t(g.N))
         return;
+    const size_t e = size_t(d / g.nx) * g.nxs + (d % g.nx);
     for (int c = 0; c < nplanes; ++c)
-        planes[size_t(c) * Npad + e] = (c < ncomp) ? aos[e * ncomp + c] : 0.0;
+        planes[size_t(c) * g.Npad + e] = (c < ncomp) ? aos[d * ncomp + c] : 0.0;
 }
-__global__ void planes2aos_kernel(size_t N, size_t Npad, int ncomp, const double* __restrict__ planes, double* __restrict__ aos)
+__global__ void planes2aos_kernel(GridDims g, int ncomp, const double* __restrict__ planes, double* __restrict__ aos)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= N)
+    const size_t d = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (d >= size_t(g.N))
         return;
+    const size_t e = size_t(d / g.nx) * g.nxs + (d % g.nx);
     for (int c = 0; c < ncomp; ++c)
-        aos[e * ncomp + c] = planes[size_t(c) * Npad + e];
+        aos[d * ncomp + c] = planes[size_t(c) * g.Npad + e];
 }
 
 } // namespace nsdg

@@ -3,8 +3,8 @@
  *
  * Layout (chosen for one-thread-per-element / one-warp-per-32-elements kernels):
  *  - element fields are structure-of-arrays "planes": component c of element e lives at
- *    f[c * Npad + e], e = ix + nx*iy.  A warp reading 32 consecutive elements of one plane
- *    touches 256 contiguous bytes.  (The reference's DGVector is element-major AoS,
+ *    f[c * Npad + e], e = ix + nxs*iy with the row stride nxs = nx rounded up to 32, so a warp
+ *    reading 32 consecutive elements of one plane touches 256 contiguous, aligned bytes.  (The reference's DGVector is element-major AoS,
  *    dynamics/src/include/dgVector.hpp:89-91; the C ABI converts at the boundary.)
  *  - per-element operator matrices (general / parametric meshes) are planes too: matrix
  *    entry k of element e at op[k * Npad + e].
@@ -55,7 +55,8 @@ struct PhysParams {
 //! Grid geometry shared by all kernels (passed by value)
 struct GridDims {
     int nx, ny; //!< elements
-    int N, Npad; //!< nx*ny and plane pitch
+    int nxs; //!< element row stride (nx rounded up to 32: every element row starts 256-B aligned)
+    int N, Npad; //!< nx*ny (dense count) and plane pitch (>= nxs*ny); element (ix,iy) lives at ix + nxs*iy
     int CG; //!< CG degree
     int cgnx, cgny; //!< CG*nx+1, CG*ny+1
     int cgs; //!< padded CG row stride

@@ -33,10 +33,11 @@ __global__ void cg2dg_kernel(GridDims g, const double* __restrict__ vx, const do
     const double* __restrict__ cg, TransportOpPtrs op, double* __restrict__ dg)
 {
     constexpr int G = gp1d(DG), Q = G * G, NR = CG + 1, ND = NR * NR;
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
-    const int ix = int(e % g.nx), iy = int(e / g.nx);
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
     double loc[ND];
     for (int r = 0; r < NR; ++r)
         for (int c = 0; c < NR; ++c)
@@ -107,7 +108,7 @@ __global__ void dg2cg_kernel(GridDims g, const double* __restrict__ src, double*
             if ((eys[a] % 2 == 1) != (pass == 0))
                 continue;
             for (int b = 0; b < nxs; ++b) {
-                const size_t e = size_t(eys[a]) * g.nx + exs[b];
+                const size_t e = size_t(eys[a]) * g.nxs + exs[b];
                 const int q = lys[a] * L + lxs[b];
                 double At = 0;
                 for (int j = 0; j < DG; ++j)
@@ -168,7 +169,7 @@ __global__ void normalvel_kernel(GridDims g, const double* __restrict__ vx, cons
             const int ey = jy - 1 + side;
             if (ey < 0 || ey >= g.ny)
                 continue;
-            const size_t e = size_t(ey) * g.nx + ix;
+            const size_t e = size_t(ey) * g.nxs + ix;
             if (!isIce(landmask, e))
                 continue;
             double ex[ED], eyv[ED];
@@ -190,7 +191,7 @@ __global__ void normalvel_kernel(GridDims g, const double* __restrict__ vx, cons
             const int ex_ = jx - 1 + side;
             if (ex_ < 0 || ex_ >= g.nx)
                 continue;
-            const size_t e = size_t(iy) * g.nx + ex_;
+            const size_t e = size_t(iy) * g.nxs + ex_;
             if (!isIce(landmask, e))
                 continue;
             double ex[ED], eyv[ED];
@@ -215,10 +216,11 @@ __global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, c
     const double* __restrict__ phi, double* __restrict__ phiup)
 {
     constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
-    const int ix = int(e % g.nx), iy = int(e / g.nx);
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
     const size_t Npad = g.Npad;
     const bool ice = isIce(landmask, e);
     double up[DG];
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, c
         const int niy = iy + (side == 2 ? 1 : (side == 0 ? -1 : 0));
         if (nix < 0 || nix >= g.nx || niy < 0 || niy >= g.ny)
             return;
-        const size_t en = size_t(niy) * g.nx + nix;
+        const size_t en = size_t(niy) * g.nxs + nix;
         if (!ice || !isIce(landmask, en))
             return;
         // c1 = left/bottom element, c2 = right/top element of the edge
@@ -385,9 +387,10 @@ __global__ void heun_kernel(size_t n, double* __restrict__ y, const double* __re
 // ------------------------------------------------------------------------------------------
 template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ f, int mode, double maxv, double minv)
 {
-    const size_t e = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= size_t(g.N))
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
         return;
+    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
     double d[DG];
 #pragma unroll
     for (int j = 0; j < DG; ++j)
