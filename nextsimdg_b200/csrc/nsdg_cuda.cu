@@ -334,7 +334,10 @@ public:
         }
 
         // ---- strips and deferred-line buffers ----
-        R = 16;
+        // element rows per warp strip: 16 on large grids; fewer on small ones so that the strip kernel still
+        // offers ~12 warps to each of the 148 SMs (a 128 x 128 grid has only 4 strips per element row)
+        nsx = (nx + 31) / 32;
+        R = int(std::max<long>(1, std::min<long>(16, long(nsx) * ny / (148 * 12))));
         if (const char* env = std::getenv("NSDG_STRIP_ROWS")) // tuning knob: element rows per warp strip
             R = std::max(1, std::atoi(env));
         nsx = (nx + 31) / 32;
