@@ -21,6 +21,7 @@
 
 #include "nsdg_momentum.cuh"
 #include "nsdg_momentum_uniform.cuh"
+#include "nsdg_momentum_uniform_bbm.cuh"
 #include "nsdg_halo.cuh"
 #include "nsdg_prepare.cuh"
 
@@ -88,7 +89,8 @@ public:
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
     DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
-    bool fastUniformMEVP = false;
+    bool fastUniformMEVP = false, fastUniformBBM = false;
+    DevBuf<double> gaussC; //!< uniform BBM: Pmax in the Gauss points
     // halo exchange (partitioned domain)
     DevBuf<unsigned char> arena; //!< my receive arena: [side][parity] payload slots + flags
     HaloArenaLayout arenaLayout {};
@@ -345,6 +347,17 @@ public:
         hbuf.alloc(size_t(nsy) * 2 * nx * NR * 2);
         vbuf.alloc(size_t(nsx) * 2 * ny * NR * 2);
         fastUniformMEVP = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6;
+        fastUniformBBM = uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6;
+        if (std::getenv("NSDG_NO_FAST_UNIFORM")) // testing knob: generic strip kernel on the uniform operator set
+            fastUniformMEVP = fastUniformBBM = false;
+        if (fastUniformBBM) {
+            for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
+                f->alloc(ncg);
+            gaussC.alloc(size_t(Q) * Npad);
+            if constexpr (CG == 2 && DGA == 6)
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_ubbm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUbbmSmemBytes)));
+        }
         if (fastUniformMEVP) {
             for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
@@ -803,6 +816,63 @@ public:
         a.DeltaMin2 = p.DeltaMin * p.DeltaMin;
         return a;
     }
+    UniformBBMArgs makeUniformBBMArgs(double deltaT) const
+    {
+        UniformBBMArgs a {};
+        a.g = g;
+        a.R = R;
+        a.nsx = nsx;
+        a.nsy = nsy;
+        a.s11 = s11;
+        a.s12 = s12;
+        a.s22 = s22;
+        a.damage = damage;
+        a.gH = gaussA;
+        a.gE = gaussB;
+        a.gP = gaussC;
+        a.landmask = d_landmask;
+        a.u = u;
+        a.v = v;
+        a.avgU = avgU;
+        a.avgV = avgV;
+        a.dte = ncC1;
+        a.cA = ncCA;
+        a.ax = ncRx;
+        a.ay = ncRy;
+        a.uO = uO;
+        a.vO = vO;
+        a.ilm = ncIlm;
+        a.nodemask = d_nodemask;
+        a.hbuf = hbuf;
+        a.vbuf = vbuf;
+        a.dx = hvx[1] - hvx[0];
+        a.dy = hvy[g.nx + 1] - hvy[0];
+        a.deltaT = deltaT;
+        a.dtfc = deltaT * p.fc;
+        a.invNSteps = 1.0 / double(cfg.nsteps);
+        a.cosA = p.cosOceanAngle;
+        a.sinA = p.sinOceanAngle;
+        a.young = p.young;
+        a.nu0 = p.nu0;
+        a.lambda0 = p.undamaged_time_relaxation_sigma;
+        a.tan_phi = p.tan_phi;
+        const double hel = std::sqrt(a.dx * a.dy); // smesh.h(i) = sqrt(area), ParametricMesh.hpp:299
+        const double scale = std::sqrt(0.1 / hel);
+        a.cohScale = p.C_lab * scale;
+        a.comprScale = p.compr_strength * scale;
+        a.invTdK = 1.0 / (hel * std::sqrt(2. * (1. + p.nu0) * p.rho_ice));
+        a.dunitK = deltaT / (1. - p.nu0 * p.nu0);
+        return a;
+    }
+    void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)
+    {
+        if constexpr (CG == 2 && DGA == 6) {
+            if (!linesOnly)
+                subcycle_strip_ubbm<0><<<nbStrip, 32 * kUbbmWarps, kUbbmSmemBytes, stream>>>(ba);
+            if (!stripOnly)
+                subcycle_lines_ubbm<<<blocksFor(nLine), 128, 0, stream>>>(ba);
+        }
+    }
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
         if constexpr (CG == 2 && DGA == 6)
@@ -839,6 +909,7 @@ public:
     {
         const SubcycleArgs a = makeArgs(deltaT);
         const UniformArgs ua = makeUniformArgs(deltaT);
+        const UniformBBMArgs ba = makeUniformBBMArgs(deltaT);
         const unsigned nbStripF = (unsigned(nsx) * nsy + 3) / 4;
         const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
         auto body = [&]() {
@@ -846,6 +917,8 @@ public:
                 if (fastUniformMEVP) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
+                } else if (fastUniformBBM) {
+                    launchPairFastBBM(ba, nbStripF, nLineF);
                 } else if (cfg.rheology == NSDG_BBM)
                     launchSubcycle<NSDG_BBM>(a);
                 else
@@ -909,6 +982,8 @@ public:
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
             if (fastUniformMEVP)
                 launchStripFast(ua, nbStrip);
+            else if (fastUniformBBM)
+                launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, true, false);
             else if (cfg.rheology == NSDG_BBM)
                 launchStrip<NSDG_BBM>(a, nbStrip);
             else
@@ -916,6 +991,8 @@ public:
             NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
             if (fastUniformMEVP)
                 launchLinesFast(ua, nLine);
+            else if (fastUniformBBM)
+                launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, false, true);
             else if (cfg.rheology == NSDG_BBM)
                 subcycle_lines<CG, NSDG_BBM><<<blocksFor(nLine), 128, 0, stream>>>(a);
             else
@@ -983,7 +1060,13 @@ public:
             deltaT = dt / double(cfg.nsteps);
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgU, 0, cgBytes, stream));
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgV, 0, cgBytes, stream));
-            gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, 1.0);
+            if (fastUniformBBM) {
+                gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
+                nodeconst_bbm_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
+                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
+                launches += 1;
+            } else
+                gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, 1.0);
         }
         launches += 1;
         lastDeltaT = deltaT;

@@ -1,0 +1,583 @@
+/*
+ * nsdg_momentum_uniform_bbm.cuh -- the BBM subcycle on a UNIFORM RECTANGULAR mesh (CG2 / DG8 / DG6),
+ * organised like the mEVP kernel of nsdg_momentum_uniform.cuh: warp strips, register carry, deferred
+ * lines, cp.async staging one element row ahead, compile-time unit-square operators, direct
+ * Gauss-point evaluation of the velocity gradient, per-node constants.
+ *
+ * Sweeps reproduced (results equal to rounding; re-association + x/y -> x * rcp(y) only):
+ *   projectVelocityToStrain  dynamics/src/CGDynamicsKernel.cpp:300-337
+ *   stressUpdateHighOrder    dynamics/src/include/BBMStressUpdateStep.hpp:31-196
+ *   stressDivergence         dynamics/src/CGDynamicsKernel.cpp:340-398
+ *   updateMomentum           dynamics/src/include/BrittleCGDynamicsKernel.hpp:206-254 (quirk Q3 kept)
+ *   applyBoundaries          dynamics/src/CGDynamicsKernel.cpp:439-444
+ * Once per timestep (constant over the subcycles):
+ *   Gauss points: h = max(h_q,0), expC = exp(C(1-a)), Pmax = P0 h^2.5 expC     (BBMStressUpdateStep.hpp:54-57,76-90)
+ *   nodes: dte = deltaT/(rho cgH), cA = cgA F_ocean, ax = cgA F_atm |ua| ua - rho cgH g dSSH/dx, ay, 1/lumped mass
+ */
+#pragma once
+#include "nsdg_momentum_uniform.cuh"
+
+namespace nsdg {
+
+struct UniformBBMArgs {
+    GridDims g;
+    int R, nsx, nsy;
+    double *s11, *s12, *s22; //!< DG8 planes
+    double* damage; //!< DG6 planes
+    const double *gH, *gE, *gP; //!< Gauss-point planes: h, expC, Pmax
+    const uint8_t* landmask;
+    double *u, *v, *avgU, *avgV;
+    const double *dte, *cA, *ax, *ay, *uO, *vO, *ilm; //!< per-node constants
+    const uint8_t* nodemask;
+    double *hbuf, *vbuf;
+    double dx, dy;
+    double deltaT, dtfc, invNSteps, cosA, sinA;
+    // rheology constants (MEBParameters.hpp:40-65) and their per-mesh products
+    double young, nu0, lambda0, tan_phi;
+    double cohScale, comprScale; //!< C_lab * sqrt(0.1/h_el), compr_strength * sqrt(0.1/h_el)
+    double invTdK; //!< 1 / (h_el sqrt(2 (1+nu) rho_ice)):  1/td = sqrt(elasticity) * invTdK
+    double dunitK; //!< deltaT / (1 - nu^2)
+};
+
+//! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240)
+__global__ void nodeconst_bbm_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
+    const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
+    const double* __restrict__ gy, const double* __restrict__ lm, double* __restrict__ dte, double* __restrict__ cA,
+    double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ ilm)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
+    const double H = cgH[n], A = cgA[n];
+    const double dragAtm = A * p.F_atm * hypot(uA[n], vA[n]);
+    dte[n] = deltaT / (p.rho_ice * H);
+    cA[n] = A * p.F_ocean;
+    ax[n] = dragAtm * uA[n] - p.rho_ice * H * p.gravity * gx[n];
+    ay[n] = dragAtm * vA[n] - p.rho_ice * H * p.gravity * gy[n];
+    ilm[n] = 1.0 / lm[n];
+}
+
+//! Gauss-point constants of the BBM law: h, exp(C(1-a)), Pmax (uniform path: one extra plane saves the pow)
+template <int DGA, int GS>
+__global__ void gaussconst_bbm3_kernel(GridDims g, PhysParams p, const double* __restrict__ hice, const double* __restrict__ cice,
+    double* __restrict__ outH, double* __restrict__ outE, double* __restrict__ outP)
+{
+    constexpr int Q = GS * GS;
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
+    double h[DGA], a[DGA];
+#pragma unroll
+    for (int j = 0; j < DGA; ++j) {
+        h[j] = hice[size_t(j) * g.Npad + e];
+        a[j] = cice[size_t(j) * g.Npad + e];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double hq = 0, aq = 0;
+#pragma unroll
+        for (int j = 0; j < DGA; ++j) {
+            const double w = PSI(GS, j, q);
+            if (w != 0.0) {
+                hq = (j == 0) ? h[0] * w : fma(h[j], w, hq);
+                aq = (j == 0) ? a[0] * w : fma(a[j], w, aq);
+            }
+        }
+        hq = fmax(hq, 0.0);
+        aq = fmin(fmax(aq, 0.0), 1.0);
+        const double expC = exp(p.compaction_param * (1.0 - aq));
+        outH[size_t(q) * g.Npad + e] = hq;
+        outE[size_t(q) * g.Npad + e] = expC;
+        outP[size_t(q) * g.Npad + e] = p.P0 * pow(hq, p.exponent_compression_factor + 1.) * expC;
+    }
+}
+
+//! brittle momentum update of one node from the per-node constants; returns the pre-boundary value for the mean
+__device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, double dte, double cA, double ax, double ay,
+    double uO, double vO, double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew,
+    double& uAvg, double& vAvg)
+{
+    const double du = uO - un, dv = vO - vn;
+    const double cPrime = cA * sqrt(du * du + dv * dv);
+    const double alpha = 1.0 + dte * (cPrime * a.cosA);
+    const double beta = a.dtfc + dte * cPrime * a.sinA;
+    const double rDenom = 1.0 / (alpha * alpha + beta * beta);
+    const double X = dSx * ilm + ax + cPrime * (uO * a.cosA - vO * a.sinA); // gradX + tauX
+    const double Y = dSy * ilm + ay + cPrime * (vO * a.cosA + uO * a.sinA); // gradY + tauY
+    unew = (alpha * un + beta * vn + dte * (alpha * X + beta * Y)) * rDenom;
+    vnew = (alpha * vn - beta * un + dte * (alpha * Y + beta * X)) * rDenom; // quirk Q3: "+ beta X" as in the reference
+    uAvg = unew * a.invNSteps; // taken before applyBoundaries, as in the reference
+    vAvg = vnew * a.invNSteps;
+    if (dirichlet) {
+        unew = 0.0;
+        vnew = 0.0;
+    }
+}
+
+struct UbbmStage {
+    double G[27][32]; //!< h, expC, Pmax in the 9 Gauss points
+    double S[24][32];
+    double D[6][32];
+    double2 ND[2][7][32];
+    double2 UV[2][2][32];
+    double UVr[2][2];
+    double pad[2];
+};
+constexpr int kUbbmWarps = 4;
+constexpr size_t kUbbmSmemBytes = sizeof(UbbmStage) * kUbbmWarps;
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const __grid_constant__ UniformBBMArgs a)
+{
+    constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
+        return;
+    UbbmStage& st = reinterpret_cast<UbbmStage*>(smemRaw)[threadIdx.x >> 5];
+    const GridDims& g = a.g;
+    const int sx = w % a.nsx, sy = w / a.nsx;
+    const int exRaw = 32 * sx + lane;
+    const bool active = exRaw < g.nx;
+    const int ex = active ? exRaw : g.nx - 1;
+    const bool lastLane = active && (lane == 31 || exRaw == g.nx - 1);
+    const bool loadsRight = (lane == 31) || (exRaw >= g.nx - 1);
+    const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
+    const size_t Npad = g.Npad;
+    const int col0 = CG * ex;
+    const double idx = 1.0 / a.dx, idy = 1.0 / a.dy;
+
+    auto issueUV = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
+                cpAsync16(&st.UV[0][k][lane], a.u + n);
+                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                if (loadsRight) {
+                    cpAsync8(&st.UVr[0][k], a.u + n + CG);
+                    cpAsync8(&st.UVr[1][k], a.v + n + CG);
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueG = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nxs + ex;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                cpAsync8(&st.G[q][lane], a.gH + size_t(q) * Npad + en);
+                cpAsync8(&st.G[9 + q][lane], a.gE + size_t(q) * Npad + en);
+                cpAsync8(&st.G[18 + q][lane], a.gP + size_t(q) * Npad + en);
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueS = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nxs + ex;
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
+            }
+#pragma unroll
+            for (int j = 0; j < DGA; ++j)
+                cpAsync8(&st.D[j][lane], a.damage + size_t(j) * Npad + en);
+        }
+        cpAsyncCommit();
+    };
+    auto issueND = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + k) * g.cgs + col0;
+                cpAsync16(&st.ND[k][0][lane], a.dte + n);
+                cpAsync16(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16(&st.ND[k][2][lane], a.ax + n);
+                cpAsync16(&st.ND[k][3][lane], a.ay + n);
+                cpAsync16(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                prefetchL2(a.avgU + n); // read-modify-written at the end of the row
+                prefetchL2(a.avgV + n);
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    double carryX[2] = { 0.0, 0.0 }, carryY[2] = { 0.0, 0.0 };
+    double ul[9], vl[9];
+    issueUV(ey0);
+    issueS(ey0); // order of first use in the row: UV, S (+damage), G, ND
+    issueG(ey0);
+    issueND(ey0);
+    {
+        const size_t n = size_t(CG * ey0) * g.cgs + col0;
+        const double2 tu = *reinterpret_cast<const double2*>(a.u + n), tv = *reinterpret_cast<const double2*>(a.v + n);
+        ul[0] = tu.x;
+        ul[1] = tu.y;
+        vl[0] = tv.x;
+        vl[1] = tv.y;
+        double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+        if (loadsRight) {
+            ru = a.u[n + CG];
+            rv = a.v[n + CG];
+        }
+        ul[2] = ru;
+        vl[2] = rv;
+    }
+
+    for (int ey = ey0; ey < ey1; ++ey) {
+        const size_t e = size_t(ey) * g.nxs + ex;
+        const bool ice = active && (__ldg(a.landmask + e) != 0);
+        cpAsyncWait<3>();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
+            ul[3 * (k + 1)] = tu.x;
+            ul[3 * (k + 1) + 1] = tu.y;
+            vl[3 * (k + 1)] = tv.x;
+            vl[3 * (k + 1) + 1] = tv.y;
+            double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+            if (loadsRight) {
+                ru = st.UVr[0][k];
+                rv = st.UVr[1][k];
+            }
+            ul[3 * (k + 1) + 2] = ru;
+            vl[3 * (k + 1) + 2] = rv;
+        }
+        issueUV(ey + 1);
+
+        // ---- velocity gradient in the 9 Gauss points (as in the mEVP kernel) ----
+        double e11[9], e12[9], e22[9];
+        {
+            double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3];
+            static_for<3>([&](auto JY) {
+                static_for<3>([&](auto QX) {
+                    constexpr int jy = decltype(JY)::value, qx = decltype(QX)::value;
+                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                    static_for<3>([&](auto JX) {
+                        constexpr int jx = decltype(JX)::value;
+                        constexpr double l = kUnitOps.L[jx][qx], lp = kUnitOps.Lp[jx][qx];
+                        if constexpr (l != 0.0) {
+                            s0 = fma(l, ul[jy * 3 + jx], s0);
+                            s2 = fma(l, vl[jy * 3 + jx], s2);
+                        }
+                        if constexpr (lp != 0.0) {
+                            s1 = fma(lp, ul[jy * 3 + jx], s1);
+                            s3 = fma(lp, vl[jy * 3 + jx], s3);
+                        }
+                    });
+                    Au[jy][qx] = s0;
+                    Adu[jy][qx] = s1;
+                    Av[jy][qx] = s2;
+                    Adv[jy][qx] = s3;
+                });
+            });
+            static_for<3>([&](auto QY) {
+                static_for<3>([&](auto QX) {
+                    constexpr int qy = decltype(QY)::value, qx = decltype(QX)::value, q = qy * 3 + qx;
+                    double ux = 0, uy = 0, vx = 0, vy = 0;
+                    static_for<3>([&](auto JY) {
+                        constexpr int jy = decltype(JY)::value;
+                        constexpr double l = kUnitOps.L[jy][qy], lp = kUnitOps.Lp[jy][qy];
+                        if constexpr (l != 0.0) {
+                            ux = fma(l, Adu[jy][qx], ux);
+                            vx = fma(l, Adv[jy][qx], vx);
+                        }
+                        if constexpr (lp != 0.0) {
+                            uy = fma(lp, Au[jy][qx], uy);
+                            vy = fma(lp, Av[jy][qx], vy);
+                        }
+                    });
+                    e11[q] = ice ? ux * idx : 0.0;
+                    e22[q] = ice ? vy * idy : 0.0;
+                    e12[q] = ice ? 0.5 * (uy * idy + vx * idx) : 0.0;
+                });
+            });
+        }
+
+        // ---- stress and damage coefficients of the row, then the BBM law point by point:
+        //      e** become the updated Gauss-point stresses, dG the updated damage ----
+        cpAsyncWait<3>();
+        double dG[9];
+        {
+            double s11c[DGs], s12c[DGs], s22c[DGs], dc[DGA];
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                s11c[j] = st.S[j][lane];
+                s12c[j] = st.S[8 + j][lane];
+                s22c[j] = st.S[16 + j][lane];
+            }
+#pragma unroll
+            for (int j = 0; j < DGA; ++j)
+                dc[j] = st.D[j][lane];
+            cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
+            static_for<9>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
+                double d = evalGauss<DGA, 3, q>(dc);
+                const double h = st.G[q][lane], expC = st.G[9 + q][lane], Pmax = st.G[18 + q][lane];
+                const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+                d = fmin(fmax(d, 1e-12), 1.0);
+                double sigma_n = 0.5 * (t11 + t22);
+                const double de = d * expC, de2 = de * de;
+                const double tv = a.lambda0 * (de2 * de2);
+                const double tildeP = (sigma_n < 0.0) ? fmin(-Pmax / sigma_n, 1.0) : 0.0;
+                const double mult = tv / (tv + (1.0 - tildeP) * a.deltaT);
+                const double elasticity = h * a.young * d * expC;
+                const double Dunit = a.dunitK * elasticity;
+                t11 = (t11 + Dunit * (g11 + a.nu0 * g22)) * mult;
+                t22 = (t22 + Dunit * (a.nu0 * g11 + g22)) * mult;
+                t12 = (t12 + Dunit * g12 * (1.0 - a.nu0)) * mult;
+                sigma_n = 0.5 * (t11 + t22);
+                const double tau = sqrt(0.25 * (t11 - t22) * (t11 - t22) + t12 * t12);
+                const double cohesion = a.cohScale * h, compr = a.comprScale * h;
+                const double mc = tau + a.tan_phi * sigma_n;
+                double dcrit = (mc > 0.0) ? cohesion / mc : 1.0;
+                if (sigma_n < -compr)
+                    dcrit = -compr / sigma_n;
+                dcrit = fmin(dcrit, 1.0);
+                const double relax = (1.0 - dcrit) * a.deltaT * (sqrt(elasticity) * a.invTdK);
+                dG[q] = d - d * relax;
+                e11[q] = t11 - t11 * relax;
+                e12[q] = t12 - t12 * relax;
+                e22[q] = t22 - t22 * relax;
+            });
+        }
+
+        // ---- damage projection (iMJwPSI_dam = psi_j w / m_j on a rectangle, j < 6) ----
+        static_for<DGA>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            double acc = 0.0;
+            static_for<9>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                constexpr double b = kUnitOps.B[j][q];
+                if constexpr (b != 0.0)
+                    acc = fma(b, dG[q], acc);
+            });
+            if (active)
+                a.damage[size_t(j) * Npad + e] = acc;
+        });
+
+        // ---- per stress component: project, store, accumulate the divergence contributions ----
+        double Tx[9], Ty[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            Tx[k] = Ty[k] = 0.0;
+        auto component = [&](double* plane, const double (&r)[9], auto COMP) {
+            constexpr int comp = decltype(COMP)::value;
+            double s[DGs];
+            static_for<DGs>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                double acc = 0.0;
+                static_for<9>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    constexpr double b = kUnitOps.B[j][q];
+                    if constexpr (b != 0.0)
+                        acc = fma(b, r[q], acc);
+                });
+                s[j] = acc;
+                if (active)
+                    plane[size_t(j) * Npad + e] = acc;
+            });
+            if (ice) {
+                static_for<9>([&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    double d1 = 0.0, d2 = 0.0;
+                    static_for<DGs>([&](auto J) {
+                        constexpr int j = decltype(J)::value;
+                        constexpr double c1 = kUnitOps.D1[k][j], c2 = kUnitOps.D2[k][j];
+                        if constexpr (c1 != 0.0 && comp != 2)
+                            d1 = fma(c1, s[j], d1);
+                        if constexpr (c2 != 0.0 && comp != 0)
+                            d2 = fma(c2, s[j], d2);
+                    });
+                    if constexpr (comp == 0)
+                        Tx[k] = fma(d1, a.dy, Tx[k]);
+                    if constexpr (comp == 1) {
+                        Tx[k] = fma(d2, a.dx, Tx[k]);
+                        Ty[k] = fma(d1, a.dy, Ty[k]);
+                    }
+                    if constexpr (comp == 2)
+                        Ty[k] = fma(d2, a.dx, Ty[k]);
+                });
+            }
+        };
+        component(a.s11, e11, std::integral_constant<int, 0> {});
+        component(a.s12, e12, std::integral_constant<int, 1> {});
+        component(a.s22, e22, std::integral_constant<int, 2> {});
+        issueS(ey + 1);
+        issueG(ey + 1);
+
+        // ---- raw contributions to the deferred lines ----
+        if (active && lane == 0 && sx > 0) {
+            double* vb = a.vbuf + ((size_t(sx - 1) * 2 + 1) * g.ny + ey) * (NR * 2);
+#pragma unroll
+            for (int jy = 0; jy < NR; ++jy) {
+                vb[jy * 2 + 0] = Tx[jy * NR];
+                vb[jy * 2 + 1] = Ty[jy * NR];
+            }
+        }
+        if (lastLane) {
+            double* vb = a.vbuf + ((size_t(sx) * 2 + 0) * g.ny + ey) * (NR * 2);
+#pragma unroll
+            for (int jy = 0; jy < NR; ++jy) {
+                vb[jy * 2 + 0] = Tx[jy * NR + CG];
+                vb[jy * 2 + 1] = Ty[jy * NR + CG];
+            }
+        }
+        const bool bottomDeferred = (ey == ey0) && (sy > 0);
+        if (active && bottomDeferred) {
+            double* hb = a.hbuf + ((size_t(sy - 1) * 2 + 1) * g.nx + ex) * (NR * 2);
+#pragma unroll
+            for (int jx = 0; jx < NR; ++jx) {
+                hb[jx * 2 + 0] = Tx[jx];
+                hb[jx * 2 + 1] = Ty[jx];
+            }
+        }
+        if (active && ey == ey1 - 1) {
+            double* hb = a.hbuf + ((size_t(sy) * 2 + 0) * g.nx + ex) * (NR * 2);
+#pragma unroll
+            for (int jx = 0; jx < NR; ++jx) {
+                hb[jx * 2 + 0] = Tx[CG * NR + jx];
+                hb[jx * 2 + 1] = Ty[CG * NR + jx];
+            }
+        }
+#pragma unroll
+        for (int jy = 0; jy < NR; ++jy) {
+            const double lx = __shfl_up_sync(FULL, Tx[jy * NR + CG], 1);
+            const double ly = __shfl_up_sync(FULL, Ty[jy * NR + CG], 1);
+            if (lane > 0) {
+                Tx[jy * NR] = lx + Tx[jy * NR];
+                Ty[jy * NR] = ly + Ty[jy * NR];
+            }
+        }
+        // ---- momentum update of the completed nodes ----
+        cpAsyncWait<3>();
+#pragma unroll
+        for (int jy = 0; jy < CG; ++jy) {
+            const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+            const double2 dte = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], ax = st.ND[jy][2][lane], ay = st.ND[jy][3][lane];
+            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const uchar2 msk = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + n0));
+            double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
+            if (jy == 0) {
+                sx0 += carryX[0];
+                sy0 += carryY[0];
+                sx1 += carryX[1];
+                sy1 += carryY[1];
+            }
+            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            double2 un, vn, ua, va;
+            momentumNodeUniformBBM(a, dte.x, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+                d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
+            momentumNodeUniformBBM(a, dte.y, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+                d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y, ua.y, va.y);
+            const bool rowSkip = !active || (jy == 0 && bottomDeferred);
+            const bool skip0 = rowSkip || (lane == 0 && sx > 0);
+            if (!rowSkip) {
+                if (!skip0) {
+                    *reinterpret_cast<double2*>(a.u + n0) = un;
+                    *reinterpret_cast<double2*>(a.v + n0) = vn;
+                    double2 au = *reinterpret_cast<const double2*>(a.avgU + n0), av = *reinterpret_cast<const double2*>(a.avgV + n0);
+                    au.x += ua.x;
+                    au.y += ua.y;
+                    av.x += va.x;
+                    av.y += va.y;
+                    *reinterpret_cast<double2*>(a.avgU + n0) = au;
+                    *reinterpret_cast<double2*>(a.avgV + n0) = av;
+                } else {
+                    a.u[n0 + 1] = un.y;
+                    a.v[n0 + 1] = vn.y;
+                    a.avgU[n0 + 1] += ua.y;
+                    a.avgV[n0 + 1] += va.y;
+                }
+            }
+        }
+        issueND(ey + 1);
+        carryX[0] = Tx[CG * NR];
+        carryX[1] = Tx[CG * NR + 1];
+        carryY[0] = Ty[CG * NR];
+        carryY[1] = Ty[CG * NR + 1];
+#pragma unroll
+        for (int jx = 0; jx < NR; ++jx) {
+            ul[jx] = ul[CG * NR + jx];
+            vl[jx] = vl[CG * NR + jx];
+        }
+    }
+    cpAsyncWait<0>();
+}
+
+//! deferred-line nodes for the uniform BBM path
+__global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant__ UniformBBMArgs a)
+{
+    constexpr int CG = 2, NR = 3;
+    const GridDims& g = a.g;
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long nH = long(a.nsy) * g.cgnx;
+    const long nV = long(a.nsx) * g.cgny;
+    if (t >= nH + nV)
+        return;
+    int c, r;
+    double sumX = 0.0, sumY = 0.0;
+    if (t < nH) {
+        const int L = int(t / g.cgnx) + 1;
+        c = int(t % g.cgnx);
+        r = min(CG * a.R * L, CG * g.ny);
+        const int jx = c % CG, exr = c / CG;
+        const bool above = r < CG * g.ny;
+        auto add = [&](int side, int ex, int j) {
+            const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
+            sumX += hb[0];
+            sumY += hb[1];
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !above)
+                break;
+            if (jx == 0 && exr > 0)
+                add(side, exr - 1, CG);
+            if (exr < g.nx)
+                add(side, exr, jx);
+        }
+    } else {
+        const long tv = t - nH;
+        const int L = int(tv / g.cgny) + 1;
+        r = int(tv % g.cgny);
+        c = min(CG * 32 * L, CG * g.nx);
+        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
+            return;
+        const int jy = r % CG, eyr = r / CG;
+        const bool right = c < CG * g.nx;
+        auto add = [&](int side, int ey, int j) {
+            const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
+            sumX += vb[0];
+            sumY += vb[1];
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !right)
+                break;
+            if (jy == 0 && eyr > 0)
+                add(side, eyr - 1, CG);
+            add(side, eyr, jy);
+        }
+    }
+    const size_t n = size_t(r) * g.cgs + c;
+    const bool d = __ldg(a.nodemask + n) & 1;
+    double un, vn, ua, va;
+    momentumNodeUniformBBM(a, __ldg(a.dte + n), __ldg(a.cA + n), __ldg(a.ax + n), __ldg(a.ay + n), __ldg(a.uO + n), __ldg(a.vO + n),
+        __ldg(a.ilm + n), d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
+    a.u[n] = un;
+    a.v[n] = vn;
+    a.avgU[n] += ua;
+    a.avgV[n] += va;
+}
+
+} // namespace nsdg
