@@ -32,7 +32,8 @@ typedef struct nsdg_handle_s* nsdg_handle;
 /* Rheology = which reference kernel is replaced. */
 enum nsdg_rheology {
     NSDG_MEVP = 0, /* MEVPDynamicsKernel  (dynamics/src/include/MEVPDynamicsKernel.hpp:17-37) */
-    NSDG_BBM = 1 /* BBMDynamicsKernel   (dynamics/src/include/BBMDynamicsKernel.hpp:18-44)  */
+    NSDG_BBM = 1, /* BBMDynamicsKernel   (dynamics/src/include/BBMDynamicsKernel.hpp:18-44)  */
+    NSDG_FREEDRIFT = 2 /* FreeDriftDynamicsKernel (dynamics/src/include/FreeDriftDynamicsKernel.hpp:19-96) */
 };
 
 /* Named fields of DynamicsKernel::setData / getDG0Data / getDGData
@@ -116,6 +117,15 @@ int nsdg_step(nsdg_handle h, double dt_seconds);
 /* Replaces: getDG0Data(name) (ncomp == 1; DynamicsKernel.hpp:114-126, CGDynamicsKernel.cpp:92-118)
  * and getDGData(name) (ncomp == dgadv; DynamicsKernel.hpp:134-156). */
 int nsdg_get_field(nsdg_handle h, int field, double* host, int ncomp);
+
+/* Device-resident synthetic forcing: evaluates the reference's benchmark atmosphere and ocean
+ * (physics/src/modules/AtmosphereBoundaryModule/BenchmarkAtmosphere.cpp:38-74: moving cyclone;
+ *  physics/src/modules/OceanBoundaryModule/BenchmarkOcean.cpp:27-36: steady gyre, ssh = 0; cell-corner
+ *  coordinates of physics/src/BenchmarkCoordinates.cpp:20-42) directly on the GPU and feeds them through the
+ * same DG0 -> CG path as nsdg_set_field(UWIND/VWIND/UOCEAN/VOCEAN/SSH), so that no forcing crosses PCIe.
+ *   elapsed_seconds : time since the first update (tst.start - t0)
+ *   domain_x/y      : extent of the GLOBAL domain in metres (the reference hard-codes 512e3) */
+int nsdg_set_benchmark_forcing(nsdg_handle h, double elapsed_seconds, double domain_x, double domain_y);
 
 /* The whole of MEVPDynamics::update / BBMDynamics::update in ONE call (MEVPDynamics.cpp:59-87,
  * BBMDynamics.cpp:66-101): uploads the 7 (8) input HFields from pinned staging with async copies,

@@ -14,7 +14,7 @@ There is no CPU fallback anywhere in this package: if the CUDA library is missin
 usable, the calls raise.
 """
 from .capi import NsdgError, load_library, library_path  # noqa: F401
-from .dynamics import CUDABBMDynamics, CUDAMEVPDynamics, CUDADynamicsBase  # noqa: F401
+from .dynamics import CUDABBMDynamics, CUDADynamicsBase, CUDAFreeDriftDynamics, CUDAMEVPDynamics  # noqa: F401
 
 __all__ = [
     "NsdgError",
@@ -22,5 +22,6 @@ __all__ = [
     "library_path",
     "CUDAMEVPDynamics",
     "CUDABBMDynamics",
+    "CUDAFreeDriftDynamics",
     "CUDADynamicsBase",
 ]

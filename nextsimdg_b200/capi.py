@@ -10,7 +10,7 @@ import numpy as np
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 
 # enum nsdg_rheology / nsdg_field (include/nsdg.h)
-MEVP, BBM = 0, 1
+MEVP, BBM, FREEDRIFT = 0, 1, 2
 HICE, CICE, DAMAGE, U, V, UWIND, VWIND, UOCEAN, VOCEAN, SSH, TAUX, TAUY = range(12)
 FIELD_IDS = {
     "hice": HICE, "cice": CICE, "damage": DAMAGE, "u": U, "v": V, "uwind": UWIND, "vwind": VWIND,
@@ -53,6 +53,7 @@ SIGNATURES = {
     "nsdg_set_field": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "nsdg_step": (c_int, [c_void_p, c_double]),
     "nsdg_get_field": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "nsdg_set_benchmark_forcing": (c_int, [c_void_p, c_double, c_double, c_double]),
     "nsdg_update": (c_int, [c_void_p, POINTER(UpdateIO), c_double]),
     "nsdg_get_landmask": (c_int, [c_void_p, c_void_p]),
     "nsdg_get_dirichlet": (c_int, [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),

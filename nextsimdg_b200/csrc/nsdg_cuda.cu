@@ -45,6 +45,7 @@ public:
     virtual void timeKernels(int n, float* stripMs, float* linesMs) = 0;
     virtual void getInternal(const std::string& name, double* host, size_t cap, size_t* count) = 0;
     virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
+    virtual void benchmarkForcing(double elapsed, double Lx, double Ly) = 0;
     virtual void haloExport(unsigned char* handle) = 0;
     virtual void haloConnect(int side, const unsigned char* handle) = 0;
     virtual void haloReady() = 0;
@@ -472,6 +473,34 @@ public:
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
+    //! BenchmarkAtmosphere::update + BenchmarkOcean::setData evaluated on the device, then the DG0 -> CG path of setData
+    void benchmarkForcing(double elapsed, double Lx, double Ly) override
+    {
+        requireMesh();
+        const int gnx = cfg.global_nx > 0 ? cfg.global_nx : g.nx, gny = cfg.global_nx > 0 ? cfg.global_ny : g.ny;
+        const int gi0 = cfg.global_nx > 0 ? cfg.box_x0 - (cfg.neighbour[NSDG_LEFT] >= 0 ? 1 : 0) : 0;
+        const int gj0 = cfg.global_nx > 0 ? cfg.box_y0 - (cfg.neighbour[NSDG_BOTTOM] >= 0 ? 1 : 0) : 0;
+        const double dx = Lx / gnx, dy = Ly / gny;
+        const double timeFraction = elapsed / 86400.0, cycloneDuration = 5.;
+        const double x0c = gnx * dx * 0.5 * (1 + timeFraction / cycloneDuration);
+        const double y0c = gny * dy * 0.5 * (1 + timeFraction / cycloneDuration);
+        const double alpha = 72. / 180. * M_PI;
+        double* pl = scratchDG; // 4 of its DGA >= 3 planes... use tmp1/tmp2 as well to be safe for DGA = 3
+        double* uw = pl;
+        double* vw = pl + g.Npad;
+        double* uo = tmp1;
+        double* vo = tmp1.p + g.Npad;
+        benchforcing_kernel<<<blocksFor(g.N), 128, 0, stream>>>(g, gi0, gj0, dx, dy, x0c, y0c, cos(alpha), sin(alpha), gnx * dx,
+            gny * dy, uw, vw, uo, vo);
+        const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
+        dg2cg_kernel<CG, 1><<<nb, 128, 0, stream>>>(g, uw, uA, -INFINITY, INFINITY);
+        dg2cg_kernel<CG, 1><<<nb, 128, 0, stream>>>(g, vw, vA, -INFINITY, INFINITY);
+        dg2cg_kernel<CG, 1><<<nb, 128, 0, stream>>>(g, uo, uO, -INFINITY, INFINITY);
+        dg2cg_kernel<CG, 1><<<nb, 128, 0, stream>>>(g, vo, vO, -INFINITY, INFINITY);
+        NSDG_CUDA_CHECK(cudaMemsetAsync(ssh, 0, size_t(g.Npad) * 8, stream));
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
     void cgToDG0(const double* cgSrc, double* host)
     {
         cg2dg_kernel<CG, DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgSrc, topA, scratchDG);
@@ -506,7 +535,9 @@ public:
             if (ncomp != 1)
                 throw std::runtime_error("nsdg_get_field: ice-ocean stress is exported as DG0 cell means");
             const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
-            if (bbm)
+            if (cfg.rheology == NSDG_FREEDRIFT)
+                iostress_kernel<NSDG_BBM><<<nb, 128, 0, stream>>>(g, p, u, v, uO, vO, taux, tauy);
+            else if (bbm)
                 iostress_kernel<NSDG_BBM><<<nb, 128, 0, stream>>>(g, p, avgU, avgV, uO, vO, taux, tauy);
             else
                 iostress_kernel<NSDG_MEVP><<<nb, 128, 0, stream>>>(g, p, u, v, uO, vO, taux, tauy);
@@ -1024,6 +1055,20 @@ public:
         const bool bbm = cfg.rheology == NSDG_BBM;
         const size_t cgBytes = ncg * 8;
         NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+        if (cfg.rheology == NSDG_FREEDRIFT) { // FreeDriftDynamicsKernel::update, FreeDriftDynamicsKernel.hpp:43-50
+            freedrift_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(g, p, uO, vO, uA, vA, d_nodemask, u, v);
+            launches += 1;
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+            exchangeNodes(u, v);
+            prepareAdvection<DGA>(u, v, topA, velx, vely, nvX, nvY);
+            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, cice, tmp1, tmp2);
+            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, hice, tmp1, tmp2);
+            limit(cice, 3, 1.0, 0.0);
+            limit(hice, 2, 0.0, 0.0);
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
+            NSDG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
+            return;
+        }
         // ---- advection + limiters (DynamicsKernel.hpp:160-172) ----
         exchangeNodes(u, v); // partitioned: non-owned node lines come from their owners (no-op otherwise)
         if (bbm)
@@ -1255,7 +1300,7 @@ public:
 
 static HandleBase* makeHandle(const nsdg_config& c)
 {
-    if (c.rheology != NSDG_MEVP && c.rheology != NSDG_BBM)
+    if (c.rheology != NSDG_MEVP && c.rheology != NSDG_BBM && c.rheology != NSDG_FREEDRIFT)
         throw std::runtime_error("nsdg_create: unknown rheology");
     if (c.nsteps < 1)
         throw std::runtime_error("nsdg_create: nsteps must be >= 1");
@@ -1350,6 +1395,14 @@ int nsdg_step(nsdg_handle h, double dt_seconds)
 {
     NSDG_TRY
     H(h)->step(dt_seconds);
+    NSDG_CATCH
+}
+int nsdg_set_benchmark_forcing(nsdg_handle h, double elapsed_seconds, double domain_x, double domain_y)
+{
+    NSDG_TRY
+    if (!(domain_x > 0) || !(domain_y > 0))
+        throw std::runtime_error("nsdg_set_benchmark_forcing: the domain extent must be positive");
+    H(h)->benchmarkForcing(elapsed_seconds, domain_x, domain_y);
     NSDG_CATCH
 }
 int nsdg_update(nsdg_handle h, const nsdg_update_io* io, double dt_seconds)

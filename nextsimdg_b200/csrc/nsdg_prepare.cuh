@@ -263,12 +263,51 @@ __global__ void iostress_kernel(GridDims g, PhysParams p, const double* __restri
         const double absocn = sqrt(uR * uR + vR * vR);
         taux[n] = p.F_ocean * absocn * uR;
         tauy[n] = p.F_ocean * absocn * vR;
-    } else { // u, v = avgU, avgV
+    } else { // BBM: u, v = avgU, avgV ; free drift: u, v (FreeDriftDynamicsKernel.hpp:70-83)
         const double uR = uO[n] - u[n], vR = vO[n] - v[n];
         const double cPrime = p.F_ocean * hypot(uR, vR);
         taux[n] = cPrime * (uR * p.cosOceanAngle - vR * p.sinOceanAngle);
         tauy[n] = cPrime * (vR * p.cosOceanAngle + uR * p.sinOceanAngle);
     }
+}
+
+//! FreeDriftDynamicsKernel::updateMomentum + applyBoundaries (FreeDriftDynamicsKernel.hpp:43-68)
+__global__ void freedrift_kernel(GridDims g, PhysParams p, const double* __restrict__ uO, const double* __restrict__ vO,
+    const double* __restrict__ uA, const double* __restrict__ vA, const uint8_t* __restrict__ nodemask, double* __restrict__ u,
+    double* __restrict__ v)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.cgnx) * g.cgny)
+        return;
+    const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
+    const double NansenNumber = sqrt(p.F_atm / p.F_ocean);
+    double un = uO[n] + NansenNumber * (uA[n] * p.cosOceanAngle - vA[n] * p.sinOceanAngle);
+    double vn = vO[n] + NansenNumber * (-uA[n] * p.sinOceanAngle + vA[n] * p.cosOceanAngle);
+    if (nodemask[n] & 1)
+        un = vn = 0.0;
+    u[n] = un;
+    v[n] = vn;
+}
+
+//! The reference's benchmark forcing per element (cell lower-left corner coordinates x = i dx, y = j dy of the
+//! GLOBAL grid): BenchmarkAtmosphere.cpp:38-74 (cyclone centred at x0c, y0c) and BenchmarkOcean.cpp:27-36.
+__global__ void benchforcing_kernel(GridDims g, int gi0, int gj0, double dx, double dy, double x0c, double y0c, double cosa,
+    double sina, double Lx, double Ly, double* __restrict__ uw, double* __restrict__ vw, double* __restrict__ uo,
+    double* __restrict__ vo)
+{
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
+    const double x = double(gi0 + ix) * dx, y = double(gj0 + iy) * dy;
+    const double xp = x - x0c, yp = y - y0c;
+    const double A = 1e-5, k = 1e-5, vMax = 30.0, vMaxOcean = 0.01;
+    const double scale = A * exp(-k * hypot(xp, yp));
+    uw[e] = -scale * vMax * (cosa * xp + sina * yp);
+    vw[e] = -scale * vMax * (-sina * xp + cosa * yp);
+    uo[e] = vMaxOcean * (2 * (y / Ly) - 1);
+    vo[e] = vMaxOcean * (1 - 2 * (x / Lx));
 }
 
 //! AoS (row-major N x ncomp, the ModelArray layout) <-> planes

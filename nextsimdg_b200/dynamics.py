@@ -165,6 +165,10 @@ class CUDADynamicsBase:
     def step(self, dt: float):
         check(self._lib.nsdg_step(self._h, float(dt)))
 
+    def set_benchmark_forcing(self, elapsed_seconds: float, domain_x: float = 512e3, domain_y: float = 512e3):
+        """Benchmark{Atmosphere,Ocean} evaluated on the device (no forcing crosses PCIe)."""
+        check(self._lib.nsdg_set_benchmark_forcing(self._h, float(elapsed_seconds), float(domain_x), float(domain_y)))
+
     def subcycles(self, n: int) -> float:
         ms = ctypes.c_float()
         check(self._lib.nsdg_subcycles(self._h, int(n), ctypes.byref(ms)))
@@ -245,3 +249,34 @@ class CUDABBMDynamics(CUDADynamicsBase):
         st = super().getState()
         st.update({"hice": self.getDGData("hice"), "cice": self.getDGData("cice"), "damage": self.getDGData("damage")})
         return st
+
+
+class CUDAFreeDriftDynamics(CUDADynamicsBase):
+    """Drop-in for Nextsim::FreeDriftDynamics (core/src/modules/DynamicsModule/include/FreeDriftDynamics.hpp:26-83)."""
+
+    rheology = capi.FREEDRIFT
+
+    def getName(self):
+        return "CUDAFreeDriftDynamics"
+
+    def setData(self, ms: dict):
+        # quirk: the reference passes isSpherical = false to kernel.initialise whatever the coordinates are
+        # (FreeDriftDynamics.hpp:69), after scaling lon/lat to radians
+        ms2 = dict(ms)
+        if self.checkSpherical(ms):
+            ms2["coords"] = np.asarray(ms["coords"], dtype=np.float64) * RADIANS
+            ms2.pop("longitude")
+            ms2.pop("latitude")
+            ms2["x"] = ms2["y"] = np.zeros_like(np.asarray(ms["mask"], dtype=np.float64))
+        super().setData(ms2)
+
+    def update(self, tst_seconds: float):
+        # FreeDriftDynamics::update sets hice, cice, uocean, vocean only (FreeDriftDynamics.hpp:39-55)
+        s = self.shared
+        for name in ("hice", "cice", "uocean", "vocean"):
+            self._set(name, s[name])
+        self.step(tst_seconds)
+        np.copyto(s["hice"], self.getDG0Data("hice"))
+        np.copyto(s["cice"], self.getDG0Data("cice"))
+        self.uice = self.getDG0Data("u")
+        self.vice = self.getDG0Data("v")

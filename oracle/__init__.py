@@ -82,7 +82,7 @@ class OracleDynamics:
         self.L = load()
         self.rheology = rheology
         self.dgadv, self.cgdegree, self.nsteps = dgadv, cgdegree, nsteps
-        self.h = self.L.nso_create(1 if rheology == "bbm" else 0, dgadv, cgdegree, nsteps)
+        self.h = self.L.nso_create({"mevp": 0, "bbm": 1, "freedrift": 2}[rheology], dgadv, cgdegree, nsteps)
         if not self.h:
             raise RuntimeError("oracle: unsupported (dgadv, cgdegree)")
         self.shared = {}
@@ -125,7 +125,8 @@ class OracleDynamics:
         self._set("cice", s["cice"])
         if self.rheology == "bbm":
             self._set("damage", self.damage)
-        for name in ("uwind", "vwind", "uocean", "vocean", "ssh"):
+        # FreeDriftDynamics::update passes only the ocean velocity (FreeDriftDynamics.hpp:44-45)
+        for name in (("uocean", "vocean") if self.rheology == "freedrift" else ("uwind", "vwind", "uocean", "vocean", "ssh")):
             self._set(name, s[name])
         self._chk(self.L.nso_update(self.h, float(dt)))
         np.copyto(s["hice"], self.getDG0Data("hice"))

@@ -31,7 +31,7 @@
 
 namespace nso {
 
-enum Rheology { MEVP = 0, BBM = 1 };
+enum Rheology { MEVP = 0, BBM = 1, FREEDRIFT = 2 };
 
 //! DynamicsParameters.hpp:32-50, VPParameters.hpp:22-23, MEBParameters.hpp:40-65
 struct Params {
@@ -822,9 +822,27 @@ public:
             throw std::runtime_error("unknown sweep " + which);
     }
 
-    //! VPCGDynamicsKernel.hpp:63-94 / BrittleCGDynamicsKernel.hpp:91-136
+    //! FreeDriftDynamicsKernel::updateMomentum, FreeDriftDynamicsKernel.hpp:57-68
+    void updateMomentumFreeDrift()
+    {
+        const double NansenNumber = sqrt(params.F_atm / params.F_ocean);
+        for (size_t i = 0; i < u.size(); ++i) {
+            u[i] = uOcean[i] + NansenNumber * (uAtmos[i] * cosOceanAngle - vAtmos[i] * sinOceanAngle);
+            v[i] = vOcean[i] + NansenNumber * (-uAtmos[i] * sinOceanAngle + vAtmos[i] * cosOceanAngle);
+        }
+    }
+
+    //! VPCGDynamicsKernel.hpp:63-94 / BrittleCGDynamicsKernel.hpp:91-136 / FreeDriftDynamicsKernel.hpp:43-50
     void update(double dt) override
     {
+        if (rheology == FREEDRIFT) {
+            updateMomentumFreeDrift();
+            dirichletZero(u);
+            dirichletZero(v);
+            dgtransport->template prepareAdvection<CG>(u, v);
+            advect(dt);
+            return;
+        }
         if (rheology == MEVP) {
             dgtransport->template prepareAdvection<CG>(u, v);
             advect(dt);
@@ -869,7 +887,12 @@ public:
         taux.resize(u.size());
         tauy.resize(u.size());
         for (size_t i = 0; i < u.size(); ++i) {
-            if (rheology == MEVP) {
+            if (rheology == FREEDRIFT) { // FreeDriftDynamicsKernel.hpp:70-83
+                const double uR = uOcean[i] - u[i], vR = vOcean[i] - v[i];
+                const double cPrime = params.F_ocean * std::hypot(uR, vR);
+                taux[i] = cPrime * (uR * cosOceanAngle - vR * sinOceanAngle);
+                tauy[i] = cPrime * (vR * cosOceanAngle + uR * sinOceanAngle);
+            } else if (rheology == MEVP) {
                 const double uR = u[i] - uOcean[i], vR = v[i] - vOcean[i];
                 const double absocn = sqrt(SQR(uR) + SQR(vR));
                 taux[i] = params.F_ocean * absocn * uR;

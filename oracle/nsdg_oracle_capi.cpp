@@ -19,7 +19,7 @@ thread_local std::string lastError;
 
 IDynOracle* make(int rheology, int dgadv, int cg)
 {
-    const Rheology r = rheology == 1 ? BBM : MEVP;
+    const Rheology r = rheology == 1 ? BBM : (rheology == 2 ? FREEDRIFT : MEVP);
     if (dgadv == 6 && cg == 2)
         return new DynOracle<6, 2>(r);
     if (dgadv == 3 && cg == 2)

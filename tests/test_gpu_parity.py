@@ -305,3 +305,44 @@ def test_multi_gpu_halo_exchange_matches_single_domain(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:])
     assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_free_drift_module():
+    """Nextsim::FreeDriftDynamics (FreeDriftDynamics.hpp:26-83, FreeDriftDynamicsKernel.hpp:43-68): third IDynamics
+    implementation; the module passes only the ocean velocity, so the ice follows the ocean and is advected."""
+    import oracle
+    from nextsimdg_b200 import CUDAFreeDriftDynamics, synthetic
+
+    ms = synthetic.para_state(30, 24, distort=0.05, irregular_mask=True)
+    f = synthetic.smooth_forcing(30, 24)
+    gpu, ref = CUDAFreeDriftDynamics(nsteps=1), oracle.OracleDynamics("freedrift", 6, 2, 1)
+    for d in (gpu, ref):
+        d.setData(ms)
+        d.shared = {"hice": np.ascontiguousarray(ms["hice"][..., 0]), "cice": np.ascontiguousarray(ms["cice"][..., 0]),
+                    **{k: v.copy() for k, v in f.items()}}
+        for _ in range(3):
+            d.update(900.0)
+    ice = ms["mask"].astype(bool)
+    for n, g, r in (("u", gpu.uice, ref.uice), ("v", gpu.vice, ref.vice), ("hice", gpu.shared["hice"], ref.shared["hice"]),
+                    ("cice", gpu.shared["cice"], ref.shared["cice"])):
+        assert rel(g[ice], r[ice]) < TOL_SWEEP, n
+    assert np.abs(gpu.uice[ice]).max() > 0  # the ice does move with the ocean
+
+
+def test_device_resident_benchmark_forcing_equals_host_forcing():
+    """nsdg_set_benchmark_forcing evaluates Benchmark{Atmosphere,Ocean} on the GPU; same CG forcing as uploading the
+    host-evaluated fields (synthetic.benchmark_forcing restates the same reference formulas)."""
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, L, t = 48, 512e3, 7200.0
+    ms = synthetic.benchmark_box(n, L=L)
+    f = synthetic.benchmark_forcing(n, t, L=L)
+    a, b = CUDAMEVPDynamics(nsteps=1), CUDAMEVPDynamics(nsteps=1)
+    a.setData(ms)
+    b.setData(ms)
+    for k in ("uwind", "vwind", "uocean", "vocean", "ssh"):
+        a._set(k, f[k])
+    b.set_benchmark_forcing(t, L, L)
+    for name in ("uAtmos", "vAtmos", "uOcean", "vOcean"):
+        x, y = a.internal(name), b.internal(name)
+        assert np.abs(x - y).max() <= 1e-13 * np.abs(x).max(), name
