@@ -243,8 +243,13 @@ def run_gpu(args):
     local_elems = dyn.nx * dyn.ny
     pair_ms = strip_ms.value + lines_ms.value
     achieved = b_alg * local_elems / (pair_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # per-launch DRAM bytes of the strip kernel from the committed ncu --set full capture of this workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload_name(args)]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
+                "traffic": traffic, "algorithmic_bytes_per_launch": b_alg * local_elems, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
                 "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_alg,
                 "peak_source": peak_src}
 

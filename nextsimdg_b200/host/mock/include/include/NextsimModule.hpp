@@ -1,0 +1,2 @@
+/* forwarding header: the nextsimdg tree includes its headers as "include/X.hpp" */
+#include "../NextsimModule.hpp"
