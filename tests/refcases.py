@@ -72,6 +72,9 @@ def run_case(d, ms, forcings, dt):
     out = {"uice": d.uice, "vice": d.vice, "taux": d.taux, "tauy": d.tauy, "hice": d.shared["hice"], "cice": d.shared["cice"]}
     if getattr(d, "rheology", "") == "bbm" or getattr(d, "_uses_damage", False):
         out["damage"] = d.damage
+    if getattr(d, "rheology", "") in ("freedrift", 2):
+        # FreeDriftDynamics::update never exports the ice-ocean stress (FreeDriftDynamics.hpp:39-58)
+        out.pop("taux"), out.pop("tauy")
     for n in INTERNALS:
         out[n] = d.internal(n)
     return {k: np.array(v, dtype=np.float64, copy=True) for k, v in out.items() if v is not None}
