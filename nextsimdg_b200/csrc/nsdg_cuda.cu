@@ -341,6 +341,25 @@ public:
         // offers ~12 warps to each of the 148 SMs (a 128 x 128 grid has only 4 strips per element row)
         nsx = (nx + 31) / 32;
         R = int(std::max<long>(1, std::min<long>(16, long(nsx) * ny / (148 * 12))));
+        if (R == 16) {
+            // large grid: pick R in [12, 24] against wave quantisation.  The strip kernels run 4 warps per block and
+            // `bps` blocks per SM (3 for the uniform mEVP kernel, 2 for the 246/255-register ones); with B blocks the
+            // last of ceil(B / slots) rounds is partly empty.  Horizontal deferred lines cost ~ 1.07 / R of a strip pass.
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg.device);
+            const bool mevpFast = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !std::getenv("NSDG_NO_FAST_UNIFORM");
+            const double slots = double(sms) * (mevpFast ? 3 : 2);
+            double best = -1.0;
+            for (int r = 12; r <= 24; ++r) {
+                const long blocks = (long(nsx) * ((ny + r - 1) / r) + 3) / 4;
+                const double waves = blocks / slots;
+                const double score = waves / std::ceil(waves) / (1.0 + 1.07 / r);
+                if (score > best + 1e-9) {
+                    best = score;
+                    R = r;
+                }
+            }
+        }
         if (const char* env = std::getenv("NSDG_STRIP_ROWS")) // tuning knob: element rows per warp strip
             R = std::max(1, std::atoi(env));
         nsx = (nx + 31) / 32;

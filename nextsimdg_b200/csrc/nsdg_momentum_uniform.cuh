@@ -276,9 +276,24 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         vl[2] = rv;
     }
 
+    // mask bytes travel one element row ahead in registers (their use right after the load cost 18 % of the
+    // stall samples, profiles/r1_strip_v3_cpasync.txt)
+    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
+    uchar2 nmNext[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (__ldg(a.landmask + e) != 0);
+        const bool ice = active && (lmNext != 0);
+        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        if (ey + 1 < ey1) {
+            lmNext = __ldg(a.landmask + e + g.nxs);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+        }
         // ---- the two upper node rows of u, v from the staging buffer ----
         cpAsyncWait<3>();
 #pragma unroll
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
             const double2 c1 = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], rx = st.ND[jy][2][lane], ry = st.ND[jy][3][lane];
             const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
-            const uchar2 msk = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + n0));
+            const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];

@@ -234,9 +234,23 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
         vl[2] = rv;
     }
 
+    // mask bytes travel one element row ahead in registers
+    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
+    uchar2 nmNext[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (__ldg(a.landmask + e) != 0);
+        const bool ice = active && (lmNext != 0);
+        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        if (ey + 1 < ey1) {
+            lmNext = __ldg(a.landmask + e + g.nxs);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+        }
         cpAsyncWait<3>();
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -467,7 +481,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
             const double2 dte = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], ax = st.ND[jy][2][lane], ay = st.ND[jy][3][lane];
             const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
-            const uchar2 msk = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + n0));
+            const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];
