@@ -22,6 +22,7 @@
 #include "nsdg_momentum.cuh"
 #include "nsdg_momentum_uniform.cuh"
 #include "nsdg_momentum_uniform_bbm.cuh"
+#include "nsdg_momentum_param.cuh"
 #include "nsdg_halo.cuh"
 #include "nsdg_prepare.cuh"
 
@@ -90,7 +91,10 @@ public:
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
     DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
+    DevBuf<double> geo; // per-element geometry planes of the parametric fast path
     bool fastUniformMEVP = false, fastUniformBBM = false;
+    bool fastParamMEVP = false; //!< factored-operator kernel on non-uniform Cartesian meshes (nsdg_momentum_param.cuh)
+    bool fastMEVP() const { return fastUniformMEVP || fastParamMEVP; }
     DevBuf<double> gaussC; //!< uniform BBM: Pmax in the Gauss points
     // halo exchange (partitioned domain)
     DevBuf<unsigned char> arena; //!< my receive arena: [side][parity] payload slots + flags
@@ -378,12 +382,22 @@ public:
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
                     subcycle_strip_ubbm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUbbmSmemBytes)));
         }
-        if (fastUniformMEVP) {
+        fastParamMEVP = !uniform && !spherical && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
+            && !std::getenv("NSDG_NO_FAST_PARAM");
+        if (fastMEVP()) {
             for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
-            if constexpr (CG == 2 && DGA == 6)
+            if constexpr (CG == 2 && DGA == 6) {
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
                     subcycle_strip_umevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmevpSmemBytes)));
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_pmevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPmevpSmemBytes)));
+            }
+        }
+        if (fastParamMEVP) {
+            geo.alloc(size_t(kGeoPlanes) * Npad);
+            paramgeom_kernel<<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, geo);
+            NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
         timing.uniform_path = uniform ? 1 : 0;
         haloActive = false;
@@ -855,6 +869,7 @@ public:
         a.uO = uO;
         a.vO = vO;
         a.ilm = ncIlm;
+        a.geo = geo;
         a.nodemask = d_nodemask;
         a.hbuf = hbuf;
         a.vbuf = vbuf;
@@ -925,8 +940,13 @@ public:
     }
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
-        if constexpr (CG == 2 && DGA == 6)
-            subcycle_strip_umevp<0><<<nbStrip, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
+        if constexpr (CG == 2 && DGA == 6) {
+            if (fastParamMEVP) {
+                const unsigned nb = (unsigned(nsx) * nsy + kPmevpWarps - 1) / kPmevpWarps;
+                subcycle_strip_pmevp<0><<<nb, 32 * kPmevpWarps, kPmevpSmemBytes, stream>>>(ua);
+            } else
+                subcycle_strip_umevp<0><<<nbStrip, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
+        }
     }
     void launchLinesFast(const UniformArgs& ua, size_t nLine)
     {
@@ -964,7 +984,7 @@ public:
         const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
         auto body = [&]() {
             for (int i = 0; i < n; ++i) {
-                if (fastUniformMEVP) {
+                if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
                 } else if (fastUniformBBM) {
@@ -1030,7 +1050,7 @@ public:
         double ts = 0, tl = 0, th = 0;
         for (int i = 0; i < n; ++i) {
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
-            if (fastUniformMEVP)
+            if (fastMEVP())
                 launchStripFast(ua, nbStrip);
             else if (fastUniformBBM)
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, true, false);
@@ -1039,7 +1059,7 @@ public:
             else
                 launchStrip<NSDG_MEVP>(a, nbStrip);
             NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
-            if (fastUniformMEVP)
+            if (fastMEVP())
                 launchLinesFast(ua, nLine);
             else if (fastUniformBBM)
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, false, true);
@@ -1114,8 +1134,8 @@ public:
             NSDG_CUDA_CHECK(cudaMemcpyAsync(v0, v, cgBytes, cudaMemcpyDeviceToDevice, stream));
             deltaT = dt;
             gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(
-                g, p, hice, cice, gaussA, gaussB, fastUniformMEVP ? 1.0 / p.alpha : 1.0);
-            if (fastUniformMEVP) {
+                g, p, hice, cice, gaussA, gaussB, fastMEVP() ? 1.0 / p.alpha : 1.0);
+            if (fastMEVP()) {
                 nodeconst_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
                 launches += 1;

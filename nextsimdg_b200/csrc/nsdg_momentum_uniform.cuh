@@ -86,6 +86,7 @@ struct UniformArgs {
     const uint8_t* landmask;
     double *u, *v;
     const double *c1, *cA, *rx, *ry, *uO, *vO, *ilm; //!< per-node constants (nodeconst_kernel)
+    const double* geo; //!< parametric fast path: kGeoPlanes geometry planes (nsdg_momentum_param.cuh)
     const uint8_t* nodemask;
     double *hbuf, *vbuf;
     double dx, dy; //!< element size
