@@ -21,7 +21,6 @@
 
 #include "nsdg_momentum.cuh"
 #include "nsdg_momentum_uniform.cuh"
-#include "nsdg_momentum_uniform_bbm.cuh"
 #include "nsdg_momentum_param.cuh"
 #include "nsdg_halo.cuh"
 #include "nsdg_prepare.cuh"
@@ -94,7 +93,9 @@ public:
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
     bool fastUniformMEVP = false, fastUniformBBM = false;
     bool fastParamMEVP = false; //!< factored-operator kernel on non-uniform Cartesian meshes (nsdg_momentum_param.cuh)
+    bool fastParamBBM = false;
     bool fastMEVP() const { return fastUniformMEVP || fastParamMEVP; }
+    bool fastBBM() const { return fastUniformBBM || fastParamBBM; }
     DevBuf<double> gaussC; //!< uniform BBM: Pmax in the Gauss points
     // halo exchange (partitioned domain)
     DevBuf<unsigned char> arena; //!< my receive arena: [side][parity] payload slots + flags
@@ -374,15 +375,22 @@ public:
         fastUniformBBM = uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6;
         if (std::getenv("NSDG_NO_FAST_UNIFORM")) // testing knob: generic strip kernel on the uniform operator set
             fastUniformMEVP = fastUniformBBM = false;
-        if (fastUniformBBM) {
+        fastParamBBM = !uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6 && !cfg.force_general
+            && !std::getenv("NSDG_NO_FAST_PARAM");
+        if (fastBBM()) {
             for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
             gaussC.alloc(size_t(Q) * Npad);
-            if constexpr (CG == 2 && DGA == 6)
+            if constexpr (CG == 2 && DGA == 6) {
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
                     subcycle_strip_ubbm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUbbmSmemBytes)));
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_pbbm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pbbmSmemBytes<false>())));
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_pbbm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pbbmSmemBytes<true>())));
+            }
         }
-        fastParamMEVP = !uniform && !spherical && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
+        fastParamMEVP = !uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
             && !std::getenv("NSDG_NO_FAST_PARAM");
         if (fastMEVP()) {
             for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
@@ -391,12 +399,23 @@ public:
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
                     subcycle_strip_umevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmevpSmemBytes)));
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_pmevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPmevpSmemBytes)));
+                    subcycle_strip_pmevp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pmevpSmemBytes(false))));
+                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
+                    subcycle_strip_pmevp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pmevpSmemBytes(true))));
             }
         }
-        if (fastParamMEVP) {
-            geo.alloc(size_t(kGeoPlanes) * Npad);
-            paramgeom_kernel<<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, geo);
+        if (fastParamMEVP || fastParamBBM) {
+            geo.alloc(size_t(fastParamBBM ? geoPlanesBBM(spherical) : geoPlanes(spherical)) * Npad);
+            if (spherical)
+                paramgeom_kernel<true><<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, geo);
+            else
+                paramgeom_kernel<false><<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, geo);
+            if (fastParamBBM) {
+                if (spherical)
+                    paramgeom_bbm_kernel<true><<<blocksFor(N), 128, 0, stream>>>(g, p, helem, geo);
+                else
+                    paramgeom_bbm_kernel<false><<<blocksFor(N), 128, 0, stream>>>(g, p, helem, geo);
+            }
             NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
         timing.uniform_path = uniform ? 1 : 0;
@@ -927,12 +946,21 @@ public:
         a.comprScale = p.compr_strength * scale;
         a.invTdK = 1.0 / (hel * std::sqrt(2. * (1. + p.nu0) * p.rho_ice));
         a.dunitK = deltaT / (1. - p.nu0 * p.nu0);
+        a.geo = geo;
+        a.C_lab = p.C_lab;
+        a.compr_strength = p.compr_strength;
         return a;
     }
     void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            if (!linesOnly)
+            if (!linesOnly && fastParamBBM) {
+                const unsigned nb = (unsigned(nsx) * nsy + kPbbmWarps - 1) / kPbbmWarps;
+                if (g.spherical)
+                    subcycle_strip_pbbm<true><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<true>(), stream>>>(ba);
+                else
+                    subcycle_strip_pbbm<false><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<false>(), stream>>>(ba);
+            } else if (!linesOnly)
                 subcycle_strip_ubbm<0><<<nbStrip, 32 * kUbbmWarps, kUbbmSmemBytes, stream>>>(ba);
             if (!stripOnly)
                 subcycle_lines_ubbm<<<blocksFor(nLine), 128, 0, stream>>>(ba);
@@ -942,8 +970,11 @@ public:
     {
         if constexpr (CG == 2 && DGA == 6) {
             if (fastParamMEVP) {
-                const unsigned nb = (unsigned(nsx) * nsy + kPmevpWarps - 1) / kPmevpWarps;
-                subcycle_strip_pmevp<0><<<nb, 32 * kPmevpWarps, kPmevpSmemBytes, stream>>>(ua);
+                const unsigned nw = pmevpWarps(g.spherical), nb = (unsigned(nsx) * nsy + nw - 1) / nw;
+                if (g.spherical)
+                    subcycle_strip_pmevp<true><<<nb, 32 * nw, pmevpSmemBytes(true), stream>>>(ua);
+                else
+                    subcycle_strip_pmevp<false><<<nb, 32 * nw, pmevpSmemBytes(false), stream>>>(ua);
             } else
                 subcycle_strip_umevp<0><<<nbStrip, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
         }
@@ -987,7 +1018,7 @@ public:
                 if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
-                } else if (fastUniformBBM) {
+                } else if (fastBBM()) {
                     launchPairFastBBM(ba, nbStripF, nLineF);
                 } else if (cfg.rheology == NSDG_BBM)
                     launchSubcycle<NSDG_BBM>(a);
@@ -1052,7 +1083,7 @@ public:
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
             if (fastMEVP())
                 launchStripFast(ua, nbStrip);
-            else if (fastUniformBBM)
+            else if (fastBBM())
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, true, false);
             else if (cfg.rheology == NSDG_BBM)
                 launchStrip<NSDG_BBM>(a, nbStrip);
@@ -1061,7 +1092,7 @@ public:
             NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
             if (fastMEVP())
                 launchLinesFast(ua, nLine);
-            else if (fastUniformBBM)
+            else if (fastBBM())
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, false, true);
             else if (cfg.rheology == NSDG_BBM)
                 subcycle_lines<CG, NSDG_BBM><<<blocksFor(nLine), 128, 0, stream>>>(a);
@@ -1144,7 +1175,7 @@ public:
             deltaT = dt / double(cfg.nsteps);
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgU, 0, cgBytes, stream));
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgV, 0, cgBytes, stream));
-            if (fastUniformBBM) {
+            if (fastBBM()) {
                 gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
                 nodeconst_bbm_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);

@@ -27,16 +27,27 @@
  * instead of 360 doubles of operators; algorithmic traffic per element and subcycle 816 + 176 = 992 B
  * instead of 3840 B.  Node side, staging and deferred lines are those of nsdg_momentum_uniform.cuh.
  *
+ * SPHERICAL meshes (template flag SPH; ParametricMap.cpp:298-351): coordinates are (lon, lat) in radians, the mass
+ * matrix is weighted with w J cos(lat) (SphericalTools::massMatrix), every derivative carries 1/R, the lat-derivative
+ * a cos(lat), and the metric terms divM / iMM = (phi, J sin(lat) psi)/R couple u and v.  With D = diag(w J cos) the same
+ * rank-one identity holds; the planes then hold 1/(J cos), cos, sin per Gauss point (40 planes):
+ *      e11 = P[ (J d_lon u - J sin v) / (R J cos) ],   e22 = P[ J d_lat v / (R J) ],
+ *      e12 = P[ ( J d_lon v + cos J d_lat u + J sin u ) / (2 R J cos) ],   stress increment = B^ P[ r / cos ].
+ *
  * Same sweeps as the reference (CGDynamicsKernel.cpp:300-398, MEVPStressUpdateStep.hpp:30-118,
  * VPCGDynamicsKernel.hpp:132-172); parity: tests/test_gpu_vs_reference.py, tests/test_gpu_parity.py.
  */
 #pragma once
 #include "nsdg_momentum_uniform.cuh"
+#include "nsdg_momentum_uniform_bbm.cuh"
 #include "nsdg_setup.cuh"
 
 namespace nsdg {
 
-constexpr int kGeoPlanes = 22; //!< xxi[3] yxi[3] (per Gauss row qy), xeta[3] yeta[3] (per Gauss column qx), 1/J[9], gamma
+//! planes: xxi[3] yxi[3] (per Gauss row qy), xeta[3] yeta[3] (per Gauss column qx), 1/J[9] (spherical: 1/(J cos)), gamma,
+//! spherical only: cos(lat)[9], sin(lat)[9]
+constexpr int kGeoPlanes = 22, kGeoPlanesSph = 40;
+constexpr int geoPlanes(bool sph) { return sph ? kGeoPlanesSph : kGeoPlanes; }
 
 //! psi_8 = (x^2 - 1/12)(y^2 - 1/12), the Q2 tensor mode missing from DG8, at the 3 x 3 Gauss points
 NSDG_HD constexpr double psi8at(int q)
@@ -49,6 +60,7 @@ NSDG_HD constexpr double psi8at(int q)
  * Per-element geometry planes of the factored operators (one thread per element, once per mesh).
  * dxT/dyT/J exactly as ParametricTools::dxT/dyT/J (ParametricTools.hpp:73-103) through elementMap.
  */
+template <bool SPH>
 __global__ void paramgeom_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy, double* __restrict__ geo)
 {
     const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -57,7 +69,7 @@ __global__ void paramgeom_kernel(GridDims g, const double* __restrict__ vx, cons
     const int ix = int(t % g.nx), iy = int(t / g.nx);
     const size_t e = size_t(iy) * g.nxs + ix;
     double c[4][2], dx[2][9], dy[2][9], J[9], lat[9];
-    elementCorners(vx, vy, g.nx, ix, iy, false, c);
+    elementCorners(vx, vy, g.nx, ix, iy, SPH, c);
     elementMap<3>(c, dx, dy, J, lat);
     for (int k = 0; k < 3; ++k) {
         geo[size_t(0 + k) * g.Npad + e] = dx[0][3 * k]; // dx/dxi   depends on the Gauss row only
@@ -67,30 +79,327 @@ __global__ void paramgeom_kernel(GridDims g, const double* __restrict__ vx, cons
     }
     double den = 0.0;
     for (int q = 0; q < 9; ++q) {
-        const double iJ = 1.0 / J[q];
+        const double iJ = SPH ? 1.0 / (J[q] * cos(lat[q])) : 1.0 / J[q];
         geo[size_t(12 + q) * g.Npad + e] = iJ;
         den += gaussweight2(3, q) * psi8at(q) * psi8at(q) * iJ;
+        if constexpr (SPH) {
+            geo[size_t(22 + q) * g.Npad + e] = cos(lat[q]);
+            geo[size_t(31 + q) * g.Npad + e] = sin(lat[q]);
+        }
     }
     geo[size_t(21) * g.Npad + e] = 1.0 / den;
 }
 
-struct PmevpStage {
+// =====================================================================================================================
+// Gauss-point building blocks shared by the parametric mEVP and BBM kernels.  GEO(k) reads geometry plane k of the
+// lane's element from the warp's staging buffer.
+// =====================================================================================================================
+
+//! n_q = w_q psi_8(q): the null vector of the DG8 Gauss-point evaluation matrix
+NSDG_HD constexpr double null8(int q) { return gaussweight2(3, q) * psi8at(q); }
+//! Q2 tensor modes missing from DG6: psi_6 = y (x^2 - 1/12), psi_7 = x (y^2 - 1/12), psi_8
+NSDG_HD constexpr double missing6at(int k, int q) { return k < 2 ? PSI(3, 6 + k, q) : psi8at(q); }
+
+//! D-weighted DG8 projection of three Gauss-point fields, in place:  y <- y - rho gamma (n . y)
+template <class GEO> __device__ __forceinline__ void projectDG8x3(const GEO& geo, double (&a)[9], double (&b)[9], double (&c)[9])
+{
+    double la = 0.0, lb = 0.0, lc = 0.0;
+    static_for<9>([&](auto QQ) {
+        constexpr int q = decltype(QQ)::value;
+        constexpr double n = null8(q);
+        la = fma(n, a[q], la);
+        lb = fma(n, b[q], lb);
+        lc = fma(n, c[q], lc);
+    });
+    const double gam = geo(21);
+    la *= gam;
+    lb *= gam;
+    lc *= gam;
+    static_for<9>([&](auto QQ) {
+        constexpr int q = decltype(QQ)::value;
+        const double rho = psi8at(q) * geo(12 + q);
+        a[q] = fma(-la, rho, a[q]);
+        b[q] = fma(-lb, rho, b[q]);
+        c[q] = fma(-lc, rho, c[q]);
+    });
+}
+
+//! 1 / cos(lat) in Gauss point q of a spherical element = J / (J cos)
+template <class GEO> __device__ __forceinline__ double invCos(const GEO& geo, int qx, int qy, int q)
+{
+    return geo(12 + q) * (geo(0 + qy) * geo(9 + qx) - geo(3 + qy) * geo(6 + qx));
+}
+
+/*
+ * projectVelocityToStrain (CGDynamicsKernel.cpp:300-337) in Gauss-point form: pointwise physical gradient of the Q2
+ * velocity, then the DG8 projection.  Land elements keep zero strain (quirk Q8).
+ */
+template <bool SPH, class GEO>
+__device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9], const double (&vl)[9], bool ice, double (&e11)[9],
+    double (&e12)[9], double (&e22)[9])
+{
+    constexpr double iR = 1.0 / EarthRadius;
+    double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3]; // [jy][qx]: value / xi-derivative contracted in x
+    static_for<3>([&](auto JY) {
+        static_for<3>([&](auto QX) {
+            constexpr int jy = decltype(JY)::value, qx = decltype(QX)::value;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            static_for<3>([&](auto JX) {
+                constexpr int jx = decltype(JX)::value;
+                constexpr double l = kUnitOps.L[jx][qx], lp = kUnitOps.Lp[jx][qx];
+                if constexpr (l != 0.0) {
+                    s0 = fma(l, ul[jy * 3 + jx], s0);
+                    s2 = fma(l, vl[jy * 3 + jx], s2);
+                }
+                if constexpr (lp != 0.0) {
+                    s1 = fma(lp, ul[jy * 3 + jx], s1);
+                    s3 = fma(lp, vl[jy * 3 + jx], s3);
+                }
+            });
+            Au[jy][qx] = s0;
+            Adu[jy][qx] = s1;
+            Av[jy][qx] = s2;
+            Adv[jy][qx] = s3;
+        });
+    });
+    static_for<3>([&](auto QY) {
+        constexpr int qy = decltype(QY)::value;
+        const double xxi = geo(0 + qy), yxi = geo(3 + qy);
+        static_for<3>([&](auto QX) {
+            constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
+            double uxi = 0, ueta = 0, vxi = 0, veta = 0; // reference derivatives
+            static_for<3>([&](auto JY) {
+                constexpr int jy = decltype(JY)::value;
+                constexpr double l = kUnitOps.L[jy][qy], lp = kUnitOps.Lp[jy][qy];
+                if constexpr (l != 0.0) {
+                    uxi = fma(l, Adu[jy][qx], uxi);
+                    vxi = fma(l, Adv[jy][qx], vxi);
+                }
+                if constexpr (lp != 0.0) {
+                    ueta = fma(lp, Au[jy][qx], ueta);
+                    veta = fma(lp, Av[jy][qx], veta);
+                }
+            });
+            const double xeta = geo(6 + qx), yeta = geo(9 + qx), iJ = geo(12 + q);
+            // J d/dx = yeta d/dxi - yxi d/deta ;  J d/dy = xxi d/deta - xeta d/dxi   (ParametricMap.cpp:248-254)
+            if constexpr (!SPH) {
+                const double ux = (yeta * uxi - yxi * ueta) * iJ, uy = (xxi * ueta - xeta * uxi) * iJ;
+                const double vx = (yeta * vxi - yxi * veta) * iJ, vy = (xxi * veta - xeta * vxi) * iJ;
+                e11[q] = ux;
+                e22[q] = vy;
+                e12[q] = 0.5 * (uy + vx);
+            } else {
+                // values of u, v in the Gauss point for the metric terms (divM / iMM, ParametricMap.cpp:321-337)
+                double uq = 0, vq = 0;
+                static_for<3>([&](auto JY) {
+                    constexpr int jy = decltype(JY)::value;
+                    constexpr double l = kUnitOps.L[jy][qy];
+                    if constexpr (l != 0.0) {
+                        uq = fma(l, Au[jy][qx], uq);
+                        vq = fma(l, Av[jy][qx], vq);
+                    }
+                });
+                const double cl = geo(22 + q), sl = geo(31 + q);
+                const double Js = (xxi * yeta - yxi * xeta) * sl; // J sin(lat)
+                const double k = iJ * iR; //                         1 / (R J cos)
+                e11[q] = ((yeta * uxi - yxi * ueta) - Js * vq) * k;
+                e22[q] = (cl * (xxi * veta - xeta * vxi)) * k;
+                e12[q] = 0.5 * ((yeta * vxi - yxi * veta) + cl * (xxi * ueta - xeta * uxi) + Js * uq) * k;
+            }
+        });
+    });
+    projectDG8x3(geo, e11, e12, e22);
+    if (!ice) {
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+            e11[q] = e12[q] = e22[q] = 0.0;
+    }
+}
+
+//! DG coefficients (first NC basis functions) of a field of the DG space given by its Gauss-point values
+template <int NC> __device__ __forceinline__ void coeffFromGauss(const double (&r)[9], double (&s)[NC])
+{
+    static_for<NC>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        double acc = 0.0;
+        static_for<9>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            constexpr double b = kUnitOps.B[j][q];
+            if constexpr (b != 0.0)
+                acc = fma(b, r[q], acc);
+        });
+        s[j] = acc;
+    });
+}
+template <int NC> __device__ __forceinline__ void gaussFromCoeff(const double (&s)[NC], double (&r)[9])
+{
+    static_for<9>([&](auto QQ) {
+        constexpr int q = decltype(QQ)::value;
+        double acc = 0.0;
+        static_for<NC>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            constexpr double p = UnitOps::clean(PSI(3, j, q));
+            if constexpr (p != 0.0)
+                acc = fma(p, s[j], acc);
+        });
+        r[q] = acc;
+    });
+}
+
+/*
+ * stressDivergence / addStressTensorCell (CGDynamicsKernel.cpp:340-398) from the stress in the Gauss points:
+ *   tx_i = sum_q phi_i,xi (w (yeta s11 - xeta s12)) + phi_i,eta (w (xxi s12 - yxi s11)) [+ metric terms],  ty alike.
+ */
+template <bool SPH, class GEO>
+__device__ __forceinline__ void gaussDivergence(const GEO& geo, const double (&s11)[9], const double (&s12)[9], const double (&s22)[9],
+    double (&Tx)[9], double (&Ty)[9])
+{
+    constexpr double iR = 1.0 / EarthRadius;
+    double CAx[3][3], CBx[3][3], CAy[3][3], CBy[3][3]; // [ix][qy]
+    double CMx[SPH ? 3 : 1][3], CMy[SPH ? 3 : 1][3]; // metric (value) terms, spherical only
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            CAx[i][k] = CBx[i][k] = CAy[i][k] = CBy[i][k] = 0.0;
+            if constexpr (SPH)
+                CMx[i][k] = CMy[i][k] = 0.0;
+        }
+    static_for<3>([&](auto QY) {
+        constexpr int qy = decltype(QY)::value;
+        const double xxi = geo(0 + qy), yxi = geo(3 + qy);
+        static_for<3>([&](auto QX) {
+            constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
+            constexpr double wq = gaussweight2(3, q);
+            const double xeta = geo(6 + qx), yeta = geo(9 + qx);
+            double ax, bx, ay, by, mx = 0.0, my = 0.0;
+            if constexpr (!SPH) {
+                ax = wq * (yeta * s11[q] - xeta * s12[q]), bx = wq * (xxi * s12[q] - yxi * s11[q]);
+                ay = wq * (yeta * s12[q] - xeta * s22[q]), by = wq * (xxi * s22[q] - yxi * s12[q]);
+            } else { // divS1 = dx_cg2 PSI^T / R, divS2 = cos dy_cg2 PSI^T / R, divM = (phi J sin w) PSI^T / R
+                constexpr double wr = wq * iR;
+                const double cl = geo(22 + q), sl = geo(31 + q);
+                const double Js = (xxi * yeta - yxi * xeta) * sl;
+                ax = wr * (yeta * s11[q] - cl * (xeta * s12[q])), bx = wr * (cl * (xxi * s12[q]) - yxi * s11[q]);
+                ay = wr * (yeta * s12[q] - cl * (xeta * s22[q])), by = wr * (cl * (xxi * s22[q]) - yxi * s12[q]);
+                mx = wr * Js * s12[q]; //  tx += divM s12
+                my = -wr * Js * s11[q]; // ty -= divM s11   (CGDynamicsKernel.cpp:348-351)
+            }
+            static_for<3>([&](auto IX) {
+                constexpr int ix = decltype(IX)::value;
+                constexpr double l = kUnitOps.L[ix][qx], lp = kUnitOps.Lp[ix][qx];
+                if constexpr (lp != 0.0) {
+                    CAx[ix][qy] = fma(lp, ax, CAx[ix][qy]);
+                    CAy[ix][qy] = fma(lp, ay, CAy[ix][qy]);
+                }
+                if constexpr (l != 0.0) {
+                    CBx[ix][qy] = fma(l, bx, CBx[ix][qy]);
+                    CBy[ix][qy] = fma(l, by, CBy[ix][qy]);
+                    if constexpr (SPH) {
+                        CMx[ix][qy] = fma(l, mx, CMx[ix][qy]);
+                        CMy[ix][qy] = fma(l, my, CMy[ix][qy]);
+                    }
+                }
+            });
+        });
+    });
+    static_for<3>([&](auto IY) {
+        static_for<3>([&](auto IX) {
+            constexpr int iy = decltype(IY)::value, ix = decltype(IX)::value;
+            double tx = 0.0, ty = 0.0;
+            static_for<3>([&](auto QY) {
+                constexpr int qy = decltype(QY)::value;
+                constexpr double l = kUnitOps.L[iy][qy], lp = kUnitOps.Lp[iy][qy];
+                if constexpr (l != 0.0) {
+                    tx = fma(l, CAx[ix][qy], tx);
+                    ty = fma(l, CAy[ix][qy], ty);
+                    if constexpr (SPH) {
+                        tx = fma(l, CMx[ix][qy], tx);
+                        ty = fma(l, CMy[ix][qy], ty);
+                    }
+                }
+                if constexpr (lp != 0.0) {
+                    tx = fma(lp, CBx[ix][qy], tx);
+                    ty = fma(lp, CBy[ix][qy], ty);
+                }
+            });
+            Tx[iy * 3 + ix] = tx;
+            Ty[iy * 3 + ix] = ty;
+        });
+    });
+}
+
+//! the warp-strip bookkeeping after the element part: deferred-line buffers and the left-neighbour shuffle
+struct StripPos {
+    int lane, sx, sy, ex, ey, ey0, ey1;
+    bool active, lastLane;
+};
+__device__ __forceinline__ bool stripScatter(const GridDims& g, const StripPos& s, double* hbuf, double* vbuf, double (&Tx)[9], double (&Ty)[9])
+{
+    constexpr int CG = 2, NR = 3;
+    constexpr unsigned FULL = 0xffffffffu;
+    if (s.active && s.lane == 0 && s.sx > 0) {
+        double* vb = vbuf + ((size_t(s.sx - 1) * 2 + 1) * g.ny + s.ey) * (NR * 2);
+#pragma unroll
+        for (int jy = 0; jy < NR; ++jy) {
+            vb[jy * 2 + 0] = Tx[jy * NR];
+            vb[jy * 2 + 1] = Ty[jy * NR];
+        }
+    }
+    if (s.lastLane) {
+        double* vb = vbuf + ((size_t(s.sx) * 2 + 0) * g.ny + s.ey) * (NR * 2);
+#pragma unroll
+        for (int jy = 0; jy < NR; ++jy) {
+            vb[jy * 2 + 0] = Tx[jy * NR + CG];
+            vb[jy * 2 + 1] = Ty[jy * NR + CG];
+        }
+    }
+    const bool bottomDeferred = (s.ey == s.ey0) && (s.sy > 0);
+    if (s.active && bottomDeferred) {
+        double* hb = hbuf + ((size_t(s.sy - 1) * 2 + 1) * g.nx + s.ex) * (NR * 2);
+#pragma unroll
+        for (int jx = 0; jx < NR; ++jx) {
+            hb[jx * 2 + 0] = Tx[jx];
+            hb[jx * 2 + 1] = Ty[jx];
+        }
+    }
+    if (s.active && s.ey == s.ey1 - 1) {
+        double* hb = hbuf + ((size_t(s.sy) * 2 + 0) * g.nx + s.ex) * (NR * 2);
+#pragma unroll
+        for (int jx = 0; jx < NR; ++jx) {
+            hb[jx * 2 + 0] = Tx[CG * NR + jx];
+            hb[jx * 2 + 1] = Ty[CG * NR + jx];
+        }
+    }
+#pragma unroll
+    for (int jy = 0; jy < NR; ++jy) {
+        const double lx = __shfl_up_sync(FULL, Tx[jy * NR + CG], 1);
+        const double ly = __shfl_up_sync(FULL, Ty[jy * NR + CG], 1);
+        if (s.lane > 0) {
+            Tx[jy * NR] = lx + Tx[jy * NR];
+            Ty[jy * NR] = ly + Ty[jy * NR];
+        }
+    }
+    return bottomDeferred;
+}
+
+// =====================================================================================================================
+// mEVP
+// =====================================================================================================================
+template <bool SPH> struct PmevpStage {
     double P[9][32];
     double S[24][32];
-    double GEO[kGeoPlanes][32];
+    double GEO[geoPlanes(SPH)][32];
     double2 ND[2][7][32];
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
 };
-constexpr int kPmevpWarps = 3;
-constexpr size_t kPmevpSmemBytes = sizeof(PmevpStage) * kPmevpWarps;
+constexpr int pmevpWarps(bool sph) { return sph ? 2 : 3; }
+constexpr size_t pmevpSmemBytes(bool sph) { return sph ? sizeof(PmevpStage<true>) * 2 : sizeof(PmevpStage<false>) * 3; }
 
-#ifndef NSDG_PMEVP_MINBLOCKS
-#define NSDG_PMEVP_MINBLOCKS 3
-#endif
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcycle_strip_pmevp(const __grid_constant__ UniformArgs a)
+template <bool SPH>
+__global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_strip_pmevp(const __grid_constant__ UniformArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8;
     constexpr unsigned FULL = 0xffffffffu;
@@ -99,7 +408,7 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
         return;
-    PmevpStage& st = reinterpret_cast<PmevpStage*>(smemRaw)[threadIdx.x >> 5];
+    PmevpStage<SPH>& st = reinterpret_cast<PmevpStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
     const int exRaw = 32 * sx + lane;
@@ -110,6 +419,7 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
     const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
     const size_t Npad = g.Npad;
     const int col0 = CG * ex;
+    auto geo = [&](int k) { return st.GEO[k][lane]; };
 
     // ---- the five staging groups of element row `row`, issued in the order UV, P, S, GEO, ND ----
     auto issueUV = [&](int row) {
@@ -152,7 +462,7 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
         if (row < ey1) {
             const size_t en = size_t(row) * g.nxs + ex;
 #pragma unroll
-            for (int k = 0; k < kGeoPlanes; ++k)
+            for (int k = 0; k < geoPlanes(SPH); ++k)
                 cpAsync8(&st.GEO[k][lane], a.geo + size_t(k) * Npad + en);
         }
         cpAsyncCommit();
@@ -231,197 +541,53 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
         }
         issueUV(ey + 1);
 
-        // ---- pointwise physical velocity gradient in the 9 Gauss points ----
+        // ---- strain in the 9 Gauss points ----
         cpAsyncWait<2>(); // P, S and GEO of this row have landed
-        const double gam = st.GEO[21][lane];
         double e11[9], e12[9], e22[9];
-        {
-            double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3]; // [jy][qx]: value / xi-derivative contracted in x
-            static_for<3>([&](auto JY) {
-                static_for<3>([&](auto QX) {
-                    constexpr int jy = decltype(JY)::value, qx = decltype(QX)::value;
-                    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                    static_for<3>([&](auto JX) {
-                        constexpr int jx = decltype(JX)::value;
-                        constexpr double l = kUnitOps.L[jx][qx], lp = kUnitOps.Lp[jx][qx];
-                        if constexpr (l != 0.0) {
-                            s0 = fma(l, ul[jy * 3 + jx], s0);
-                            s2 = fma(l, vl[jy * 3 + jx], s2);
-                        }
-                        if constexpr (lp != 0.0) {
-                            s1 = fma(lp, ul[jy * 3 + jx], s1);
-                            s3 = fma(lp, vl[jy * 3 + jx], s3);
-                        }
-                    });
-                    Au[jy][qx] = s0;
-                    Adu[jy][qx] = s1;
-                    Av[jy][qx] = s2;
-                    Adv[jy][qx] = s3;
-                });
-            });
-            double l11 = 0.0, l12 = 0.0, l22 = 0.0; // n . y
-            static_for<3>([&](auto QY) {
-                constexpr int qy = decltype(QY)::value;
-                const double xxi = st.GEO[0 + qy][lane], yxi = st.GEO[3 + qy][lane];
-                static_for<3>([&](auto QX) {
-                    constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
-                    double uxi = 0, ueta = 0, vxi = 0, veta = 0; // reference derivatives
-                    static_for<3>([&](auto JY) {
-                        constexpr int jy = decltype(JY)::value;
-                        constexpr double l = kUnitOps.L[jy][qy], lp = kUnitOps.Lp[jy][qy];
-                        if constexpr (l != 0.0) {
-                            uxi = fma(l, Adu[jy][qx], uxi);
-                            vxi = fma(l, Adv[jy][qx], vxi);
-                        }
-                        if constexpr (lp != 0.0) {
-                            ueta = fma(lp, Au[jy][qx], ueta);
-                            veta = fma(lp, Av[jy][qx], veta);
-                        }
-                    });
-                    const double xeta = st.GEO[6 + qx][lane], yeta = st.GEO[9 + qx][lane], iJ = st.GEO[12 + q][lane];
-                    // J d/dx = yeta d/dxi - yxi d/deta ;  J d/dy = xxi d/deta - xeta d/dxi   (ParametricMap.cpp:248-254)
-                    const double ux = (yeta * uxi - yxi * ueta) * iJ, uy = (xxi * ueta - xeta * uxi) * iJ;
-                    const double vx = (yeta * vxi - yxi * veta) * iJ, vy = (xxi * veta - xeta * vxi) * iJ;
-                    e11[q] = ux;
-                    e22[q] = vy;
-                    e12[q] = 0.5 * (uy + vx);
-                    constexpr double n = gaussweight2(3, q) * psi8at(q);
-                    l11 = fma(n, e11[q], l11);
-                    l22 = fma(n, e22[q], l22);
-                    l12 = fma(n, e12[q], l12);
-                });
-            });
-            // remove the psi_8 component (rank-one part of the DG8 projection); land elements keep zero strain (Q8)
-            l11 *= gam;
-            l12 *= gam;
-            l22 *= gam;
-            static_for<9>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                const double rho = psi8at(q) * st.GEO[12 + q][lane];
-                e11[q] = ice ? fma(-l11, rho, e11[q]) : 0.0;
-                e12[q] = ice ? fma(-l12, rho, e12[q]) : 0.0;
-                e22[q] = ice ? fma(-l22, rho, e22[q]) : 0.0;
-            });
-        }
+        gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 
-        // ---- VP law in the Gauss points (MEVPStressUpdateStep.hpp:62-117), then the same rank-one projection ----
-        {
-            double l11 = 0.0, l12 = 0.0, l22 = 0.0;
-            static_for<9>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                const double Pa = st.P[q][lane];
-                const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
-                const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
-                const double pd = 0.125 * Pa * iD;
-                e11[q] = fma(pd, 5.0 * g11 + 3.0 * g22, -0.5 * Pa);
-                e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);
-                e12[q] = 2.0 * pd * g12;
-                constexpr double n = gaussweight2(3, q) * psi8at(q);
-                l11 = fma(n, e11[q], l11);
-                l22 = fma(n, e22[q], l22);
-                l12 = fma(n, e12[q], l12);
-            });
-            l11 *= gam;
-            l12 *= gam;
-            l22 *= gam;
-            static_for<9>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                const double rho = psi8at(q) * st.GEO[12 + q][lane];
-                e11[q] = fma(-l11, rho, e11[q]);
-                e12[q] = fma(-l12, rho, e12[q]);
-                e22[q] = fma(-l22, rho, e22[q]);
-            });
-        }
+        // ---- VP law in the Gauss points (MEVPStressUpdateStep.hpp:62-117), then the same projection ----
+        static_for<9>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            const double Pa = st.P[q][lane];
+            const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+            const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+            const double pd = 0.125 * Pa * iD;
+            e11[q] = fma(pd, 5.0 * g11 + 3.0 * g22, -0.5 * Pa);
+            e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);
+            e12[q] = 2.0 * pd * g12;
+            if constexpr (SPH) { // iMJwPSI weights with w J, the mass with w J cos (ParametricMap.cpp:339-343)
+                const double icos = invCos(geo, q % 3, q / 3, q);
+                e11[q] *= icos;
+                e22[q] *= icos;
+                e12[q] *= icos;
+            }
+        });
+        projectDG8x3(geo, e11, e12, e22);
         issueP(ey + 1);
 
         // ---- per stress component: coefficients of the projected increment, relax, store, value at the Gauss points ----
         auto component = [&](double* plane, double (&r)[9], auto COMP) {
             constexpr int comp = decltype(COMP)::value; // 0: s11, 1: s12, 2: s22
             double s[DGs];
-            static_for<DGs>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                double acc = 0.0;
-                static_for<9>([&](auto QQ) {
-                    constexpr int q = decltype(QQ)::value;
-                    constexpr double b = kUnitOps.B[j][q];
-                    if constexpr (b != 0.0)
-                        acc = fma(b, r[q], acc);
-                });
-                s[j] = fma(st.S[comp * 8 + j][lane], a.keep, acc);
+            coeffFromGauss<DGs>(r, s);
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                s[j] = fma(st.S[comp * 8 + j][lane], a.keep, s[j]);
                 if (active)
                     plane[size_t(j) * Npad + e] = s[j];
-            });
-            // the new stress in the Gauss points (overwrites the increment)
-            static_for<9>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                double acc = 0.0;
-                static_for<DGs>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    constexpr double p = UnitOps::clean(PSI(3, j, q));
-                    if constexpr (p != 0.0)
-                        acc = fma(p, s[j], acc);
-                });
-                r[q] = acc;
-            });
+            }
+            gaussFromCoeff<DGs>(s, r); // the new stress in the Gauss points (overwrites the increment)
         };
         component(a.s11, e11, std::integral_constant<int, 0> {});
         component(a.s12, e12, std::integral_constant<int, 1> {});
         component(a.s22, e22, std::integral_constant<int, 2> {});
         issueS(ey + 1);
 
-        // ---- stress divergence: (w J grad phi_i, sigma) by contraction with the 1-d Q2 tables ----
+        // ---- stress divergence ----
         double Tx[9], Ty[9];
         if (ice) {
-            double CAx[3][3], CBx[3][3], CAy[3][3], CBy[3][3]; // [ix][qy]
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    CAx[i][k] = CBx[i][k] = CAy[i][k] = CBy[i][k] = 0.0;
-            static_for<3>([&](auto QY) {
-                constexpr int qy = decltype(QY)::value;
-                const double xxi = st.GEO[0 + qy][lane], yxi = st.GEO[3 + qy][lane];
-                static_for<3>([&](auto QX) {
-                    constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
-                    constexpr double wq = gaussweight2(3, q);
-                    const double xeta = st.GEO[6 + qx][lane], yeta = st.GEO[9 + qx][lane];
-                    // tx_i = sum_q phi_i,xi (w (yeta s11 - xeta s12)) + phi_i,eta (w (xxi s12 - yxi s11)),  ty alike
-                    const double ax = wq * (yeta * e11[q] - xeta * e12[q]), bx = wq * (xxi * e12[q] - yxi * e11[q]);
-                    const double ay = wq * (yeta * e12[q] - xeta * e22[q]), by = wq * (xxi * e22[q] - yxi * e12[q]);
-                    static_for<3>([&](auto IX) {
-                        constexpr int ix = decltype(IX)::value;
-                        constexpr double l = kUnitOps.L[ix][qx], lp = kUnitOps.Lp[ix][qx];
-                        if constexpr (lp != 0.0) {
-                            CAx[ix][qy] = fma(lp, ax, CAx[ix][qy]);
-                            CAy[ix][qy] = fma(lp, ay, CAy[ix][qy]);
-                        }
-                        if constexpr (l != 0.0) {
-                            CBx[ix][qy] = fma(l, bx, CBx[ix][qy]);
-                            CBy[ix][qy] = fma(l, by, CBy[ix][qy]);
-                        }
-                    });
-                });
-            });
-            static_for<3>([&](auto IY) {
-                static_for<3>([&](auto IX) {
-                    constexpr int iy = decltype(IY)::value, ix = decltype(IX)::value;
-                    double tx = 0.0, ty = 0.0;
-                    static_for<3>([&](auto QY) {
-                        constexpr int qy = decltype(QY)::value;
-                        constexpr double l = kUnitOps.L[iy][qy], lp = kUnitOps.Lp[iy][qy];
-                        if constexpr (l != 0.0) {
-                            tx = fma(l, CAx[ix][qy], tx);
-                            ty = fma(l, CAy[ix][qy], ty);
-                        }
-                        if constexpr (lp != 0.0) {
-                            tx = fma(lp, CBx[ix][qy], tx);
-                            ty = fma(lp, CBy[ix][qy], ty);
-                        }
-                    });
-                    Tx[iy * 3 + ix] = tx;
-                    Ty[iy * 3 + ix] = ty;
-                });
-            });
+            gaussDivergence<SPH>(geo, e11, e12, e22, Tx, Ty);
         } else {
 #pragma unroll
             for (int k = 0; k < 9; ++k)
@@ -429,50 +595,7 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
         }
         issueGEO(ey + 1);
 
-        // ---- raw contributions to the deferred lines ----
-        if (active && lane == 0 && sx > 0) {
-            double* vb = a.vbuf + ((size_t(sx - 1) * 2 + 1) * g.ny + ey) * (NR * 2);
-#pragma unroll
-            for (int jy = 0; jy < NR; ++jy) {
-                vb[jy * 2 + 0] = Tx[jy * NR];
-                vb[jy * 2 + 1] = Ty[jy * NR];
-            }
-        }
-        if (lastLane) {
-            double* vb = a.vbuf + ((size_t(sx) * 2 + 0) * g.ny + ey) * (NR * 2);
-#pragma unroll
-            for (int jy = 0; jy < NR; ++jy) {
-                vb[jy * 2 + 0] = Tx[jy * NR + CG];
-                vb[jy * 2 + 1] = Ty[jy * NR + CG];
-            }
-        }
-        const bool bottomDeferred = (ey == ey0) && (sy > 0);
-        if (active && bottomDeferred) {
-            double* hb = a.hbuf + ((size_t(sy - 1) * 2 + 1) * g.nx + ex) * (NR * 2);
-#pragma unroll
-            for (int jx = 0; jx < NR; ++jx) {
-                hb[jx * 2 + 0] = Tx[jx];
-                hb[jx * 2 + 1] = Ty[jx];
-            }
-        }
-        if (active && ey == ey1 - 1) {
-            double* hb = a.hbuf + ((size_t(sy) * 2 + 0) * g.nx + ex) * (NR * 2);
-#pragma unroll
-            for (int jx = 0; jx < NR; ++jx) {
-                hb[jx * 2 + 0] = Tx[CG * NR + jx];
-                hb[jx * 2 + 1] = Ty[CG * NR + jx];
-            }
-        }
-        // ---- left neighbour's right column by shuffle ----
-#pragma unroll
-        for (int jy = 0; jy < NR; ++jy) {
-            const double lx = __shfl_up_sync(FULL, Tx[jy * NR + CG], 1);
-            const double ly = __shfl_up_sync(FULL, Ty[jy * NR + CG], 1);
-            if (lane > 0) {
-                Tx[jy * NR] = lx + Tx[jy * NR];
-                Ty[jy * NR] = ly + Ty[jy * NR];
-            }
-        }
+        const bool bottomDeferred = stripScatter(g, StripPos { lane, sx, sy, ex, ey, ey0, ey1, active, lastLane }, a.hbuf, a.vbuf, Tx, Ty);
         // ---- momentum update of the completed nodes (rows 2ey, 2ey+1; columns 2ex, 2ex+1) ----
         cpAsyncWait<4>();
 #pragma unroll
@@ -503,6 +626,390 @@ __global__ void __launch_bounds__(32 * kPmevpWarps, NSDG_PMEVP_MINBLOCKS) subcyc
                 } else {
                     a.u[n0 + 1] = un.y;
                     a.v[n0 + 1] = vn.y;
+                }
+            }
+        }
+        issueND(ey + 1);
+        carryX[0] = Tx[CG * NR];
+        carryX[1] = Tx[CG * NR + 1];
+        carryY[0] = Ty[CG * NR];
+        carryY[1] = Ty[CG * NR + 1];
+#pragma unroll
+        for (int jx = 0; jx < NR; ++jx) {
+            ul[jx] = ul[CG * NR + jx];
+            vl[jx] = vl[CG * NR + jx];
+        }
+    }
+    cpAsyncWait<0>();
+}
+
+// =====================================================================================================================
+// BBM
+// =====================================================================================================================
+/*
+ * Extra planes of the BBM kernel, after the geoPlanes(SPH) common ones:
+ *   +0..5  G3 = (N^T D^-1 N)^-1 (symmetric 3 x 3: 00 01 02 11 12 22), N = w psi_{6,7,8}: the DG6 projection of the
+ *          damage (iMJwPSI_dam, ParametricMap.cpp:289-296) is  y - D^-1 N G3 N^T y  in Gauss-point values
+ *   +6     scale_coef = sqrt(0.1 / h_el)                                   (BBMStressUpdateStep.hpp:134)
+ *   +7     1 / (h_el sqrt(2 (1 + nu) rho_ice))                             (BBMStressUpdateStep.hpp:158)
+ */
+constexpr int kBbmExtraPlanes = 8;
+constexpr int geoPlanesBBM(bool sph) { return geoPlanes(sph) + kBbmExtraPlanes; }
+
+template <bool SPH>
+__global__ void paramgeom_bbm_kernel(GridDims g, PhysParams p, const double* __restrict__ helem, double* __restrict__ geo)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(g.nx) * g.ny)
+        return;
+    const size_t e = size_t(t / g.nx) * g.nxs + (t % g.nx);
+    constexpr int base = geoPlanes(SPH);
+    double A[3][3];
+    for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < 3; ++l) {
+            double s = 0.0;
+            for (int q = 0; q < 9; ++q)
+                s += gaussweight2(3, q) * missing6at(k, q) * missing6at(l, q) * geo[size_t(12 + q) * g.Npad + e];
+            A[k][l] = s;
+        }
+    double inv[3][3];
+    inverse<3>(A, inv);
+    geo[size_t(base + 0) * g.Npad + e] = inv[0][0];
+    geo[size_t(base + 1) * g.Npad + e] = 0.5 * (inv[0][1] + inv[1][0]);
+    geo[size_t(base + 2) * g.Npad + e] = 0.5 * (inv[0][2] + inv[2][0]);
+    geo[size_t(base + 3) * g.Npad + e] = inv[1][1];
+    geo[size_t(base + 4) * g.Npad + e] = 0.5 * (inv[1][2] + inv[2][1]);
+    geo[size_t(base + 5) * g.Npad + e] = inv[2][2];
+    const double hel = helem[e];
+    geo[size_t(base + 6) * g.Npad + e] = sqrt(0.1 / hel);
+    geo[size_t(base + 7) * g.Npad + e] = 1.0 / (hel * sqrt(2. * (1. + p.nu0) * p.rho_ice));
+}
+
+template <bool SPH> struct PbbmStage {
+    double G[27][32]; //!< h, expC, Pmax in the 9 Gauss points
+    double S[24][32];
+    double D[6][32];
+    double GEO[geoPlanesBBM(SPH)][32];
+    double2 ND[2][7][32];
+    double2 UV[2][2][32];
+    double UVr[2][2];
+    double pad[2];
+};
+constexpr int kPbbmWarps = 2;
+template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps; }
+
+template <bool SPH>
+__global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
+{
+    constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GB = geoPlanes(SPH); // first BBM-specific plane
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
+        return;
+    PbbmStage<SPH>& st = reinterpret_cast<PbbmStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
+    const GridDims& g = a.g;
+    const int sx = w % a.nsx, sy = w / a.nsx;
+    const int exRaw = 32 * sx + lane;
+    const bool active = exRaw < g.nx;
+    const int ex = active ? exRaw : g.nx - 1;
+    const bool lastLane = active && (lane == 31 || exRaw == g.nx - 1);
+    const bool loadsRight = (lane == 31) || (exRaw >= g.nx - 1);
+    const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
+    const size_t Npad = g.Npad;
+    const int col0 = CG * ex;
+    auto geo = [&](int k) { return st.GEO[k][lane]; };
+
+    // staging groups, issued in the order UV, S(+D), G, GEO, ND
+    auto issueUV = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
+                cpAsync16(&st.UV[0][k][lane], a.u + n);
+                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                if (loadsRight) {
+                    cpAsync8(&st.UVr[0][k], a.u + n + CG);
+                    cpAsync8(&st.UVr[1][k], a.v + n + CG);
+                }
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueG = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nxs + ex;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                cpAsync8(&st.G[q][lane], a.gH + size_t(q) * Npad + en);
+                cpAsync8(&st.G[9 + q][lane], a.gE + size_t(q) * Npad + en);
+                cpAsync8(&st.G[18 + q][lane], a.gP + size_t(q) * Npad + en);
+            }
+        }
+        cpAsyncCommit();
+    };
+    auto issueS = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nxs + ex;
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
+                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
+            }
+#pragma unroll
+            for (int j = 0; j < DGA; ++j)
+                cpAsync8(&st.D[j][lane], a.damage + size_t(j) * Npad + en);
+        }
+        cpAsyncCommit();
+    };
+    auto issueGEO = [&](int row) {
+        if (row < ey1) {
+            const size_t en = size_t(row) * g.nxs + ex;
+#pragma unroll
+            for (int k = 0; k < geoPlanesBBM(SPH); ++k)
+                cpAsync8(&st.GEO[k][lane], a.geo + size_t(k) * Npad + en);
+        }
+        cpAsyncCommit();
+    };
+    auto issueND = [&](int row) {
+        if (row < ey1) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t n = size_t(CG * row + k) * g.cgs + col0;
+                cpAsync16(&st.ND[k][0][lane], a.dte + n);
+                cpAsync16(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16(&st.ND[k][2][lane], a.ax + n);
+                cpAsync16(&st.ND[k][3][lane], a.ay + n);
+                cpAsync16(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                prefetchL2(a.avgU + n); // read-modify-written at the end of the row
+                prefetchL2(a.avgV + n);
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    double carryX[2] = { 0.0, 0.0 }, carryY[2] = { 0.0, 0.0 };
+    double ul[9], vl[9];
+    issueUV(ey0);
+    issueS(ey0);
+    issueG(ey0);
+    issueGEO(ey0);
+    issueND(ey0);
+    {
+        const size_t n = size_t(CG * ey0) * g.cgs + col0;
+        const double2 tu = *reinterpret_cast<const double2*>(a.u + n), tv = *reinterpret_cast<const double2*>(a.v + n);
+        ul[0] = tu.x;
+        ul[1] = tu.y;
+        vl[0] = tv.x;
+        vl[1] = tv.y;
+        double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+        if (loadsRight) {
+            ru = a.u[n + CG];
+            rv = a.v[n + CG];
+        }
+        ul[2] = ru;
+        vl[2] = rv;
+    }
+    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
+    uchar2 nmNext[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+
+    for (int ey = ey0; ey < ey1; ++ey) {
+        const size_t e = size_t(ey) * g.nxs + ex;
+        const bool ice = active && (lmNext != 0);
+        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        if (ey + 1 < ey1) {
+            lmNext = __ldg(a.landmask + e + g.nxs);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+        }
+        cpAsyncWait<4>();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
+            ul[3 * (k + 1)] = tu.x;
+            ul[3 * (k + 1) + 1] = tu.y;
+            vl[3 * (k + 1)] = tv.x;
+            vl[3 * (k + 1) + 1] = tv.y;
+            double ru = __shfl_down_sync(FULL, tu.x, 1), rv = __shfl_down_sync(FULL, tv.x, 1);
+            if (loadsRight) {
+                ru = st.UVr[0][k];
+                rv = st.UVr[1][k];
+            }
+            ul[3 * (k + 1) + 2] = ru;
+            vl[3 * (k + 1) + 2] = rv;
+        }
+        issueUV(ey + 1);
+
+        // ---- strain in the 9 Gauss points ----
+        cpAsyncWait<2>(); // S, G and GEO of this row have landed
+        double e11[9], e12[9], e22[9];
+        gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
+
+        // ---- the BBM law point by point (BBMStressUpdateStep.hpp:66-160): e** become the updated stresses ----
+        double dG[9];
+        {
+            double s11c[DGs], s12c[DGs], s22c[DGs], dc[DGA];
+#pragma unroll
+            for (int j = 0; j < DGs; ++j) {
+                s11c[j] = st.S[j][lane];
+                s12c[j] = st.S[8 + j][lane];
+                s22c[j] = st.S[16 + j][lane];
+            }
+#pragma unroll
+            for (int j = 0; j < DGA; ++j)
+                dc[j] = st.D[j][lane];
+            const double scale = geo(GB + 6), invTdK = geo(GB + 7);
+            const double cohScale = a.C_lab * scale, comprScale = a.compr_strength * scale;
+            static_for<9>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
+                double d = evalGauss<DGA, 3, q>(dc);
+                const double h = st.G[q][lane], expC = st.G[9 + q][lane], Pmax = st.G[18 + q][lane];
+                const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+                d = fmin(fmax(d, 1e-12), 1.0);
+                double sigma_n = 0.5 * (t11 + t22);
+                const double de = d * expC, de2 = de * de;
+                const double tv = a.lambda0 * (de2 * de2);
+                const double tildeP = (sigma_n < 0.0) ? fmin(-Pmax / sigma_n, 1.0) : 0.0;
+                const double mult = tv / (tv + (1.0 - tildeP) * a.deltaT);
+                const double elasticity = h * a.young * d * expC;
+                const double Dunit = a.dunitK * elasticity;
+                t11 = (t11 + Dunit * (g11 + a.nu0 * g22)) * mult;
+                t22 = (t22 + Dunit * (a.nu0 * g11 + g22)) * mult;
+                t12 = (t12 + Dunit * g12 * (1.0 - a.nu0)) * mult;
+                sigma_n = 0.5 * (t11 + t22);
+                const double tau = sqrt(0.25 * (t11 - t22) * (t11 - t22) + t12 * t12);
+                const double cohesion = cohScale * h, compr = comprScale * h;
+                const double mc = tau + a.tan_phi * sigma_n;
+                double dcrit = (mc > 0.0) ? cohesion / mc : 1.0;
+                if (sigma_n < -compr)
+                    dcrit = -compr / sigma_n;
+                dcrit = fmin(dcrit, 1.0);
+                const double relax = (1.0 - dcrit) * a.deltaT * (sqrt(elasticity) * invTdK);
+                double dn = d - d * relax;
+                t11 -= t11 * relax;
+                t12 -= t12 * relax;
+                t22 -= t22 * relax;
+                if constexpr (SPH) { // the projections weight with w J, the mass matrices with w J cos
+                    const double icos = invCos(geo, q % 3, q / 3, q);
+                    dn *= icos;
+                    t11 *= icos;
+                    t12 *= icos;
+                    t22 *= icos;
+                }
+                dG[q] = dn;
+                e11[q] = t11;
+                e12[q] = t12;
+                e22[q] = t22;
+            });
+        }
+        issueG(ey + 1);
+
+        // ---- damage: DG6 projection = remove the three missing tensor modes, then the coefficients ----
+        {
+            double m0 = 0.0, m1 = 0.0, m2 = 0.0; // N^T y
+            static_for<9>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                constexpr double w = gaussweight2(3, q);
+                constexpr double n0 = w * missing6at(0, q), n1 = w * missing6at(1, q), n2 = w * missing6at(2, q);
+                if constexpr (n0 != 0.0)
+                    m0 = fma(n0, dG[q], m0);
+                if constexpr (n1 != 0.0)
+                    m1 = fma(n1, dG[q], m1);
+                m2 = fma(n2, dG[q], m2);
+            });
+            const double g00 = geo(GB + 0), g01 = geo(GB + 1), g02 = geo(GB + 2), g11 = geo(GB + 3), g12 = geo(GB + 4), g22 = geo(GB + 5);
+            const double c0 = g00 * m0 + g01 * m1 + g02 * m2, c1 = g01 * m0 + g11 * m1 + g12 * m2, c2 = g02 * m0 + g12 * m1 + g22 * m2;
+            static_for<9>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                constexpr double p0 = missing6at(0, q), p1 = missing6at(1, q), p2 = missing6at(2, q);
+                dG[q] = fma(-(p0 * c0 + p1 * c1 + p2 * c2), geo(12 + q), dG[q]);
+            });
+            double dc[DGA];
+            coeffFromGauss<DGA>(dG, dc);
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < DGA; ++j)
+                    a.damage[size_t(j) * Npad + e] = dc[j];
+            }
+        }
+
+        // ---- stress: DG8 projection, coefficients, store, back to the Gauss points for the divergence ----
+        projectDG8x3(geo, e11, e12, e22);
+        auto component = [&](double* plane, double (&r)[9]) {
+            double s[DGs];
+            coeffFromGauss<DGs>(r, s);
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < DGs; ++j)
+                    plane[size_t(j) * Npad + e] = s[j];
+            }
+            gaussFromCoeff<DGs>(s, r);
+        };
+        component(a.s11, e11);
+        component(a.s12, e12);
+        component(a.s22, e22);
+        issueS(ey + 1);
+
+        double Tx[9], Ty[9];
+        if (ice) {
+            gaussDivergence<SPH>(geo, e11, e12, e22, Tx, Ty);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                Tx[k] = Ty[k] = 0.0;
+        }
+        issueGEO(ey + 1);
+
+        const bool bottomDeferred = stripScatter(g, StripPos { lane, sx, sy, ex, ey, ey0, ey1, active, lastLane }, a.hbuf, a.vbuf, Tx, Ty);
+        // ---- momentum update of the completed nodes ----
+        cpAsyncWait<4>();
+#pragma unroll
+        for (int jy = 0; jy < CG; ++jy) {
+            const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+            const double2 dte = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], ax = st.ND[jy][2][lane], ay = st.ND[jy][3][lane];
+            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const uchar2 msk = nm[jy];
+            double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
+            if (jy == 0) {
+                sx0 += carryX[0];
+                sy0 += carryY[0];
+                sx1 += carryX[1];
+                sy1 += carryY[1];
+            }
+            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            double2 un, vn, ua, va;
+            momentumNodeUniformBBM(a, dte.x, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+                d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
+            momentumNodeUniformBBM(a, dte.y, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+                d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y, ua.y, va.y);
+            const bool rowSkip = !active || (jy == 0 && bottomDeferred);
+            const bool skip0 = rowSkip || (lane == 0 && sx > 0);
+            if (!rowSkip) {
+                if (!skip0) {
+                    *reinterpret_cast<double2*>(a.u + n0) = un;
+                    *reinterpret_cast<double2*>(a.v + n0) = vn;
+                    double2 au = *reinterpret_cast<const double2*>(a.avgU + n0), av = *reinterpret_cast<const double2*>(a.avgV + n0);
+                    au.x += ua.x;
+                    au.y += ua.y;
+                    av.x += va.x;
+                    av.y += va.y;
+                    *reinterpret_cast<double2*>(a.avgU + n0) = au;
+                    *reinterpret_cast<double2*>(a.avgV + n0) = av;
+                } else {
+                    a.u[n0 + 1] = un.y;
+                    a.v[n0 + 1] = vn.y;
+                    a.avgU[n0 + 1] += ua.y;
+                    a.avgV[n0 + 1] += va.y;
                 }
             }
         }

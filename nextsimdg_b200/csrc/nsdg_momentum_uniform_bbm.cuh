@@ -37,6 +37,9 @@ struct UniformBBMArgs {
     double cohScale, comprScale; //!< C_lab * sqrt(0.1/h_el), compr_strength * sqrt(0.1/h_el)
     double invTdK; //!< 1 / (h_el sqrt(2 (1+nu) rho_ice)):  1/td = sqrt(elasticity) * invTdK
     double dunitK; //!< deltaT / (1 - nu^2)
+    // parametric fast path (nsdg_momentum_param.cuh): per-element geometry planes; h_el varies per element
+    const double* geo;
+    double C_lab, compr_strength;
 };
 
 //! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240)
