@@ -17,8 +17,11 @@
  *            dynamics/src/include/{DynamicsParameters,VPParameters,MEBParameters}.hpp
  *
  * PARITY STATUS: the advection half is pinned by the reference's KATs (see nsdg_kat.cpp);
- * the momentum half has NO golden vector in the reference: it is
- * "parity unpinned" and checked only by the analytic self-consistency tests in tests/.
+ * the momentum half has no golden vector in the reference's tests; it is pinned
+ * against OUTPUTS OF THE REFERENCE ITSELF: oracle/_ref (the reference's kernels compiled from
+ * /root/reference, `make -C oracle ref`) run on the same inputs, live in
+ * tests/test_oracle_vs_reference.py and as committed fixtures tests/golden/ref_outputs.npz
+ * (agreement 1e-13 after 100 subcycles), plus the analytic self-consistency tests.
  *
  * Unlike the reference (quirk Q9) all state is explicitly zero-initialised.
  */
