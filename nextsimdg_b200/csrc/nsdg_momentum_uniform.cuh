@@ -149,6 +149,28 @@ __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem));
 }
+//! 16 B, L2 only (bypasses L1): the form that reaches the copy bandwidth of HBM; the 8-byte .ca form saturates at
+//! ~5.1 TB/s whatever the occupancy (scripts/microbench/stage_bw.cu: 5.09 vs 6.35 TB/s read+write on a B200)
+__device__ __forceinline__ void cpAsync16cg(void* smem, const void* gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+/*
+ * Warp-cooperative staging of NPL plane rows (32 consecutive doubles = 256 B of each plane) global -> shared:
+ * lanes 0-15 copy plane p, lanes 16-31 plane p+1, 16 B each.  `first` is the element index of the strip's lane 0
+ * in the row.  Consumers read slots copied by OTHER lanes: __syncwarp() after the wait, and before a refill.
+ */
+template <int NPL>
+__device__ __forceinline__ void stagePlanes(double (*dst)[32], const double* __restrict__ src, size_t pitch, size_t first, int lane)
+{
+    const int half = lane >> 4, k2 = 2 * (lane & 15);
+#pragma unroll
+    for (int p = 0; p < NPL; p += 2) {
+        const int pp = p + half;
+        if ((NPL % 2 == 0) || pp < NPL)
+            cpAsync16cg(&dst[pp][k2], src + size_t(pp) * pitch + first + k2);
+    }
+}
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -206,8 +228,8 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
-                cpAsync16(&st.UV[0][k][lane], a.u + n);
-                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                cpAsync16cg(&st.UV[0][k][lane], a.u + n);
+                cpAsync16cg(&st.UV[1][k][lane], a.v + n);
                 if (loadsRight) {
                     cpAsync8(&st.UVr[0][k], a.u + n + CG);
                     cpAsync8(&st.UVr[1][k], a.v + n + CG);
@@ -217,23 +239,18 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         cpAsyncCommit();
     };
     auto issueP = [&](int row) {
-        if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-                cpAsync8(&st.P[q][lane], a.Pa + size_t(q) * Npad + en);
-        }
+        __syncwarp(); // every lane has consumed the region that is refilled
+        if (row < ey1)
+            stagePlanes<9>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        __syncwarp();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int j = 0; j < DGs; ++j) {
-                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
-            }
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<8>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8>(st.S + 16, a.s22, Npad, first, lane);
         }
         cpAsyncCommit();
     };
@@ -242,13 +259,13 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16(&st.ND[k][0][lane], a.c1 + n);
-                cpAsync16(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16(&st.ND[k][2][lane], a.rx + n);
-                cpAsync16(&st.ND[k][3][lane], a.ry + n);
-                cpAsync16(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.c1 + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.rx + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.ry + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
             }
         }
         cpAsyncCommit();
@@ -366,6 +383,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 
         // ---- VP law in the Gauss points: e** become the integrands r** (MEVPStressUpdateStep.hpp:62-117) ----
         cpAsyncWait<3>();
+        __syncwarp(); // P was staged cooperatively
         static_for<9>([&](auto QQ) {
             constexpr int q = decltype(QQ)::value;
             const double Pa = st.P[q][lane];
@@ -384,6 +402,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         for (int k = 0; k < 9; ++k)
             Tx[k] = Ty[k] = 0.0;
         cpAsyncWait<3>();
+        __syncwarp(); // S was staged cooperatively
         auto component = [&](double* plane, const double (&r)[9], auto COMP) {
             constexpr int comp = decltype(COMP)::value; // 0: s11, 1: s12, 2: s22
             double s[DGs];
