@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
-                cpAsync16(&st.UV[0][k][lane], a.u + n);
-                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                cpAsync16cg(&st.UV[0][k][lane], a.u + n);
+                cpAsync16cg(&st.UV[1][k][lane], a.v + n);
                 if (loadsRight) {
                     cpAsync8(&st.UVr[0][k], a.u + n + CG);
                     cpAsync8(&st.UVr[1][k], a.v + n + CG);
@@ -438,33 +438,25 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
         cpAsyncCommit();
     };
     auto issueP = [&](int row) {
-        if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int q = 0; q < 9; ++q)
-                cpAsync8(&st.P[q][lane], a.Pa + size_t(q) * Npad + en);
-        }
+        stageBarrier<SPH>(); // every lane has consumed the region that is refilled
+        if (row < ey1)
+            stagePlanes<9, SPH>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        stageBarrier<SPH>();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int j = 0; j < DGs; ++j) {
-                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
-            }
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<8, SPH>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, SPH>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, SPH>(st.S + 16, a.s22, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
-        if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int k = 0; k < geoPlanes(SPH); ++k)
-                cpAsync8(&st.GEO[k][lane], a.geo + size_t(k) * Npad + en);
-        }
+        stageBarrier<SPH>();
+        if (row < ey1)
+            stagePlanes<geoPlanes(SPH), SPH>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueND = [&](int row) {
@@ -472,13 +464,13 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16(&st.ND[k][0][lane], a.c1 + n);
-                cpAsync16(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16(&st.ND[k][2][lane], a.rx + n);
-                cpAsync16(&st.ND[k][3][lane], a.ry + n);
-                cpAsync16(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.c1 + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.rx + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.ry + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
             }
         }
         cpAsyncCommit();
@@ -543,6 +535,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
 
         // ---- strain in the 9 Gauss points ----
         cpAsyncWait<2>(); // P, S and GEO of this row have landed
+        stageBarrier<SPH>(); //     (staged cooperatively: visible to every lane after the warp barrier)
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 
@@ -728,8 +721,8 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
-                cpAsync16(&st.UV[0][k][lane], a.u + n);
-                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                cpAsync16cg(&st.UV[0][k][lane], a.u + n);
+                cpAsync16cg(&st.UV[1][k][lane], a.v + n);
                 if (loadsRight) {
                     cpAsync8(&st.UVr[0][k], a.u + n + CG);
                     cpAsync8(&st.UVr[1][k], a.v + n + CG);
@@ -739,39 +732,30 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
         cpAsyncCommit();
     };
     auto issueG = [&](int row) {
+        stageBarrier<SPH>();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                cpAsync8(&st.G[q][lane], a.gH + size_t(q) * Npad + en);
-                cpAsync8(&st.G[9 + q][lane], a.gE + size_t(q) * Npad + en);
-                cpAsync8(&st.G[18 + q][lane], a.gP + size_t(q) * Npad + en);
-            }
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<9, SPH>(st.G, a.gH, Npad, first, lane);
+            stagePlanes<9, SPH>(st.G + 9, a.gE, Npad, first, lane);
+            stagePlanes<9, SPH>(st.G + 18, a.gP, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        stageBarrier<SPH>();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int j = 0; j < DGs; ++j) {
-                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
-            }
-#pragma unroll
-            for (int j = 0; j < DGA; ++j)
-                cpAsync8(&st.D[j][lane], a.damage + size_t(j) * Npad + en);
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<8, SPH>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, SPH>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, SPH>(st.S + 16, a.s22, Npad, first, lane);
+            stagePlanes<DGA, SPH>(st.D, a.damage, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
-        if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int k = 0; k < geoPlanesBBM(SPH); ++k)
-                cpAsync8(&st.GEO[k][lane], a.geo + size_t(k) * Npad + en);
-        }
+        stageBarrier<SPH>();
+        if (row < ey1)
+            stagePlanes<geoPlanesBBM(SPH), SPH>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueND = [&](int row) {
@@ -779,13 +763,13 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16(&st.ND[k][0][lane], a.dte + n);
-                cpAsync16(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16(&st.ND[k][2][lane], a.ax + n);
-                cpAsync16(&st.ND[k][3][lane], a.ay + n);
-                cpAsync16(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.dte + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ax + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.ay + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
                 prefetchL2(a.avgU + n); // read-modify-written at the end of the row
                 prefetchL2(a.avgV + n);
             }
@@ -851,6 +835,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 
         // ---- strain in the 9 Gauss points ----
         cpAsyncWait<2>(); // S, G and GEO of this row have landed
+        stageBarrier<SPH>();
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 

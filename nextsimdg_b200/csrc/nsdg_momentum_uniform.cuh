@@ -159,17 +159,30 @@ __device__ __forceinline__ void cpAsync16cg(void* smem, const void* gmem)
  * Warp-cooperative staging of NPL plane rows (32 consecutive doubles = 256 B of each plane) global -> shared:
  * lanes 0-15 copy plane p, lanes 16-31 plane p+1, 16 B each.  `first` is the element index of the strip's lane 0
  * in the row.  Consumers read slots copied by OTHER lanes: __syncwarp() after the wait, and before a refill.
+ * COOP = false is the per-lane form (8 B, .ca, every lane copies and reads only its own slots, no barriers): the
+ * register-bound BBM kernels and the Cartesian parametric kernels are faster with it (scripts/quickbench_all.sh).
  */
-template <int NPL>
+template <int NPL, bool COOP = true>
 __device__ __forceinline__ void stagePlanes(double (*dst)[32], const double* __restrict__ src, size_t pitch, size_t first, int lane)
 {
-    const int half = lane >> 4, k2 = 2 * (lane & 15);
+    if constexpr (COOP) {
+        const int half = lane >> 4, k2 = 2 * (lane & 15);
 #pragma unroll
-    for (int p = 0; p < NPL; p += 2) {
-        const int pp = p + half;
-        if ((NPL % 2 == 0) || pp < NPL)
-            cpAsync16cg(&dst[pp][k2], src + size_t(pp) * pitch + first + k2);
+        for (int p = 0; p < NPL; p += 2) {
+            const int pp = p + half;
+            if ((NPL % 2 == 0) || pp < NPL)
+                cpAsync16cg(&dst[pp][k2], src + size_t(pp) * pitch + first + k2);
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < NPL; ++p)
+            cpAsync8(&dst[p][lane], src + size_t(p) * pitch + first + lane);
     }
+}
+template <bool COOP> __device__ __forceinline__ void stageBarrier()
+{
+    if constexpr (COOP)
+        __syncwarp();
 }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }

@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
-                cpAsync16(&st.UV[0][k][lane], a.u + n);
-                cpAsync16(&st.UV[1][k][lane], a.v + n);
+                cpAsync16cg(&st.UV[0][k][lane], a.u + n);
+                cpAsync16cg(&st.UV[1][k][lane], a.v + n);
                 if (loadsRight) {
                     cpAsync8(&st.UVr[0][k], a.u + n + CG);
                     cpAsync8(&st.UVr[1][k], a.v + n + CG);
@@ -170,29 +170,23 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
         cpAsyncCommit();
     };
     auto issueG = [&](int row) {
+        stageBarrier<false>();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                cpAsync8(&st.G[q][lane], a.gH + size_t(q) * Npad + en);
-                cpAsync8(&st.G[9 + q][lane], a.gE + size_t(q) * Npad + en);
-                cpAsync8(&st.G[18 + q][lane], a.gP + size_t(q) * Npad + en);
-            }
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<9, false>(st.G, a.gH, Npad, first, lane);
+            stagePlanes<9, false>(st.G + 9, a.gE, Npad, first, lane);
+            stagePlanes<9, false>(st.G + 18, a.gP, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        stageBarrier<false>();
         if (row < ey1) {
-            const size_t en = size_t(row) * g.nxs + ex;
-#pragma unroll
-            for (int j = 0; j < DGs; ++j) {
-                cpAsync8(&st.S[j][lane], a.s11 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[8 + j][lane], a.s12 + size_t(j) * Npad + en);
-                cpAsync8(&st.S[16 + j][lane], a.s22 + size_t(j) * Npad + en);
-            }
-#pragma unroll
-            for (int j = 0; j < DGA; ++j)
-                cpAsync8(&st.D[j][lane], a.damage + size_t(j) * Npad + en);
+            const size_t first = size_t(row) * g.nxs + 32 * sx;
+            stagePlanes<8, false>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, false>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, false>(st.S + 16, a.s22, Npad, first, lane);
+            stagePlanes<DGA, false>(st.D, a.damage, Npad, first, lane);
         }
         cpAsyncCommit();
     };
@@ -201,13 +195,13 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16(&st.ND[k][0][lane], a.dte + n);
-                cpAsync16(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16(&st.ND[k][2][lane], a.ax + n);
-                cpAsync16(&st.ND[k][3][lane], a.ay + n);
-                cpAsync16(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.dte + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ax + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.ay + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
                 prefetchL2(a.avgU + n); // read-modify-written at the end of the row
                 prefetchL2(a.avgV + n);
             }
@@ -324,6 +318,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
         // ---- stress and damage coefficients of the row, then the BBM law point by point:
         //      e** become the updated Gauss-point stresses, dG the updated damage ----
         cpAsyncWait<3>();
+        stageBarrier<false>(); // S and D were staged cooperatively
         double dG[9];
         {
             double s11c[DGs], s12c[DGs], s22c[DGs], dc[DGA];
@@ -337,6 +332,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
             for (int j = 0; j < DGA; ++j)
                 dc[j] = st.D[j][lane];
             cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
+            stageBarrier<false>();
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
                 double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
