@@ -91,6 +91,7 @@ public:
     DevBuf<double> hbuf, vbuf;
     DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
+    DevBuf<double> vcon; // compact node constants of the vertical deferred lines (vcon_kernel)
     bool fastUniformMEVP = false, fastUniformBBM = false;
     bool fastParamMEVP = false; //!< factored-operator kernel on non-uniform Cartesian meshes (nsdg_momentum_param.cuh)
     bool fastParamBBM = false;
@@ -404,6 +405,8 @@ public:
                     subcycle_strip_pmevp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pmevpSmemBytes(true))));
             }
         }
+        if (fastMEVP() || fastBBM())
+            vcon.alloc(size_t(kVconPlanes) * nsx * g.cgny);
         if (fastParamMEVP || fastParamBBM) {
             geo.alloc(size_t(fastParamBBM ? geoPlanesBBM(spherical) : geoPlanes(spherical)) * Npad);
             if (spherical)
@@ -889,6 +892,7 @@ public:
         a.vO = vO;
         a.ilm = ncIlm;
         a.geo = geo;
+        a.vcon = vcon;
         a.nodemask = d_nodemask;
         a.hbuf = hbuf;
         a.vbuf = vbuf;
@@ -947,6 +951,7 @@ public:
         a.invTdK = 1.0 / (hel * std::sqrt(2. * (1. + p.nu0) * p.rho_ice));
         a.dunitK = deltaT / (1. - p.nu0 * p.nu0);
         a.geo = geo;
+        a.vcon = vcon;
         a.C_lab = p.C_lab;
         a.compr_strength = p.compr_strength;
         return a;
@@ -1169,7 +1174,9 @@ public:
             if (fastMEVP()) {
                 nodeconst_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
-                launches += 1;
+                vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+                    g, nsx, ncC1, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
+                launches += 2;
             }
         } else { // BrittleCGDynamicsKernel.hpp:110-114
             deltaT = dt / double(cfg.nsteps);
@@ -1179,7 +1186,9 @@ public:
                 gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
                 nodeconst_bbm_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
-                launches += 1;
+                vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+                    g, nsx, ncC1, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
+                launches += 2;
             } else
                 gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, 1.0);
         }

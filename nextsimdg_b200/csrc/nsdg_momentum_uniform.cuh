@@ -86,6 +86,7 @@ struct UniformArgs {
     const uint8_t* landmask;
     double *u, *v;
     const double *c1, *cA, *rx, *ry, *uO, *vO, *ilm; //!< per-node constants (nodeconst_kernel)
+    const double* vcon; //!< compact per-vertical-line copies of the node constants (vcon_kernel)
     const double* geo; //!< parametric fast path: kGeoPlanes geometry planes (nsdg_momentum_param.cuh)
     const uint8_t* nodemask;
     double *hbuf, *vbuf;
@@ -120,6 +121,31 @@ __global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const 
     rx[n] = k1 * u0[n] + A * (p.F_atm * absatm * uA[n]) - p.rho_ice * H * p.gravity * gx[n];
     ry[n] = k1 * v0[n] + A * (p.F_atm * absatm * vA[n]) - p.rho_ice * H * p.gravity * gy[n];
     ilm[n] = 1.0 / lm[n];
+}
+
+/*
+ * The nodes of the vertical deferred lines (every 64th node column) are visited column-wise by the lines kernels:
+ * a strided walk through the row-major node arrays costs one 64-B DRAM atom per 8-B value.  Their seven constants
+ * and the Dirichlet flag are therefore gathered once per timestep into a compact array
+ *     vcon[(k * nsx + line) * cgny + row],  k = 0..7,
+ * so that only u and v remain strided (lines kernel: 394 -> ~190 MB per launch at 2048^2).
+ */
+constexpr int kVconPlanes = 8;
+__global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2,
+    const double* __restrict__ k3, const double* __restrict__ k4, const double* __restrict__ k5, const double* __restrict__ k6,
+    const uint8_t* __restrict__ nodemask, double* __restrict__ vcon)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= long(nsx) * g.cgny)
+        return;
+    const int line = int(t / g.cgny), r = int(t % g.cgny);
+    const int c = min(2 * 32 * (line + 1), 2 * g.nx);
+    const size_t n = size_t(r) * g.cgs + c;
+    const double* src[7] = { k0, k1, k2, k3, k4, k5, k6 };
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        vcon[(size_t(k) * nsx + line) * g.cgny + r] = src[k][n];
+    vcon[(size_t(7) * nsx + line) * g.cgny + r] = (nodemask[n] & 1) ? 1.0 : 0.0;
 }
 
 //! mEVP momentum update of one node from the per-node constants (+ Dirichlet)
@@ -562,7 +588,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
     const long nV = long(a.nsx) * g.cgny;
     if (t >= nH + nV)
         return;
-    int c, r;
+    int c, r, vline = 0;
     double sumX = 0.0, sumY = 0.0;
     if (t < nH) {
         const int L = int(t / g.cgnx) + 1;
@@ -586,6 +612,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
     } else {
         const long tv = t - nH;
         const int L = int(tv / g.cgny) + 1;
+        vline = L - 1;
         r = int(tv % g.cgny);
         c = min(CG * 32 * L, CG * g.nx);
         if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
@@ -606,10 +633,23 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
         }
     }
     const size_t n = size_t(r) * g.cgs + c;
-    const bool d = __ldg(a.nodemask + n) & 1;
+    double k[7];
+    bool d;
+    if (t < nH) {
+        const double* src[7] = { a.c1, a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            k[i] = __ldg(src[i] + n);
+        d = __ldg(a.nodemask + n) & 1;
+    } else { // vertical line: compact copies (vcon_kernel)
+        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            k[i] = __ldg(a.vcon + i * pitch + m);
+        d = __ldg(a.vcon + 7 * pitch + m) != 0.0;
+    }
     double un, vn;
-    momentumNodeUniform(a, __ldg(a.c1 + n), __ldg(a.cA + n), __ldg(a.rx + n), __ldg(a.ry + n), __ldg(a.uO + n), __ldg(a.vO + n),
-        __ldg(a.ilm + n), d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
+    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], k[6], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
     a.u[n] = un;
     a.v[n] = vn;
 }

@@ -39,6 +39,7 @@ struct UniformBBMArgs {
     double dunitK; //!< deltaT / (1 - nu^2)
     // parametric fast path (nsdg_momentum_param.cuh): per-element geometry planes; h_el varies per element
     const double* geo;
+    const double* vcon; //!< compact per-vertical-line node constants (vcon_kernel)
     double C_lab, compr_strength;
 };
 
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
     const long nV = long(a.nsx) * g.cgny;
     if (t >= nH + nV)
         return;
-    int c, r;
+    int c, r, vline = 0;
     double sumX = 0.0, sumY = 0.0;
     if (t < nH) {
         const int L = int(t / g.cgnx) + 1;
@@ -563,6 +564,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
     } else {
         const long tv = t - nH;
         const int L = int(tv / g.cgny) + 1;
+        vline = L - 1;
         r = int(tv % g.cgny);
         c = min(CG * 32 * L, CG * g.nx);
         if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
@@ -583,10 +585,23 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
         }
     }
     const size_t n = size_t(r) * g.cgs + c;
-    const bool d = __ldg(a.nodemask + n) & 1;
+    double k[7];
+    bool d;
+    if (t < nH) {
+        const double* src[7] = { a.dte, a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            k[i] = __ldg(src[i] + n);
+        d = __ldg(a.nodemask + n) & 1;
+    } else { // vertical line: compact copies (vcon_kernel)
+        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            k[i] = __ldg(a.vcon + i * pitch + m);
+        d = __ldg(a.vcon + 7 * pitch + m) != 0.0;
+    }
     double un, vn, ua, va;
-    momentumNodeUniformBBM(a, __ldg(a.dte + n), __ldg(a.cA + n), __ldg(a.ax + n), __ldg(a.ay + n), __ldg(a.uO + n), __ldg(a.vO + n),
-        __ldg(a.ilm + n), d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
+    momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], k[6], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
     a.u[n] = un;
     a.v[n] = vn;
     a.avgU[n] += ua;
