@@ -66,6 +66,9 @@ public:
     GridDims g {};
     bool uniform = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr; //!< update(): forcing uploads / early downloads beside the compute stream
+    cudaEvent_t evForcing = nullptr, evCopyDone = nullptr;
+    bool forcingPending = false;
     cudaEvent_t ev[5] {};
     int cg1s = 0; //!< CG1 row stride
     size_t ncg = 0, ncg1 = 0; //!< allocated CG / CG1 doubles
@@ -141,6 +144,11 @@ public:
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
+        for (cudaEvent_t e : { evForcing, evCopyDone })
+            if (e)
+                cudaEventDestroy(e);
+        if (copyStream)
+            cudaStreamDestroy(copyStream);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -1162,6 +1170,10 @@ public:
             limit(damage, 3, 1.0, 1e-12);
         }
         NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
+        if (forcingPending) { // update(): the forcing fields were uploaded on the copy stream while the advection ran
+            NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evForcing, 0));
+            forcingPending = false;
+        }
         // ---- prepareIteration ----
         prepareIteration();
         double deltaT;
@@ -1241,13 +1253,52 @@ public:
             pin(ptr, bytes);
         for (double* ptr : outs)
             pin(ptr, bytes);
-        for (int i = 0; i < 8; ++i)
+        /*
+         * The module-level call with host buffers.  What the advection needs (hice, cice, damage) goes up on the compute
+         * stream; the five forcing fields go up, and are interpolated to CG, on a second stream while the advection
+         * runs (they are first read by prepareIteration); hice and cice are final after advection + limiters and come
+         * down on the second stream while the subcycles run.  Only u, v and the ice-ocean stress wait for the last subcycle.
+         */
+        const bool overlap = cfg.rheology != NSDG_FREEDRIFT && !std::getenv("NSDG_NO_COPY_OVERLAP");
+        if (overlap && !copyStream) {
+            NSDG_CUDA_CHECK(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+            NSDG_CUDA_CHECK(cudaEventCreateWithFlags(&evForcing, cudaEventDisableTiming));
+            NSDG_CUDA_CHECK(cudaEventCreateWithFlags(&evCopyDone, cudaEventDisableTiming));
+        }
+        for (int i = 0; i < 3; ++i)
             if (ins[i])
                 setFieldAsync(inField[i], ins[i], 1);
+        if (overlap) {
+            // the previous work of the compute stream (this handle's earlier calls) must not be overtaken
+            NSDG_CUDA_CHECK(cudaEventRecord(evCopyDone, stream));
+            NSDG_CUDA_CHECK(cudaStreamWaitEvent(copyStream, evCopyDone, 0));
+            std::swap(stream, copyStream);
+        }
+        for (int i = 3; i < 8; ++i)
+            if (ins[i])
+                setFieldAsync(inField[i], ins[i], 1);
+        if (overlap) {
+            NSDG_CUDA_CHECK(cudaEventRecord(evForcing, stream));
+            std::swap(stream, copyStream);
+            forcingPending = true;
+        }
         stepAsync(dt);
-        for (int i = 0; i < 7; ++i)
+        int firstLate = 0;
+        if (overlap) { // hice, cice: final since ev[1] (end of advection + limiters)
+            NSDG_CUDA_CHECK(cudaStreamWaitEvent(copyStream, ev[1], 0));
+            std::swap(stream, copyStream);
+            for (int i = 0; i < 2; ++i)
+                if (outs[i])
+                    getFieldAsync(outField[i], outs[i], 1);
+            NSDG_CUDA_CHECK(cudaEventRecord(evCopyDone, stream));
+            std::swap(stream, copyStream);
+            firstLate = 2;
+        }
+        for (int i = firstLate; i < 7; ++i)
             if (outs[i] && !(outField[i] == NSDG_DAMAGE && cfg.rheology != NSDG_BBM))
                 getFieldAsync(outField[i], outs[i], 1);
+        if (overlap)
+            NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evCopyDone, 0));
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
         finishTiming();
     }
