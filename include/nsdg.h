@@ -151,6 +151,17 @@ int nsdg_get_dirichlet(nsdg_handle h, int edge /* 0 bottom,1 right,2 top,3 left 
 int nsdg_get_internal(nsdg_handle h, const char* name, double* host, size_t capacity, size_t* count);
 int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_t count);
 
+/* ---- restart state --------------------------------------------------------------------------------
+ * Everything the dynamics carries from one timestep to the next, in the reference's layouts, as one flat buffer of
+ * doubles: an 8-double header {magic, version, rheology, dgadv, cgdegree, nx, ny, nfields}, then per field its
+ * length followed by its data.  Fields: hice, cice [, damage] (N x DGadv, the prognostic DG fields a restart file
+ * holds, BBMDynamics.cpp:104-132), the CG velocity u, v and the DG stresses s11, s12, s22 -- which the reference does
+ * NOT checkpoint (CGDynamicsKernel.cpp:57 TODO; its restarts begin from zero stress) -- and, for BBM, the running-mean
+ * velocity that advects the next step (BrittleCGDynamicsKernel.hpp:89).  get -> set on a fresh handle with the same
+ * mesh resumes bit-reproducibly (tests/test_gpu_parity.py::test_restart_state_resumes_bitwise). */
+int nsdg_get_state(nsdg_handle h, double* host, size_t capacity, size_t* count /* doubles written or needed */);
+int nsdg_set_state(nsdg_handle h, const double* host, size_t count);
+
 /* Run n bare subcycles on the current device state (no advection / prepare); the unit the
  * throughput metric counts.  Returns device milliseconds of the loop through *ms (CUDA events). */
 int nsdg_subcycles(nsdg_handle h, int n, float* ms);

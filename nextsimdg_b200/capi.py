@@ -59,6 +59,8 @@ SIGNATURES = {
     "nsdg_get_dirichlet": (c_int, [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),
     "nsdg_get_internal": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, POINTER(c_size_t)]),
     "nsdg_set_internal": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "nsdg_get_state": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "nsdg_set_state": (c_int, [c_void_p, c_void_p, c_size_t]),
     "nsdg_subcycles": (c_int, [c_void_p, c_int, POINTER(c_float)]),
     "nsdg_time_kernels": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_float)]),
     "nsdg_get_timing": (c_int, [c_void_p, POINTER(Timing)]),

@@ -46,6 +46,7 @@ public:
     virtual void getInternal(const std::string& name, double* host, size_t cap, size_t* count) = 0;
     virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
     virtual void benchmarkForcing(double elapsed, double Lx, double Ly) = 0;
+    virtual void dims(int* nx, int* ny) = 0;
     virtual void haloExport(unsigned char* handle) = 0;
     virtual void haloConnect(int side, const unsigned char* handle) = 0;
     virtual void haloReady() = 0;
@@ -1339,6 +1340,12 @@ public:
         out = it->second;
         return true;
     }
+    void dims(int* nx, int* ny) override
+    {
+        requireMesh();
+        *nx = g.nx;
+        *ny = g.ny;
+    }
     void getInternal(const std::string& name, double* host, size_t cap, size_t* count) override
     {
         requireMesh();
@@ -1595,6 +1602,78 @@ int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_
 {
     NSDG_TRY
     H(h)->setInternal(name, host, count);
+    NSDG_CATCH
+}
+namespace {
+constexpr double kStateMagic = 1314079815.0; // 'NSDG'
+std::vector<std::string> stateFields(const nsdg_config& c)
+{
+    std::vector<std::string> f = { "hice", "cice" };
+    if (c.rheology == NSDG_BBM)
+        f.push_back("damage");
+    for (const char* n : { "cg_u", "cg_v", "s11", "s12", "s22" })
+        f.push_back(n);
+    if (c.rheology == NSDG_BBM) {
+        f.push_back("avgU");
+        f.push_back("avgV");
+    }
+    return f;
+}
+}
+int nsdg_get_state(nsdg_handle h, double* host, size_t capacity, size_t* count)
+{
+    NSDG_TRY
+    HandleBase* hb = H(h);
+    const auto fields = stateFields(hb->cfg);
+    size_t total = 8;
+    std::vector<size_t> len(fields.size());
+    for (size_t i = 0; i < fields.size(); ++i) {
+        hb->getInternal(fields[i], nullptr, 0, &len[i]);
+        total += 1 + len[i];
+    }
+    if (count)
+        *count = total;
+    if (!host || capacity < total) {
+        if (host)
+            throw std::runtime_error("nsdg_get_state: buffer too small");
+        return 0;
+    }
+    int nx = 0, ny = 0;
+    hb->dims(&nx, &ny);
+    const double hdr[8] = { kStateMagic, 1.0, double(hb->cfg.rheology), double(hb->cfg.dgadv), double(hb->cfg.cgdegree), double(nx),
+        double(ny), double(fields.size()) };
+    std::copy(hdr, hdr + 8, host);
+    size_t off = 8;
+    for (size_t i = 0; i < fields.size(); ++i) {
+        host[off++] = double(len[i]);
+        size_t got = 0;
+        hb->getInternal(fields[i], host + off, len[i], &got);
+        off += len[i];
+    }
+    NSDG_CATCH
+}
+int nsdg_set_state(nsdg_handle h, const double* host, size_t count)
+{
+    NSDG_TRY
+    HandleBase* hb = H(h);
+    const auto fields = stateFields(hb->cfg);
+    int nx = 0, ny = 0;
+    hb->dims(&nx, &ny);
+    if (!host || count < 8 || host[0] != kStateMagic || host[1] != 1.0)
+        throw std::runtime_error("nsdg_set_state: not a state buffer of this library version");
+    if (int(host[2]) != hb->cfg.rheology || int(host[3]) != hb->cfg.dgadv || int(host[4]) != hb->cfg.cgdegree || int(host[5]) != nx
+        || int(host[6]) != ny || size_t(host[7]) != fields.size())
+        throw std::runtime_error("nsdg_set_state: state was written for a different configuration or mesh");
+    size_t off = 8;
+    for (const std::string& f : fields) {
+        if (off >= count)
+            throw std::runtime_error("nsdg_set_state: truncated buffer");
+        const size_t len = size_t(host[off++]);
+        if (off + len > count)
+            throw std::runtime_error("nsdg_set_state: truncated buffer");
+        hb->setInternal(f, host + off, len);
+        off += len;
+    }
     NSDG_CATCH
 }
 int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handle)

@@ -150,6 +150,18 @@ class CUDADynamicsBase:
         a = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
         check(self._lib.nsdg_set_internal(self._h, name.encode(), as_c(a), a.size))
 
+    # -- restart state: everything carried from one timestep to the next, one flat float64 buffer
+    def get_state(self) -> np.ndarray:
+        n = ctypes.c_size_t()
+        check(self._lib.nsdg_get_state(self._h, None, 0, ctypes.byref(n)))
+        out = np.empty(n.value)
+        check(self._lib.nsdg_get_state(self._h, out.ctypes.data_as(c_void_p), out.size, ctypes.byref(n)))
+        return out
+
+    def set_state(self, state: np.ndarray):
+        a = np.ascontiguousarray(state, dtype=np.float64)
+        check(self._lib.nsdg_set_state(self._h, a.ctypes.data_as(c_void_p), a.size))
+
     def landmask(self) -> np.ndarray:
         out = np.empty(self.nx * self.ny, dtype=np.uint8)
         check(self._lib.nsdg_get_landmask(self._h, out.ctypes.data_as(c_void_p)))

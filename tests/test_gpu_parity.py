@@ -232,6 +232,49 @@ def test_parametric_factored_path_equals_streamed_operator_path(mesh, rheo):
         assert rel(g, r) < 1e-8
 
 
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_restart_state_resumes_bitwise(rheo):
+    """nsdg_get_state / nsdg_set_state (N3): two steps in one run == one step, checkpoint, fresh handle, restore, one step."""
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, NsdgError, synthetic
+
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    nx, ny, dt = 40, 33, 900.0
+    ms = synthetic.para_state(nx, ny, distort=0.04, irregular_mask=True)
+    f = [synthetic.smooth_forcing(nx, ny, seed=s) for s in (1, 2)]
+
+    def fresh():
+        d = cls(nsteps=60)
+        d.setData(ms)
+        d.shared = {"hice": np.array(ms["hice"][..., 0], order="C", copy=True), "cice": np.array(ms["cice"][..., 0], order="C", copy=True)}
+        return d
+
+    a = fresh()
+    for k in range(2):
+        a.shared.update({n: v.copy() for n, v in f[k].items()})
+        a.update(dt)
+    b = fresh()
+    b.shared.update({n: v.copy() for n, v in f[0].items()})
+    b.update(dt)
+    state, shared = b.get_state(), {k: v.copy() for k, v in b.shared.items()}
+    dmg = None if b.damage is None else b.damage.copy()
+    b.close()
+    c = fresh()
+    c.set_state(state)
+    c.shared.update(shared)
+    if rheo == "bbm":
+        c.damage = dmg
+    c.shared.update({n: v.copy() for n, v in f[1].items()})
+    c.update(dt)
+    for name in ("uice", "vice", "taux", "tauy"):
+        assert np.array_equal(getattr(a, name), getattr(c, name)), name
+    for name in ("s11", "s12", "s22", "cg_u", "cg_v", "hice", "cice"):
+        assert np.array_equal(a.internal(name), c.internal(name)), name
+    with pytest.raises(NsdgError):  # a state of another configuration is refused
+        other = CUDAMEVPDynamics(nsteps=1) if rheo == "bbm" else CUDABBMDynamics(nsteps=1)
+        other.setData(ms)
+        other.set_state(state)
+
+
 def test_cuda_graph_and_plain_launches_identical():
     from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
 
