@@ -104,10 +104,10 @@ __device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, 
     double& uAvg, double& vAvg)
 {
     const double du = uO - un, dv = vO - vn;
-    const double cPrime = cA * sqrt(du * du + dv * dv);
+    const double cPrime = cA * fastSqrt(du * du + dv * dv);
     const double alpha = 1.0 + dte * (cPrime * a.cosA);
     const double beta = a.dtfc + dte * cPrime * a.sinA;
-    const double rDenom = 1.0 / (alpha * alpha + beta * beta);
+    const double rDenom = fastRcp(alpha * alpha + beta * beta);
     const double X = dSx * ilm + ax + cPrime * (uO * a.cosA - vO * a.sinA); // gradX + tauX
     const double Y = dSy * ilm + ay + cPrime * (vO * a.cosA + uO * a.sinA); // gradY + tauY
     unew = (alpha * un + beta * vn + dte * (alpha * X + beta * Y)) * rDenom;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
                 const bool full = compress && (Pmax >= -sigma_n);
                 const double mnum = compress ? tv * sigma_n : tv;
                 const double mden = compress ? fma(sigma_n + Pmax, a.deltaT, tv * sigma_n) : tv + a.deltaT;
-                const double mult = full ? 1.0 : mnum / mden;
+                const double mult = full ? 1.0 : mnum * fastRcp(mden);
                 const double elasticity = h * a.young * d * expC;
                 const double Dunit = a.dunitK * elasticity;
                 t11 = (t11 + Dunit * (g11 + a.nu0 * g22)) * mult;
@@ -359,14 +359,14 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
                 t12 = (t12 + Dunit * g12 * (1.0 - a.nu0)) * mult;
                 sigma_n = 0.5 * (t11 + t22);
                 const double tau2 = 0.25 * (t11 - t22) * (t11 - t22) + t12 * t12;
-                const double tau = tau2 > 0.0 ? tau2 * rsqrt(tau2) : 0.0; // sqrt to 1 ulp without the IEEE fix-up path
+                const double tau = fastSqrt(tau2);
                 const double cohesion = a.cohScale * h, compr = a.comprScale * h;
                 const double mc = tau + a.tan_phi * sigma_n;
                 // one division: the compressive cap, when active, replaces the Mohr-Coulomb value (same operands, same result)
                 const bool capped = sigma_n < -compr;
-                double dcrit = (capped || mc > 0.0) ? (capped ? -compr : cohesion) / (capped ? sigma_n : mc) : 1.0;
+                double dcrit = (capped || mc > 0.0) ? (capped ? -compr : cohesion) * fastRcp(capped ? sigma_n : mc) : 1.0;
                 dcrit = fmin(dcrit, 1.0);
-                const double sqrtE = elasticity > 0.0 ? elasticity * rsqrt(elasticity) : 0.0;
+                const double sqrtE = fastSqrt(elasticity);
                 const double relax = (1.0 - dcrit) * a.deltaT * (sqrtE * a.invTdK);
                 dG[q] = d - d * relax;
                 e11[q] = t11 - t11 * relax;
