@@ -989,8 +989,10 @@ public:
                     subcycle_strip_pmevp<true><<<nb, 32 * nw, pmevpSmemBytes(true), stream>>>(ua);
                 else
                     subcycle_strip_pmevp<false><<<nb, 32 * nw, pmevpSmemBytes(false), stream>>>(ua);
-            } else
-                subcycle_strip_umevp<0><<<nbStrip, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
+            } else {
+                const unsigned nb = (unsigned(nsx) * nsy + kUmevpWarps - 1) / kUmevpWarps;
+                subcycle_strip_umevp<0><<<nb, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
+            }
         }
     }
     void launchLinesFast(const UniformArgs& ua, size_t nLine)

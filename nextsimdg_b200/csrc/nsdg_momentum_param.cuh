@@ -395,11 +395,21 @@ template <bool SPH> struct PmevpStage {
     double UVr[2][2];
     double pad[2];
 };
-constexpr int pmevpWarps(bool sph) { return sph ? 2 : 3; }
-constexpr size_t pmevpSmemBytes(bool sph) { return sph ? sizeof(PmevpStage<true>) * 2 : sizeof(PmevpStage<false>) * 3; }
+#ifndef NSDG_COOP_PARAM_CART
+#define NSDG_COOP_PARAM_CART 0
+#endif
+//! staging mode of the plane rows: cooperative cp.async.cg on spherical meshes, per lane on Cartesian ones
+template <bool SPH> constexpr bool kCoopPmevp = SPH || (NSDG_COOP_PARAM_CART != 0);
+template <bool SPH> constexpr bool kCoopPbbm = SPH || (NSDG_COOP_PARAM_CART != 0);
+#ifndef NSDG_PMEVP_WARPS
+#define NSDG_PMEVP_WARPS 2 // 8 warps/SM with up to 255 registers beat 9 warps at 168 (0.91 -> 0.80 ms at 2048^2)
+#define NSDG_PMEVP_MINB 4
+#endif
+constexpr int pmevpWarps(bool sph) { return sph ? 2 : NSDG_PMEVP_WARPS; }
+constexpr size_t pmevpSmemBytes(bool sph) { return sph ? sizeof(PmevpStage<true>) * 2 : sizeof(PmevpStage<false>) * NSDG_PMEVP_WARPS; }
 
 template <bool SPH>
-__global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_strip_pmevp(const __grid_constant__ UniformArgs a)
+__global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MINB) subcycle_strip_pmevp(const __grid_constant__ UniformArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8;
     constexpr unsigned FULL = 0xffffffffu;
@@ -438,25 +448,25 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
         cpAsyncCommit();
     };
     auto issueP = [&](int row) {
-        stageBarrier<SPH>(); // every lane has consumed the region that is refilled
+        stageBarrier<kCoopPmevp<SPH>>(); // every lane has consumed the region that is refilled
         if (row < ey1)
-            stagePlanes<9, SPH>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
+            stagePlanes<9, kCoopPmevp<SPH>>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPmevp<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<8, SPH>(st.S, a.s11, Npad, first, lane);
-            stagePlanes<8, SPH>(st.S + 8, a.s12, Npad, first, lane);
-            stagePlanes<8, SPH>(st.S + 16, a.s22, Npad, first, lane);
+            stagePlanes<8, kCoopPmevp<SPH>>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, kCoopPmevp<SPH>>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, kCoopPmevp<SPH>>(st.S + 16, a.s22, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPmevp<SPH>>();
         if (row < ey1)
-            stagePlanes<geoPlanes(SPH), SPH>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
+            stagePlanes<geoPlanes(SPH), kCoopPmevp<SPH>>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueND = [&](int row) {
@@ -535,7 +545,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : 3) subcycle_st
 
         // ---- strain in the 9 Gauss points ----
         cpAsyncWait<2>(); // P, S and GEO of this row have landed
-        stageBarrier<SPH>(); //     (staged cooperatively: visible to every lane after the warp barrier)
+        stageBarrier<kCoopPmevp<SPH>>(); //     (staged cooperatively: visible to every lane after the warp barrier)
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 
@@ -732,30 +742,30 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
         cpAsyncCommit();
     };
     auto issueG = [&](int row) {
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<9, SPH>(st.G, a.gH, Npad, first, lane);
-            stagePlanes<9, SPH>(st.G + 9, a.gE, Npad, first, lane);
-            stagePlanes<9, SPH>(st.G + 18, a.gP, Npad, first, lane);
+            stagePlanes<9, kCoopPbbm<SPH>>(st.G, a.gH, Npad, first, lane);
+            stagePlanes<9, kCoopPbbm<SPH>>(st.G + 9, a.gE, Npad, first, lane);
+            stagePlanes<9, kCoopPbbm<SPH>>(st.G + 18, a.gP, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<8, SPH>(st.S, a.s11, Npad, first, lane);
-            stagePlanes<8, SPH>(st.S + 8, a.s12, Npad, first, lane);
-            stagePlanes<8, SPH>(st.S + 16, a.s22, Npad, first, lane);
-            stagePlanes<DGA, SPH>(st.D, a.damage, Npad, first, lane);
+            stagePlanes<8, kCoopPbbm<SPH>>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, kCoopPbbm<SPH>>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, kCoopPbbm<SPH>>(st.S + 16, a.s22, Npad, first, lane);
+            stagePlanes<DGA, kCoopPbbm<SPH>>(st.D, a.damage, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1)
-            stagePlanes<geoPlanesBBM(SPH), SPH>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
+            stagePlanes<geoPlanesBBM(SPH), kCoopPbbm<SPH>>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueND = [&](int row) {
@@ -835,7 +845,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 
         // ---- strain in the 9 Gauss points ----
         cpAsyncWait<2>(); // S, G and GEO of this row have landed
-        stageBarrier<SPH>();
+        stageBarrier<kCoopPbbm<SPH>>();
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 

@@ -249,7 +249,10 @@ struct UmevpStage {
     double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
     double pad[2];
 };
-constexpr int kUmevpWarps = 4;
+#ifndef NSDG_UMEVP_WARPS
+#define NSDG_UMEVP_WARPS 4
+#endif
+constexpr int kUmevpWarps = NSDG_UMEVP_WARPS;
 constexpr size_t kUmevpSmemBytes = sizeof(UmevpStage) * kUmevpWarps;
 
 #ifndef NSDG_UMEVP_MINBLOCKS

@@ -130,6 +130,10 @@ struct UbbmStage {
     double pad[2];
 };
 constexpr int kUbbmWarps = 4;
+#ifndef NSDG_COOP_UBBM
+#define NSDG_COOP_UBBM 0
+#endif
+constexpr bool kCoopUbbm = NSDG_COOP_UBBM != 0; //!< plane rows staged cooperatively (cp.async.cg) or per lane
 constexpr size_t kUbbmSmemBytes = sizeof(UbbmStage) * kUbbmWarps;
 
 template <int DUMMY = 0>
@@ -171,23 +175,23 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
         cpAsyncCommit();
     };
     auto issueG = [&](int row) {
-        stageBarrier<false>();
+        stageBarrier<kCoopUbbm>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<9, false>(st.G, a.gH, Npad, first, lane);
-            stagePlanes<9, false>(st.G + 9, a.gE, Npad, first, lane);
-            stagePlanes<9, false>(st.G + 18, a.gP, Npad, first, lane);
+            stagePlanes<9, kCoopUbbm>(st.G, a.gH, Npad, first, lane);
+            stagePlanes<9, kCoopUbbm>(st.G + 9, a.gE, Npad, first, lane);
+            stagePlanes<9, kCoopUbbm>(st.G + 18, a.gP, Npad, first, lane);
         }
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
-        stageBarrier<false>();
+        stageBarrier<kCoopUbbm>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<8, false>(st.S, a.s11, Npad, first, lane);
-            stagePlanes<8, false>(st.S + 8, a.s12, Npad, first, lane);
-            stagePlanes<8, false>(st.S + 16, a.s22, Npad, first, lane);
-            stagePlanes<DGA, false>(st.D, a.damage, Npad, first, lane);
+            stagePlanes<8, kCoopUbbm>(st.S, a.s11, Npad, first, lane);
+            stagePlanes<8, kCoopUbbm>(st.S + 8, a.s12, Npad, first, lane);
+            stagePlanes<8, kCoopUbbm>(st.S + 16, a.s22, Npad, first, lane);
+            stagePlanes<DGA, kCoopUbbm>(st.D, a.damage, Npad, first, lane);
         }
         cpAsyncCommit();
     };
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
         // ---- stress and damage coefficients of the row, then the BBM law point by point:
         //      e** become the updated Gauss-point stresses, dG the updated damage ----
         cpAsyncWait<3>();
-        stageBarrier<false>(); // S and D were staged cooperatively
+        stageBarrier<kCoopUbbm>(); // S and D were staged cooperatively
         double dG[9];
         {
             double s11c[DGs], s12c[DGs], s22c[DGs], dc[DGA];
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
             for (int j = 0; j < DGA; ++j)
                 dc[j] = st.D[j][lane];
             cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
-            stageBarrier<false>();
+            stageBarrier<kCoopUbbm>();
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
                 double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
