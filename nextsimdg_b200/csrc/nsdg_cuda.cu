@@ -93,7 +93,7 @@ public:
     DevBuf<double> u, v, u0, v0, cgH, cgA, gradX, gradY, uO, vO, uA, vA, lmass, avgU, avgV, taux, tauy;
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
-    DevBuf<double> ncC1, ncCA, ncRx, ncRy, ncIlm; // per-node constants of the uniform mEVP path
+    DevBuf<double> ncCA, ncRx, ncRy, ncIlm; // per-node constants of the fast paths (plus uO, vO)
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
     DevBuf<double> vcon; // compact node constants of the vertical deferred lines (vcon_kernel)
     bool fastUniformMEVP = false, fastUniformBBM = false;
@@ -388,7 +388,7 @@ public:
         fastParamBBM = !uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6 && !cfg.force_general
             && !std::getenv("NSDG_NO_FAST_PARAM");
         if (fastBBM()) {
-            for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
+            for (auto* f : { &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
             gaussC.alloc(size_t(Q) * Npad);
             if constexpr (CG == 2 && DGA == 6) {
@@ -403,7 +403,7 @@ public:
         fastParamMEVP = !uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
             && !std::getenv("NSDG_NO_FAST_PARAM");
         if (fastMEVP()) {
-            for (auto* f : { &ncC1, &ncCA, &ncRx, &ncRy, &ncIlm })
+            for (auto* f : { &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
             if constexpr (CG == 2 && DGA == 6) {
                 NSDG_CUDA_CHECK(cudaFuncSetAttribute(
@@ -893,7 +893,6 @@ public:
         a.landmask = d_landmask;
         a.u = u;
         a.v = v;
-        a.c1 = ncC1;
         a.cA = ncCA;
         a.rx = ncRx;
         a.ry = ncRy;
@@ -932,7 +931,6 @@ public:
         a.v = v;
         a.avgU = avgU;
         a.avgV = avgV;
-        a.dte = ncC1;
         a.cA = ncCA;
         a.ax = ncRx;
         a.ay = ncRy;
@@ -1188,9 +1186,9 @@ public:
                 g, p, hice, cice, gaussA, gaussB, fastMEVP() ? 1.0 / p.alpha : 1.0);
             if (fastMEVP()) {
                 nodeconst_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
-                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
+                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncCA, ncRx, ncRy, ncIlm);
                 vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
-                    g, nsx, ncC1, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
+                    g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 2;
             }
         } else { // BrittleCGDynamicsKernel.hpp:110-114
@@ -1200,9 +1198,9 @@ public:
             if (fastBBM()) {
                 gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
                 nodeconst_bbm_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
-                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncC1, ncCA, ncRx, ncRy, ncIlm);
+                    g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncCA, ncRx, ncRy, ncIlm);
                 vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
-                    g, nsx, ncC1, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
+                    g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 2;
             } else
                 gaussconst_kernel<DGA, GS, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, 1.0);

@@ -390,7 +390,7 @@ template <bool SPH> struct PmevpStage {
     double P[9][32];
     double S[24][32];
     double GEO[geoPlanes(SPH)][32];
-    double2 ND[2][7][32];
+    double2 ND[2][kNodeConsts][32];
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -474,13 +474,12 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16cg(&st.ND[k][0][lane], a.c1 + n);
-                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16cg(&st.ND[k][2][lane], a.rx + n);
-                cpAsync16cg(&st.ND[k][3][lane], a.ry + n);
-                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.rx + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ry + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
             }
         }
         cpAsyncCommit();
@@ -604,8 +603,8 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 c1 = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], rx = st.ND[jy][2][lane], ry = st.ND[jy][3][lane];
-            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const double2 cA = st.ND[jy][0][lane], rx = st.ND[jy][1][lane], ry = st.ND[jy][2][lane];
+            const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
             const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
@@ -616,9 +615,9 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
             }
             const bool d0 = msk.x & 1, d1 = msk.y & 1;
             double2 un, vn;
-            momentumNodeUniform(a, c1.x, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+            momentumNodeUniform(a, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x);
-            momentumNodeUniform(a, c1.y, cA.y, rx.y, ry.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+            momentumNodeUniform(a, cA.y, rx.y, ry.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
                 d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y);
             const bool rowSkip = !active || (jy == 0 && bottomDeferred);
             const bool skip0 = rowSkip || (lane == 0 && sx > 0);
@@ -693,7 +692,7 @@ template <bool SPH> struct PbbmStage {
     double S[24][32];
     double D[6][32];
     double GEO[geoPlanesBBM(SPH)][32];
-    double2 ND[2][7][32];
+    double2 ND[2][kNodeConsts][32];
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -773,13 +772,12 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16cg(&st.ND[k][0][lane], a.dte + n);
-                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16cg(&st.ND[k][2][lane], a.ax + n);
-                cpAsync16cg(&st.ND[k][3][lane], a.ay + n);
-                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.ax + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ay + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
                 prefetchL2(a.avgU + n); // read-modify-written at the end of the row
                 prefetchL2(a.avgV + n);
             }
@@ -979,8 +977,8 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 dte = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], ax = st.ND[jy][2][lane], ay = st.ND[jy][3][lane];
-            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const double2 cA = st.ND[jy][0][lane], ax = st.ND[jy][1][lane], ay = st.ND[jy][2][lane];
+            const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
             const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
@@ -991,9 +989,9 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
             }
             const bool d0 = msk.x & 1, d1 = msk.y & 1;
             double2 un, vn, ua, va;
-            momentumNodeUniformBBM(a, dte.x, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+            momentumNodeUniformBBM(a, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
-            momentumNodeUniformBBM(a, dte.y, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+            momentumNodeUniformBBM(a, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
                 d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y, ua.y, va.y);
             const bool rowSkip = !active || (jy == 0 && bottomDeferred);
             const bool skip0 = rowSkip || (lane == 0 && sx > 0);

@@ -85,7 +85,7 @@ struct UniformArgs {
     const double* Pa; //!< Gauss-point planes of P/alpha, P = P* h exp(-20(1-a))
     const uint8_t* landmask;
     double *u, *v;
-    const double *c1, *cA, *rx, *ry, *uO, *vO, *ilm; //!< per-node constants (nodeconst_kernel)
+    const double *cA, *rx, *ry, *uO, *vO, *ilm; //!< per-node constants (nodeconst_kernel)
     const double* vcon; //!< compact per-vertical-line copies of the node constants (vcon_kernel)
     const double* geo; //!< parametric fast path: kGeoPlanes geometry planes (nsdg_momentum_param.cuh)
     const uint8_t* nodemask;
@@ -97,43 +97,43 @@ struct UniformArgs {
 };
 
 /*
- * Per-node constants of VPCGDynamicsKernel::updateMomentum (VPCGDynamicsKernel.hpp:147-170):
- *   c1  = rho_ice cgH / deltaT
- *   cA  = cgA F_ocean
- *   rx  = c1 u0 + cgA F_atm |ua| ua - rho_ice cgH g dSSH/dx          (ry alike)
- *   ilm = 1 / lumpedcgmass
- * so that   u_new = ( c1 beta u + rx + cA |du_ocn| uO - c1 dt fc u + dStressX ilm ) / ( c1 (1+beta) + cA |du_ocn| ).
+ * Per-node constants of VPCGDynamicsKernel::updateMomentum (VPCGDynamicsKernel.hpp:147-170).  With
+ *   c1 = rho_ice cgH / deltaT   (> 0: cgH is clamped to 1e-4 in prepareIteration)
+ * the update  u_new = ( c1 beta u + R + cgA F_ocean |du_ocn| uO - c1 dt fc u + dStressX / lumpedmass ) / ( c1 (1+beta) + cgA F_ocean |du_ocn| ),
+ * R = c1 u0 + cgA F_atm |ua| ua - rho_ice cgH g dSSH/dx, is divided through by c1, which leaves SIX constants per node:
+ *   cA  = cgA F_ocean / c1,   rx = R_x / c1,   ry = R_y / c1,   ilm = 1 / (lumpedcgmass c1),   and uO, vO
+ * (one array and 32 B per element and subcycle less than keeping c1).
  */
 __global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
     const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
     const double* __restrict__ gy, const double* __restrict__ u0, const double* __restrict__ v0, const double* __restrict__ lm,
-    double* __restrict__ c1, double* __restrict__ cA, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ ilm)
+    double* __restrict__ cA, double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ ilm)
 {
     const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= long(g.cgnx) * g.cgny)
         return;
     const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
     const double H = cgH[n], A = cgA[n];
-    const double k1 = p.rho_ice * H / deltaT;
+    const double k1 = p.rho_ice * H / deltaT, ik1 = 1.0 / k1;
     const double absatm = sqrt(uA[n] * uA[n] + vA[n] * vA[n]);
-    c1[n] = k1;
-    cA[n] = A * p.F_ocean;
-    rx[n] = k1 * u0[n] + A * (p.F_atm * absatm * uA[n]) - p.rho_ice * H * p.gravity * gx[n];
-    ry[n] = k1 * v0[n] + A * (p.F_atm * absatm * vA[n]) - p.rho_ice * H * p.gravity * gy[n];
-    ilm[n] = 1.0 / lm[n];
+    cA[n] = A * p.F_ocean * ik1;
+    rx[n] = (k1 * u0[n] + A * (p.F_atm * absatm * uA[n]) - p.rho_ice * H * p.gravity * gx[n]) * ik1;
+    ry[n] = (k1 * v0[n] + A * (p.F_atm * absatm * vA[n]) - p.rho_ice * H * p.gravity * gy[n]) * ik1;
+    ilm[n] = ik1 / lm[n];
 }
 
 /*
  * The nodes of the vertical deferred lines (every 64th node column) are visited column-wise by the lines kernels:
- * a strided walk through the row-major node arrays costs one 64-B DRAM atom per 8-B value.  Their seven constants
+ * a strided walk through the row-major node arrays costs one 64-B DRAM atom per 8-B value.  Their six constants
  * and the Dirichlet flag are therefore gathered once per timestep into a compact array
- *     vcon[(k * nsx + line) * cgny + row],  k = 0..7,
+ *     vcon[(k * nsx + line) * cgny + row],  k = 0..6,
  * so that only u and v remain strided (lines kernel: 394 -> ~190 MB per launch at 2048^2).
  */
-constexpr int kVconPlanes = 8;
+constexpr int kNodeConsts = 6;
+constexpr int kVconPlanes = kNodeConsts + 1;
 __global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2,
-    const double* __restrict__ k3, const double* __restrict__ k4, const double* __restrict__ k5, const double* __restrict__ k6,
-    const uint8_t* __restrict__ nodemask, double* __restrict__ vcon)
+    const double* __restrict__ k3, const double* __restrict__ k4, const double* __restrict__ k5, const uint8_t* __restrict__ nodemask,
+    double* __restrict__ vcon)
 {
     const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= long(nsx) * g.cgny)
@@ -141,11 +141,11 @@ __global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, 
     const int line = int(t / g.cgny), r = int(t % g.cgny);
     const int c = min(2 * 32 * (line + 1), 2 * g.nx);
     const size_t n = size_t(r) * g.cgs + c;
-    const double* src[7] = { k0, k1, k2, k3, k4, k5, k6 };
+    const double* src[kNodeConsts] = { k0, k1, k2, k3, k4, k5 };
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
+    for (int k = 0; k < kNodeConsts; ++k)
         vcon[(size_t(k) * nsx + line) * g.cgny + r] = src[k][n];
-    vcon[(size_t(7) * nsx + line) * g.cgny + r] = (nodemask[n] & 1) ? 1.0 : 0.0;
+    vcon[(size_t(kNodeConsts) * nsx + line) * g.cgny + r] = (nodemask[n] & 1) ? 1.0 : 0.0;
 }
 
 /*
@@ -166,17 +166,16 @@ __device__ __forceinline__ double fastRcp(double x)
 __device__ __forceinline__ double fastSqrt(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
 
 //! mEVP momentum update of one node from the per-node constants (+ Dirichlet)
-__device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double c1, double cA, double rx, double ry, double uO,
-    double vO, double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew)
+__device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double cA, double rx, double ry, double uO, double vO,
+    double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew)
 {
     const double uOcnRel = uO - un;
     const double vOcnRel = vn - vO;
     const double absocn = fastSqrt(uOcnRel * uOcnRel + vOcnRel * vOcnRel);
     const double drag = cA * absocn;
-    const double inv = fastRcp(c1 * (1.0 + a.beta) + drag);
-    const double cf = c1 * a.dtfc;
-    unew = inv * (c1 * (a.beta * un) + rx + drag * uO - cf * un + dSx * ilm);
-    vnew = inv * (c1 * (a.beta * vn) + ry + drag * vO + cf * vn + dSy * ilm);
+    const double inv = fastRcp((1.0 + a.beta) + drag);
+    unew = inv * (a.beta * un + rx + drag * uO - a.dtfc * un + dSx * ilm);
+    vnew = inv * (a.beta * vn + ry + drag * vO + a.dtfc * vn + dSy * ilm);
     if (dirichlet) {
         unew = 0.0;
         vnew = 0.0;
@@ -236,7 +235,7 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("c
  * of the register file that is filled one element row ahead of use, region by region:
  *   P   9 x 32 doubles      Gauss-point P/alpha of the row          refilled right after the VP law
  *   S  24 x 32 doubles      the three DG8 stresses of the row       refilled after the projection
- *   ND  2 x 7 x 32 double2  the seven node constants, 2 node rows   refilled after the momentum update
+ *   ND  2 x 6 x 32 double2  the six node constants, 2 node rows     refilled after the momentum update
  *   UV  2 x 2 x 32 double2  u, v of the two upper node rows         refilled at the top of the row
  * Four groups are always in flight; cp.async groups retire in order, so "wait_group 3" before each
  * region's first read is exactly "the group issued one row ago has landed".
@@ -244,7 +243,7 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("c
 struct UmevpStage {
     double P[9][32];
     double S[24][32];
-    double2 ND[2][7][32];
+    double2 ND[2][kNodeConsts][32];
     double2 UV[2][2][32];
     double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
     double pad[2];
@@ -318,13 +317,12 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16cg(&st.ND[k][0][lane], a.c1 + n);
-                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16cg(&st.ND[k][2][lane], a.rx + n);
-                cpAsync16cg(&st.ND[k][3][lane], a.ry + n);
-                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.rx + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ry + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
             }
         }
         cpAsyncCommit();
@@ -556,8 +554,8 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 c1 = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], rx = st.ND[jy][2][lane], ry = st.ND[jy][3][lane];
-            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const double2 cA = st.ND[jy][0][lane], rx = st.ND[jy][1][lane], ry = st.ND[jy][2][lane];
+            const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
             const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
@@ -568,9 +566,9 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
             }
             const bool d0 = msk.x & 1, d1 = msk.y & 1;
             double2 un, vn;
-            momentumNodeUniform(a, c1.x, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+            momentumNodeUniform(a, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x);
-            momentumNodeUniform(a, c1.y, cA.y, rx.y, ry.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+            momentumNodeUniform(a, cA.y, rx.y, ry.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
                 d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y);
             const bool rowSkip = !active || (jy == 0 && bottomDeferred);
             const bool skip0 = rowSkip || (lane == 0 && sx > 0);
@@ -653,23 +651,23 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
         }
     }
     const size_t n = size_t(r) * g.cgs + c;
-    double k[7];
+    double k[kNodeConsts];
     bool d;
     if (t < nH) {
-        const double* src[7] = { a.c1, a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
+        const double* src[kNodeConsts] = { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < kNodeConsts; ++i)
             k[i] = __ldg(src[i] + n);
         d = __ldg(a.nodemask + n) & 1;
     } else { // vertical line: compact copies (vcon_kernel)
         const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < kNodeConsts; ++i)
             k[i] = __ldg(a.vcon + i * pitch + m);
-        d = __ldg(a.vcon + 7 * pitch + m) != 0.0;
+        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
     }
     double un, vn;
-    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], k[6], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
+    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
     a.u[n] = un;
     a.v[n] = vn;
 }

@@ -27,7 +27,7 @@ struct UniformBBMArgs {
     const double *gH, *gE, *gP; //!< Gauss-point planes: h, expC, Pmax
     const uint8_t* landmask;
     double *u, *v, *avgU, *avgV;
-    const double *dte, *cA, *ax, *ay, *uO, *vO, *ilm; //!< per-node constants
+    const double *cA, *ax, *ay, *uO, *vO, *ilm; //!< per-node constants (all pre-multiplied by dte = deltaT / (rho cgH))
     const uint8_t* nodemask;
     double *hbuf, *vbuf;
     double dx, dy;
@@ -43,11 +43,12 @@ struct UniformBBMArgs {
     double C_lab, compr_strength;
 };
 
-//! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240)
+//! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240); the factor
+//! dte = deltaT / (rho_ice cgH) that multiplies every one of them in the update is folded in (six arrays instead of seven)
 __global__ void nodeconst_bbm_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
     const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
-    const double* __restrict__ gy, const double* __restrict__ lm, double* __restrict__ dte, double* __restrict__ cA,
-    double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ ilm)
+    const double* __restrict__ gy, const double* __restrict__ lm, double* __restrict__ cA, double* __restrict__ ax,
+    double* __restrict__ ay, double* __restrict__ ilm)
 {
     const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= long(g.cgnx) * g.cgny)
@@ -55,11 +56,11 @@ __global__ void nodeconst_bbm_kernel(GridDims g, PhysParams p, double deltaT, co
     const size_t n = size_t(t / g.cgnx) * g.cgs + (t % g.cgnx);
     const double H = cgH[n], A = cgA[n];
     const double dragAtm = A * p.F_atm * hypot(uA[n], vA[n]);
-    dte[n] = deltaT / (p.rho_ice * H);
-    cA[n] = A * p.F_ocean;
-    ax[n] = dragAtm * uA[n] - p.rho_ice * H * p.gravity * gx[n];
-    ay[n] = dragAtm * vA[n] - p.rho_ice * H * p.gravity * gy[n];
-    ilm[n] = 1.0 / lm[n];
+    const double dte = deltaT / (p.rho_ice * H);
+    cA[n] = dte * (A * p.F_ocean);
+    ax[n] = dte * (dragAtm * uA[n] - p.rho_ice * H * p.gravity * gx[n]);
+    ay[n] = dte * (dragAtm * vA[n] - p.rho_ice * H * p.gravity * gy[n]);
+    ilm[n] = dte / lm[n];
 }
 
 //! Gauss-point constants of the BBM law: h, exp(C(1-a)), Pmax (uniform path: one extra plane saves the pow)
@@ -99,19 +100,18 @@ __global__ void gaussconst_bbm3_kernel(GridDims g, PhysParams p, const double* _
 }
 
 //! brittle momentum update of one node from the per-node constants; returns the pre-boundary value for the mean
-__device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, double dte, double cA, double ax, double ay,
-    double uO, double vO, double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew,
-    double& uAvg, double& vAvg)
+__device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, double cA, double ax, double ay, double uO, double vO,
+    double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew, double& uAvg, double& vAvg)
 {
     const double du = uO - un, dv = vO - vn;
-    const double cPrime = cA * fastSqrt(du * du + dv * dv);
-    const double alpha = 1.0 + dte * (cPrime * a.cosA);
-    const double beta = a.dtfc + dte * cPrime * a.sinA;
+    const double cPrime = cA * fastSqrt(du * du + dv * dv); // dte * cPrime of the reference
+    const double alpha = 1.0 + cPrime * a.cosA;
+    const double beta = a.dtfc + cPrime * a.sinA;
     const double rDenom = fastRcp(alpha * alpha + beta * beta);
-    const double X = dSx * ilm + ax + cPrime * (uO * a.cosA - vO * a.sinA); // gradX + tauX
-    const double Y = dSy * ilm + ay + cPrime * (vO * a.cosA + uO * a.sinA); // gradY + tauY
-    unew = (alpha * un + beta * vn + dte * (alpha * X + beta * Y)) * rDenom;
-    vnew = (alpha * vn - beta * un + dte * (alpha * Y + beta * X)) * rDenom; // quirk Q3: "+ beta X" as in the reference
+    const double X = dSx * ilm + ax + cPrime * (uO * a.cosA - vO * a.sinA); // dte (gradX + tauX)
+    const double Y = dSy * ilm + ay + cPrime * (vO * a.cosA + uO * a.sinA); // dte (gradY + tauY)
+    unew = (alpha * un + beta * vn + (alpha * X + beta * Y)) * rDenom;
+    vnew = (alpha * vn - beta * un + (alpha * Y + beta * X)) * rDenom; // quirk Q3: "+ beta X" as in the reference
     uAvg = unew * a.invNSteps; // taken before applyBoundaries, as in the reference
     vAvg = vnew * a.invNSteps;
     if (dirichlet) {
@@ -124,7 +124,7 @@ struct UbbmStage {
     double G[27][32]; //!< h, expC, Pmax in the 9 Gauss points
     double S[24][32];
     double D[6][32];
-    double2 ND[2][7][32];
+    double2 ND[2][kNodeConsts][32];
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -200,13 +200,12 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16cg(&st.ND[k][0][lane], a.dte + n);
-                cpAsync16cg(&st.ND[k][1][lane], a.cA + n);
-                cpAsync16cg(&st.ND[k][2][lane], a.ax + n);
-                cpAsync16cg(&st.ND[k][3][lane], a.ay + n);
-                cpAsync16cg(&st.ND[k][4][lane], a.uO + n);
-                cpAsync16cg(&st.ND[k][5][lane], a.vO + n);
-                cpAsync16cg(&st.ND[k][6][lane], a.ilm + n);
+                cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
+                cpAsync16cg(&st.ND[k][1][lane], a.ax + n);
+                cpAsync16cg(&st.ND[k][2][lane], a.ay + n);
+                cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
+                cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
+                cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
                 prefetchL2(a.avgU + n); // read-modify-written at the end of the row
                 prefetchL2(a.avgV + n);
             }
@@ -491,8 +490,8 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 dte = st.ND[jy][0][lane], cA = st.ND[jy][1][lane], ax = st.ND[jy][2][lane], ay = st.ND[jy][3][lane];
-            const double2 uO = st.ND[jy][4][lane], vO = st.ND[jy][5][lane], ilm = st.ND[jy][6][lane];
+            const double2 cA = st.ND[jy][0][lane], ax = st.ND[jy][1][lane], ay = st.ND[jy][2][lane];
+            const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
             const uchar2 msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
@@ -503,9 +502,9 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
             }
             const bool d0 = msk.x & 1, d1 = msk.y & 1;
             double2 un, vn, ua, va;
-            momentumNodeUniformBBM(a, dte.x, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
+            momentumNodeUniformBBM(a, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
-            momentumNodeUniformBBM(a, dte.y, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
+            momentumNodeUniformBBM(a, cA.y, ax.y, ay.y, uO.y, vO.y, ilm.y, d1, ul[jy * NR + 1], vl[jy * NR + 1],
                 d1 ? 0.0 : -sx1, d1 ? 0.0 : -sy1, un.y, vn.y, ua.y, va.y);
             const bool rowSkip = !active || (jy == 0 && bottomDeferred);
             const bool skip0 = rowSkip || (lane == 0 && sx > 0);
@@ -597,23 +596,23 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
         }
     }
     const size_t n = size_t(r) * g.cgs + c;
-    double k[7];
+    double k[kNodeConsts];
     bool d;
     if (t < nH) {
-        const double* src[7] = { a.dte, a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
+        const double* src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < kNodeConsts; ++i)
             k[i] = __ldg(src[i] + n);
         d = __ldg(a.nodemask + n) & 1;
     } else { // vertical line: compact copies (vcon_kernel)
         const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < kNodeConsts; ++i)
             k[i] = __ldg(a.vcon + i * pitch + m);
-        d = __ldg(a.vcon + 7 * pitch + m) != 0.0;
+        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
     }
     double un, vn, ua, va;
-    momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], k[6], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
+    momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
     a.u[n] = un;
     a.v[n] = vn;
     a.avgU[n] += ua;
