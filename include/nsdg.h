@@ -151,6 +151,14 @@ int nsdg_get_dirichlet(nsdg_handle h, int edge /* 0 bottom,1 right,2 top,3 left 
 int nsdg_get_internal(nsdg_handle h, const char* name, double* host, size_t capacity, size_t* count);
 int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_t count);
 
+/* Damage healing on the device: Nextsim::ConstantHealing::updateElement
+ * (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:60-80) applied to the DG0 damage of a BBM handle, so that
+ * the damage can stay resident between nsdg_step calls:
+ *   damage = (damage (cice - g) + g) / cice,  g = max(0, delta_cice);  damage = min(1, damage + dt / td).
+ * delta_cice: host array of nx*ny lateral concentration growth from the thermodynamics, or NULL for none.
+ * td_seconds: ConstantHealing.td (default 15 days) in seconds. */
+int nsdg_heal_damage(nsdg_handle h, double dt_seconds, double td_seconds, const double* delta_cice);
+
 /* ---- restart state --------------------------------------------------------------------------------
  * Everything the dynamics carries from one timestep to the next, in the reference's layouts, as one flat buffer of
  * doubles: an 8-double header {magic, version, rheology, dgadv, cgdegree, nx, ny, nfields}, then per field its

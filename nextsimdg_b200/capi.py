@@ -59,6 +59,7 @@ SIGNATURES = {
     "nsdg_get_dirichlet": (c_int, [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),
     "nsdg_get_internal": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t, POINTER(c_size_t)]),
     "nsdg_set_internal": (c_int, [c_void_p, c_char_p, c_void_p, c_size_t]),
+    "nsdg_heal_damage": (c_int, [c_void_p, ctypes.c_double, ctypes.c_double, c_void_p]),
     "nsdg_get_state": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
     "nsdg_set_state": (c_int, [c_void_p, c_void_p, c_size_t]),
     "nsdg_subcycles": (c_int, [c_void_p, c_int, POINTER(c_float)]),

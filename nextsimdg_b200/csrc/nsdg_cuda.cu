@@ -47,6 +47,7 @@ public:
     virtual void setInternal(const std::string& name, const double* host, size_t count) = 0;
     virtual void benchmarkForcing(double elapsed, double Lx, double Ly) = 0;
     virtual void dims(int* nx, int* ny) = 0;
+    virtual void healDamage(double dt, double td, const double* deltaCi) = 0;
     virtual void haloExport(unsigned char* handle) = 0;
     virtual void haloConnect(int side, const unsigned char* handle) = 0;
     virtual void haloReady() = 0;
@@ -1340,6 +1341,21 @@ public:
         out = it->second;
         return true;
     }
+    void healDamage(double dt, double td, const double* deltaCi) override
+    {
+        requireMesh();
+        if (cfg.rheology != NSDG_BBM)
+            throw std::runtime_error("nsdg_heal_damage: the handle has no damage field (BBM only)");
+        if (!(td > 0.0))
+            throw std::runtime_error("nsdg_heal_damage: td must be positive");
+        const double* dci = nullptr;
+        if (deltaCi) { // DG0 host field -> plane 0 of the scratch field
+            uploadPlanes(deltaCi, 1, 1, scratchDG);
+            dci = scratchDG;
+        }
+        healing_kernel<<<blocksFor(g.N), 128, 0, stream>>>(g, dt, td, dci, cice, damage);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     void dims(int* nx, int* ny) override
     {
         requireMesh();
@@ -1602,6 +1618,12 @@ int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_
 {
     NSDG_TRY
     H(h)->setInternal(name, host, count);
+    NSDG_CATCH
+}
+int nsdg_heal_damage(nsdg_handle h, double dt_seconds, double td_seconds, const double* delta_cice)
+{
+    NSDG_TRY
+    H(h)->healDamage(dt_seconds, td_seconds, delta_cice);
     NSDG_CATCH
 }
 namespace {

@@ -289,6 +289,25 @@ __global__ void freedrift_kernel(GridDims g, PhysParams p, const double* __restr
     v[n] = vn;
 }
 
+/*
+ * IDamageHealing::ConstantHealing::updateElement (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:60-80) on
+ * the DG0 damage and concentration:  lateral ice formation is undamaged, then linear healing with time scale tD.
+ * deltaCi may be null (no thermodynamic growth, as with DummyIceThermodynamics).
+ */
+__global__ void healing_kernel(GridDims g, double step, double tD, const double* __restrict__ deltaCi, const double* __restrict__ cice,
+    double* __restrict__ damage)
+{
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
+    const double lateralGrowth = deltaCi ? fmax(0., deltaCi[e]) : 0.;
+    double d = damage[e];
+    d = (d * (cice[e] - lateralGrowth) + lateralGrowth) / cice[e];
+    d += step / tD;
+    damage[e] = fmin(1., d);
+}
+
 //! The reference's benchmark forcing per element (cell lower-left corner coordinates x = i dx, y = j dy of the
 //! GLOBAL grid): BenchmarkAtmosphere.cpp:38-74 (cyclone centred at x0c, y0c) and BenchmarkOcean.cpp:27-36.
 __global__ void benchforcing_kernel(GridDims g, int gi0, int gj0, double dx, double dy, double x0c, double y0c, double cosa,

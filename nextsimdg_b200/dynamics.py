@@ -150,6 +150,14 @@ class CUDADynamicsBase:
         a = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
         check(self._lib.nsdg_set_internal(self._h, name.encode(), as_c(a), a.size))
 
+    def heal_damage(self, dt: float, td_seconds: float = 15 * 86400.0, delta_cice: np.ndarray | None = None):
+        """Nextsim::ConstantHealing on the device-resident DG0 damage (ConstantHealing.cpp:60-80); BBM handles only."""
+        ptr = None
+        if delta_cice is not None:
+            self._dci = np.ascontiguousarray(delta_cice, dtype=np.float64)
+            ptr = self._dci.ctypes.data_as(c_void_p)
+        check(self._lib.nsdg_heal_damage(self._h, float(dt), float(td_seconds), ptr))
+
     # -- restart state (SURVEY 8(f) N3): everything carried from one timestep to the next, one flat float64 buffer
     def get_state(self) -> np.ndarray:
         n = ctypes.c_size_t()

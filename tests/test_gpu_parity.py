@@ -275,6 +275,33 @@ def test_restart_state_resumes_bitwise(rheo):
         other.set_state(state)
 
 
+def test_constant_healing_on_device():
+    """nsdg_heal_damage (N4) against the restatement of ConstantHealing::updateElement, bit-exact arithmetic."""
+    from oracle.healing import constant_healing
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, NsdgError, synthetic
+
+    nx, ny = 37, 21
+    ms = synthetic.para_state(nx, ny, irregular_mask=True)
+    rng = np.random.default_rng(7)
+    ice = ms["mask"].astype(bool)
+    cice = np.where(ice, 0.5 + 0.4 * rng.random((ny, nx)), 1.0)
+    dmg = np.where(ice, 0.2 + 0.8 * rng.random((ny, nx)), 1.0)
+    dci = 0.05 * (rng.random((ny, nx)) - 0.5)
+    d = CUDABBMDynamics(nsteps=1)
+    ms2 = dict(ms, cice=cice, damage=dmg)
+    d.setData(ms2)
+    for delta in (None, dci):
+        d._set("damage", dmg)
+        d.heal_damage(900.0, 2 * 86400.0, delta)
+        got = d.getDG0Data("damage")
+        want = constant_healing(dmg, cice, delta, 900.0, 2 * 86400.0)
+        assert np.abs(got - want).max() <= 4e-16, np.abs(got - want).max()  # fma contraction: <= 1 ulp
+    with pytest.raises(NsdgError):
+        m = CUDAMEVPDynamics(nsteps=1)
+        m.setData(ms)
+        m.heal_damage(900.0)
+
+
 def test_cuda_graph_and_plain_launches_identical():
     from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
 
