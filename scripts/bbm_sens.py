@@ -1,6 +1,6 @@
 import os, sys, subprocess, pickle
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1:
     from nextsimdg_b200 import CUDABBMDynamics, synthetic
     ms = synthetic.para_state(96, 64, dxy=8000.0, distort=0.04, irregular_mask=True)
