@@ -352,35 +352,44 @@ def test_error_behaviour():
         d._set("hice", np.zeros((8, 8, 4)))  # neither 1 nor DGCOMP components
 
 
-def test_locality_and_determinism_at_full_size():
-    """BASELINE size (2048 x 2048, mEVP, uniform path): (a) two runs are bitwise identical;
-    (b) information travels one element per subcycle, so after k subcycles a window far from the crop
-    edge equals the same window computed on a small cropped domain -- checked against the ORACLE run on
-    the crop, which ties the full-size run to the oracle without running the oracle at full size."""
+@pytest.mark.parametrize("rheo,mesh", [("mevp", "rect"), ("mevp", "distorted"), ("bbm", "rect"), ("bbm", "distorted")])
+def test_locality_and_determinism_at_full_size(rheo, mesh):
+    """BASELINE size (2048 x 2048), every fast kernel: (a) two runs are bitwise identical; (b) information travels one
+    element per subcycle, so after k subcycles a window far from the crop edge equals the same window computed on a
+    small cropped domain -- checked against the ORACLE run on the crop (the reference's own kernels when oracle/_ref
+    travelled), which ties the full-size run to the oracle without running the oracle at full size."""
     import oracle
-    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, synthetic
 
-    n, crop, k, dt = 2048, 96, 12, 120.0
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    n, crop = 2048, 96
+    # BBM subcycles with dt / nSteps: keep the reference's 1.2 s (120 s / 100); 10 s would put the explicit elastic
+    # scheme at c_elastic dt_sub / dx ~ 2, where rounding noise is amplified and no two summation orders agree.
+    # dt must be a whole number of seconds (the reference's TimestepTime::step.seconds() is integral, quirk Q11).
+    k, dt = (12, 120.0) if rheo == "mevp" else (10, 12.0)
     L = 4000.0 * n  # stable mEVP regime (>= 2 km cells for alpha = beta = 1500, dt = 120 s)
     ms = synthetic.benchmark_box(n, L=L, ring_mask=False)
+    if mesh == "distorted":
+        ms["coords"] = synthetic.distort_coords(ms["coords"], 0.02)
     f = synthetic.benchmark_forcing(n, 0.0, L=L)
     runs = []
     for _ in range(2):
-        d = CUDAMEVPDynamics(nsteps=k)
+        d = cls(nsteps=k)
         d.setData(ms)
         d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{a: b.copy() for a, b in f.items()}}
         d.update(dt)
+        assert d.timing().uniform_path == (1 if mesh == "rect" else 0)
         runs.append((d.uice.copy(), d.vice.copy()))
         d.close()
     assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
-    # crop window [j0:j0+crop, i0:i0+crop] of the big domain, translated to the origin
+    # crop window [j0:j0+crop, i0:i0+crop] of the big domain (translated to the origin: Cartesian operators are translation invariant)
     i0, j0 = 1000, 700
     sl = (slice(j0, j0 + crop), slice(i0, i0 + crop))
     msc = {"coords": np.ascontiguousarray(ms["coords"][j0:j0 + crop + 1, i0:i0 + crop + 1] - ms["coords"][j0, i0]),
            "mask": np.ones((crop, crop)), "x": np.zeros((crop, crop)), "y": np.zeros((crop, crop)),
            "hice": np.ascontiguousarray(ms["hice"][sl]), "cice": np.ascontiguousarray(ms["cice"][sl]),
            "u": np.zeros((crop, crop)), "v": np.zeros((crop, crop))}
-    ref = oracle.OracleDynamics("mevp", 6, 2, k)
+    ref = oracle.OracleDynamics(rheo, 6, 2, k, impl="reference" if oracle.have_ref(2) else "port")
     ref.setData(msc)
     ref.shared = {"hice": msc["hice"].copy(), "cice": msc["cice"].copy(), **{a: np.ascontiguousarray(b[sl]) for a, b in f.items()}}
     ref.update(dt)
