@@ -322,18 +322,18 @@ public:
             setup_transport_kernel<DGs><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, topS, nel);
             helem_kernel<<<blocksFor(N), 128, 0, stream>>>(g, vx, vy, helem);
         }
-        oGx.alloc(size_t(DGs) * ND * opN);
-        oGy.alloc(size_t(DGs) * ND * opN);
-        oB.alloc(size_t(DGs) * Q * opN);
-        oBd.alloc(size_t(DGA) * Q * opN);
-        oD1.alloc(size_t(ND) * DGs * opN);
-        oD2.alloc(size_t(ND) * DGs * opN);
+        // the streamed per-element matrices (360 - 558 doubles per element) are built only for the kernel that streams
+        // them; the factored-operator kernels need the 4 x 4 SSH matrices alone (ensureStreamedOps builds the rest on demand)
+        const bool factored = !uniform && CG == 2 && DGA == 6 && !cfg.force_general && !std::getenv("NSDG_NO_FAST_PARAM")
+            && (cfg.rheology == NSDG_MEVP || cfg.rheology == NSDG_BBM);
         odX.alloc(16 * opN);
         odY.alloc(16 * opN);
-        oGM.alloc(spherical ? size_t(DGs) * ND * opN : 0);
-        oDM.alloc(spherical ? size_t(ND) * DGs * opN : 0);
-        mop = { oGx, oGy, oGM, oB, oBd, oD1, oD2, oDM, odX, odY, opN, uniform ? 0 : 1 };
-        setup_momentum_kernel<CG, DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, mop, nel);
+        streamedOpsBuilt = false;
+        mop = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, odX, odY, opN, uniform ? 0 : 1 };
+        if (factored)
+            setup_momentum_kernel<CG, DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, mop, nel, false);
+        else
+            ensureStreamedOps();
         constexpr int CGGP = (CG == 1 ? 1 : 4);
         lumpedmass_kernel<CG, CGGP><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(g, g.cgnx, g.cgny, g.cgs, vx, vy, lmass);
         lumpedmass_kernel<1, 2><<<blocksFor(size_t(nx + 1) * (ny + 1)), 128, 0, stream>>>(g, nx + 1, ny + 1, cg1s, vx, vy, mass1);
@@ -1356,6 +1356,28 @@ public:
         healing_kernel<<<blocksFor(g.N), 128, 0, stream>>>(g, dt, td, dci, cice, damage);
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
+    bool streamedOpsBuilt = false;
+    //! allocate and fill the reference's per-element momentum matrices (generic kernel; nsdg_get_internal of an operator)
+    void ensureStreamedOps()
+    {
+        if (streamedOpsBuilt)
+            return;
+        const bool spherical = g.spherical != 0;
+        const size_t opN = uniform ? 1 : g.Npad;
+        const int nel = uniform ? 1 : g.N;
+        oGx.alloc(size_t(DGs) * ND * opN);
+        oGy.alloc(size_t(DGs) * ND * opN);
+        oB.alloc(size_t(DGs) * Q * opN);
+        oBd.alloc(size_t(DGA) * Q * opN);
+        oD1.alloc(size_t(ND) * DGs * opN);
+        oD2.alloc(size_t(ND) * DGs * opN);
+        oGM.alloc(spherical ? size_t(DGs) * ND * opN : 0);
+        oDM.alloc(spherical ? size_t(ND) * DGs * opN : 0);
+        mop = { oGx, oGy, oGM, oB, oBd, oD1, oD2, oDM, odX, odY, opN, uniform ? 0 : 1 };
+        setup_momentum_kernel<CG, DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, mop, nel, true);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        streamedOpsBuilt = true;
+    }
     void dims(int* nx, int* ny) override
     {
         requireMesh();
@@ -1365,6 +1387,9 @@ public:
     void getInternal(const std::string& name, double* host, size_t cap, size_t* count) override
     {
         requireMesh();
+        for (const char* opName : { "divS1", "divS2", "divM", "iMgradX", "iMgradY", "iMM", "iMJwPSI", "iMJwPSI_dam" })
+            if (name == opName)
+                ensureStreamedOps();
         Internal in;
         if (!lookup(name, in))
             throw std::runtime_error("nsdg_get_internal: unknown or unallocated array " + name);

@@ -32,7 +32,7 @@ __global__ void setup_transport_kernel(GridDims g, const double* __restrict__ vx
 
 template <int CG, int DGA>
 __global__ void setup_momentum_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
-    MomentumOpPtrs op, int nelem)
+    MomentumOpPtrs op, int nelem, bool full)
 {
     const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t_ >= size_t(nelem))
@@ -41,7 +41,7 @@ __global__ void setup_momentum_kernel(GridDims g, const double* __restrict__ vx,
     const size_t e = size_t(iy) * g.nxs + ix;
     double c[4][2];
     elementCorners(vx, vy, g.nx, ix, iy, g.spherical, c);
-    momentumOpsOfElement<CG, DGA>(c, g.spherical, op, e);
+    momentumOpsOfElement<CG, DGA>(c, g.spherical, op, e, full);
 }
 
 //! element size h = sqrt(area) (ParametricMesh.hpp:276-299), used by the BBM stress update

@@ -166,8 +166,9 @@ __host__ __device__ inline void transportOpsOfElement(const double (&c)[4][2], b
 }
 
 //! ParametricMap.cpp:209-356 for one element
+//! full = false: only the 4 x 4 sea-surface-height matrices (the factored-operator kernels need nothing else)
 template <int CG, int DGA>
-__host__ __device__ inline void momentumOpsOfElement(const double (&c)[4][2], bool sph, MomentumOpPtrs o, size_t e)
+__host__ __device__ inline void momentumOpsOfElement(const double (&c)[4][2], bool sph, MomentumOpPtrs o, size_t e, bool full = true)
 {
     constexpr int DGs = cg2dgstress(CG), GS = gp1d(DGs), Q = GS * GS, ND = cgdofs(CG);
     double Fx[2][Q], Fy[2][Q], J[Q], lat[Q], cl[Q], sl[Q];
@@ -197,10 +198,12 @@ __host__ __device__ inline void momentumOpsOfElement(const double (&c)[4][2], bo
             d1[i][j] = sph ? a / EarthRadius : a;
             d2[i][j] = sph ? b / EarthRadius : b;
             dm[i][j] = sph ? m / EarthRadius : 0.0;
-            o.D1[(i * DGs + j) * o.pitch + eo] = d1[i][j];
-            o.D2[(i * DGs + j) * o.pitch + eo] = d2[i][j];
-            if (sph)
-                o.DM[(i * DGs + j) * o.pitch + eo] = dm[i][j];
+            if (full) {
+                o.D1[(i * DGs + j) * o.pitch + eo] = d1[i][j];
+                o.D2[(i * DGs + j) * o.pitch + eo] = d2[i][j];
+                if (sph)
+                    o.DM[(i * DGs + j) * o.pitch + eo] = dm[i][j];
+            }
         }
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) {
@@ -214,6 +217,8 @@ __host__ __device__ inline void momentumOpsOfElement(const double (&c)[4][2], bo
             o.dXssh[(i * 4 + j) * o.pitch + eo] = sph ? a / EarthRadius : a;
             o.dYssh[(i * 4 + j) * o.pitch + eo] = sph ? b / EarthRadius : b;
         }
+    if (!full)
+        return;
     double M[DGs][DGs], iM[DGs][DGs];
     massMatrix<DGs>(c, sph, M);
     inverse<DGs>(M, iM);
