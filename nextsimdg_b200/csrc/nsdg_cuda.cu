@@ -794,10 +794,12 @@ public:
         const size_t pX = alignUp(size_t(g.nx) * (g.ny + 1), 32), pY = alignUp(size_t(g.nx + 1) * g.ny, 32);
         const size_t n = size_t(DG) * g.Npad;
         const unsigned nb = blocksFor(g.N);
-        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t1);
+        // parametric fast paths: the cell-term operators come from the geometry planes (DG6 and DG8 share the 3 x 3 Gauss points)
+        const double* gp = (fastParamMEVP || fastParamBBM) && !std::getenv("NSDG_NO_FACTORED_TRANSPORT") ? geo.p : nullptr;
+        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, gp, phi, t1);
         add_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t1);
         exchangePlanes(phi, DG); // ring elements of the RK stage value come from their owners
-        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, phi, t2);
+        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, gp, phi, t2);
         heun_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t2, t1);
         exchangePlanes(phi, DG);
         launches += 4;

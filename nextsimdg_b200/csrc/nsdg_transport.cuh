@@ -213,7 +213,7 @@ template <int DG>
 __global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, const uint8_t* __restrict__ landmask,
     const uint8_t* __restrict__ dirmask, const double* __restrict__ velx, const double* __restrict__ vely,
     const double* __restrict__ nvX, size_t pitchX, const double* __restrict__ nvY, size_t pitchY, TransportOpPtrs op,
-    const double* __restrict__ phi, double* __restrict__ phiup)
+    const double* __restrict__ geo, const double* __restrict__ phi, double* __restrict__ phiup)
 {
     constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
     const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -252,16 +252,47 @@ __global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, c
                 }
             }
         }
+        if (G == 3 && geo != nullptr) {
+            // AdvectionCellTermX/Y (ParametricMap.cpp:13-66) are w (PSIx dyT_1 - PSIy dxT_1) and w (PSIy dxT_0 - PSIx dyT_0):
+            // formed from the 12 element-map values of the factored-operator path (nsdg_momentum_param.cuh, planes 0..11)
+            // instead of streaming 2 x DG x 9 doubles per element
+            double m[12];
 #pragma unroll
-        for (int j = 0; j < DG; ++j) {
-            double s = 0;
+            for (int k = 0; k < 12; ++k)
+                m[k] = __ldg(geo + size_t(k) * Npad + e);
+            double aq[Q], bq[Q];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const double ax = __ldg(op.AdvX + (j * Q + q) * op.pitch + eo);
-                const double ay = __ldg(op.AdvY + (j * Q + q) * op.pitch + eo);
-                s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
+                const int qx = q % 3, qy = q / 3;
+                const double wp = (dt * gaussweight2(3, q)) * pg[q];
+                aq[q] = wp * (m[9 + qx] * vxg[q] - m[6 + qx] * vyg[q]); // yeta vx - xeta vy
+                bq[q] = wp * (m[0 + qy] * vyg[q] - m[3 + qy] * vxg[q]); // xxi vy - yxi vx
             }
-            up[j] += s;
+#pragma unroll
+            for (int j = 0; j < DG; ++j) {
+                double s = 0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double px = PSIx(G, j, q), py = PSIy(G, j, q);
+                    if (px != 0.0)
+                        s = fma(px, aq[q], s);
+                    if (py != 0.0)
+                        s = fma(py, bq[q], s);
+                }
+                up[j] += s;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < DG; ++j) {
+                double s = 0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double ax = __ldg(op.AdvX + (j * Q + q) * op.pitch + eo);
+                    const double ay = __ldg(op.AdvY + (j * Q + q) * op.pitch + eo);
+                    s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
+                }
+                up[j] += s;
+            }
         }
     }
     // ---- interior edges (DGTransport.cpp:390-433) ----
