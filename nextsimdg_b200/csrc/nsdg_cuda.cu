@@ -69,6 +69,8 @@ public:
     bool uniform = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr; //!< update(): forcing uploads / early downloads beside the compute stream
+    cudaStream_t haloStream = nullptr; //!< partitioned boxes: frame strips + halo exchange beside the interior strips
+    cudaEvent_t evLines2 = nullptr, evFrame = nullptr, evHalo = nullptr;
     cudaEvent_t evForcing = nullptr, evCopyDone = nullptr;
     bool forcingPending = false;
     cudaEvent_t ev[5] {};
@@ -146,7 +148,9 @@ public:
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
-        for (cudaEvent_t e : { evForcing, evCopyDone })
+        if (haloStream)
+            cudaStreamDestroy(haloStream);
+        for (cudaEvent_t e : { evForcing, evCopyDone, evLines2, evFrame, evHalo })
             if (e)
                 cudaEventDestroy(e);
         if (copyStream)
@@ -1044,6 +1048,62 @@ public:
                 exchangeNodes(u, v); // no-op for a single domain
             }
         };
+        /*
+         * Partitioned box, fast kernels: the halo exchange is hidden behind the interior strips.  Stream H runs the FRAME
+         * (the band of strips, two thick, along the neighbour sides -- every node line that travels is computed there),
+         * the deferred lines that lie inside it, and the exchange; the compute stream runs the interior strips, then the
+         * remaining deferred lines once the frame's line-buffer contributions exist.  Per subcycle H waits for the
+         * previous subcycle's second lines pass, the compute stream for the frame; nothing else is shared: interior strips
+         * read neither ring nodes nor frame-complete line nodes, and the second lines pass writes none of the travelling lines.
+         *
+         * MEASURED (2 GPUs, 2048^2 per GPU): 70.9 ms per 100 subcycles against 67.5 ms for the plain sequence -- the
+         * exchange it hides costs 27 us per subcycle, the two extra launches, the split lines pass and the frame kernel's
+         * poor occupancy cost ~60 us.  It is therefore OFF unless NSDG_HALO_OVERLAP=1 (profiles/r1_weak_scaling.txt).
+         */
+        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && std::getenv("NSDG_HALO_OVERLAP");
+        if (overlap) {
+            if (!haloStream) {
+                NSDG_CUDA_CHECK(cudaStreamCreateWithFlags(&haloStream, cudaStreamNonBlocking));
+                for (cudaEvent_t* e : { &evLines2, &evFrame, &evHalo })
+                    NSDG_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+            }
+            StripSubset fr { 1, hasNeighbour(NSDG_LEFT) ? 2 : 0, hasNeighbour(NSDG_RIGHT) ? 2 : 0, hasNeighbour(NSDG_BOTTOM) ? 2 : 0,
+                hasNeighbour(NSDG_TOP) ? 2 : 0 };
+            UniformArgs uaF = ua, uaI = ua;
+            UniformBBMArgs baF = ba, baI = ba;
+            uaF.sub = baF.sub = fr;
+            fr.subset = 2;
+            uaI.sub = baI.sub = fr;
+            auto pair = [&](const UniformArgs& x, const UniformBBMArgs& y, bool strips, bool lines) {
+                if (fastMEVP()) {
+                    if (strips)
+                        launchStripFast(x, nbStripF);
+                    if (lines)
+                        launchLinesFast(x, nLineF);
+                } else
+                    launchPairFastBBM(y, nbStripF, nLineF, !lines, !strips);
+            };
+            NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
+            for (int i = 0; i < n; ++i) {
+                // ---- stream H: frame strips, frame lines, exchange ----
+                NSDG_CUDA_CHECK(cudaStreamWaitEvent(haloStream, evLines2, 0));
+                std::swap(stream, haloStream);
+                pair(uaF, baF, true, true);
+                NSDG_CUDA_CHECK(cudaEventRecord(evFrame, stream));
+                exchangeNodes(u, v);
+                NSDG_CUDA_CHECK(cudaEventRecord(evHalo, stream));
+                std::swap(stream, haloStream);
+                // ---- compute stream: interior strips, then the remaining deferred lines ----
+                pair(uaI, baI, true, false);
+                NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evFrame, 0));
+                pair(uaI, baI, false, true);
+                NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
+            }
+            NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evHalo, 0));
+            NSDG_CUDA_CHECK(cudaGetLastError());
+            launches += 4L * n;
+            return;
+        }
         // the exchange epochs are kernel arguments, so a partitioned box replays plain launches
         if (cfg.use_cuda_graph && n > 1 && !haloActive) {
             if (!graphExec || graphN != n || graphDeltaT != deltaT) {

@@ -77,10 +77,27 @@ inline constexpr UnitOps kUnitOps {};
 //! pull the line holding `p` into L2 (no register, no scoreboard): used one element row ahead
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+/*
+ * Strip subsets for overlapping the halo exchange with interior work (partitioned boxes).  The FRAME is the band of
+ * strips, fr* strips thick, along the sides that have a neighbour box; every node line that travels in the halo
+ * exchange is computed by frame strips alone.  subset 0: all strips; 1: frame strips only; 2: interior strips only.
+ * For the lines kernels subset 1 selects the deferred-line nodes all of whose strips are frame strips, 2 the others.
+ */
+struct StripSubset {
+    int subset, frL, frR, frB, frT;
+};
+__device__ __forceinline__ bool inFrame(const StripSubset& f, int nsx, int nsy, int sx, int sy)
+{
+    return sx < f.frL || sx >= nsx - f.frR || sy < f.frB || sy >= nsy - f.frT;
+}
+//! true if this strip (or line node, given the conjunction over its strips) is not part of the launched subset
+__device__ __forceinline__ bool skipSubset(const StripSubset& f, bool frame) { return f.subset != 0 && ((f.subset == 1) != frame); }
+
 //! arguments of the uniform mEVP kernels
 struct UniformArgs {
     GridDims g;
     int R, nsx, nsy;
+    StripSubset sub;
     double *s11, *s12, *s22; //!< DG8 planes
     const double* Pa; //!< Gauss-point planes of P/alpha, P = P* h exp(-20(1-a))
     const uint8_t* landmask;
@@ -270,6 +287,8 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     UmevpStage& st = reinterpret_cast<UmevpStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
+    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
+        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
@@ -614,6 +633,17 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
         r = min(CG * a.R * L, CG * g.ny);
         const int jx = c % CG, exr = c / CG;
         const bool above = r < CG * g.ny;
+        if (a.sub.subset) { // frame-complete: every strip that contributes to the node is a frame strip
+            bool fr = true;
+            for (int side = 0; side < (above ? 2 : 1); ++side) {
+                if (jx == 0 && exr > 0)
+                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, (exr - 1) / 32, L - 1 + side);
+                if (exr < g.nx)
+                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, exr / 32, L - 1 + side);
+            }
+            if (skipSubset(a.sub, fr))
+                return;
+        }
         auto add = [&](int side, int ex, int j) {
             const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
             sumX += hb[0];
@@ -637,6 +667,12 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
             return;
         const int jy = r % CG, eyr = r / CG;
         const bool right = c < CG * g.nx;
+        if (a.sub.subset) {
+            const int sy = min(eyr, g.ny - 1) / a.R; // the node lies strictly inside one strip row
+            const bool fr = inFrame(a.sub, a.nsx, a.nsy, L - 1, sy) && (!right || inFrame(a.sub, a.nsx, a.nsy, L, sy));
+            if (skipSubset(a.sub, fr))
+                return;
+        }
         auto add = [&](int side, int ey, int j) {
             const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
             sumX += vb[0];

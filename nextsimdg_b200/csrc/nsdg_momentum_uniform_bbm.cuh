@@ -22,6 +22,7 @@ namespace nsdg {
 struct UniformBBMArgs {
     GridDims g;
     int R, nsx, nsy;
+    StripSubset sub;
     double *s11, *s12, *s22; //!< DG8 planes
     double* damage; //!< DG6 planes
     const double *gH, *gE, *gP; //!< Gauss-point planes: h, expC, Pmax
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const 
     UbbmStage& st = reinterpret_cast<UbbmStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
+    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
+        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
@@ -559,6 +562,17 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
         r = min(CG * a.R * L, CG * g.ny);
         const int jx = c % CG, exr = c / CG;
         const bool above = r < CG * g.ny;
+        if (a.sub.subset) { // frame-complete: every strip that contributes to the node is a frame strip
+            bool fr = true;
+            for (int side = 0; side < (above ? 2 : 1); ++side) {
+                if (jx == 0 && exr > 0)
+                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, (exr - 1) / 32, L - 1 + side);
+                if (exr < g.nx)
+                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, exr / 32, L - 1 + side);
+            }
+            if (skipSubset(a.sub, fr))
+                return;
+        }
         auto add = [&](int side, int ex, int j) {
             const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
             sumX += hb[0];
@@ -582,6 +596,12 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
             return;
         const int jy = r % CG, eyr = r / CG;
         const bool right = c < CG * g.nx;
+        if (a.sub.subset) {
+            const int sy = min(eyr, g.ny - 1) / a.R; // the node lies strictly inside one strip row
+            const bool fr = inFrame(a.sub, a.nsx, a.nsy, L - 1, sy) && (!right || inFrame(a.sub, a.nsx, a.nsy, L, sy));
+            if (skipSubset(a.sub, fr))
+                return;
+        }
         auto add = [&](int side, int ey, int j) {
             const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
             sumX += vb[0];
