@@ -979,8 +979,10 @@ public:
                     subcycle_strip_pbbm<true><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<true>(), stream>>>(ba);
                 else
                     subcycle_strip_pbbm<false><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<false>(), stream>>>(ba);
-            } else if (!linesOnly)
-                subcycle_strip_ubbm<0><<<nbStrip, 32 * kUbbmWarps, kUbbmSmemBytes, stream>>>(ba);
+            } else if (!linesOnly) {
+                const unsigned nb = (unsigned(nsx) * nsy + kUbbmWarps - 1) / kUbbmWarps;
+                subcycle_strip_ubbm<0><<<nb, 32 * kUbbmWarps, kUbbmSmemBytes, stream>>>(ba);
+            }
             if (!stripOnly)
                 subcycle_lines_ubbm<<<blocksFor(nLine), 128, 0, stream>>>(ba);
         }

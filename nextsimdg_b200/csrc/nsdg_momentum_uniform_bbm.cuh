@@ -130,7 +130,11 @@ struct UbbmStage {
     double UVr[2][2];
     double pad[2];
 };
-constexpr int kUbbmWarps = 4;
+#ifndef NSDG_UBBM_WARPS
+#define NSDG_UBBM_WARPS 4
+#define NSDG_UBBM_MINB 2
+#endif
+constexpr int kUbbmWarps = NSDG_UBBM_WARPS;
 #ifndef NSDG_COOP_UBBM
 #define NSDG_COOP_UBBM 0
 #endif
@@ -138,7 +142,7 @@ constexpr bool kCoopUbbm = NSDG_COOP_UBBM != 0; //!< plane rows staged cooperati
 constexpr size_t kUbbmSmemBytes = sizeof(UbbmStage) * kUbbmWarps;
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(32 * kUbbmWarps, 2) subcycle_strip_ubbm(const __grid_constant__ UniformBBMArgs a)
+__global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_strip_ubbm(const __grid_constant__ UniformBBMArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
