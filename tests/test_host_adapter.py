@@ -18,6 +18,27 @@ def test_cpp_modules_compile_against_mock_headers():
     assert r.returncode == 0, r.stderr
 
 
+def test_cpp_modules_compile_against_the_reference_headers(tmp_path):
+    """The same translation unit against the REAL nextsimdg headers (IDynamics, ModelComponent, ModelArray, Configured,
+    IDamageHealing ... under /root/reference), with the two absent third-party header sets replaced by the test shims
+    oracle/mini_eigen (Eigen) and oracle/mini_boost (the boost::program_options declarations Configured.hpp mentions).
+    Type-checks every override, ModelArrayRef access and ModelState use of the adapter against upstream."""
+    ref = os.environ.get("NSDG_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "core", "src", "modules", "include")):
+        pytest.skip("reference tree not present")
+    inc = tmp_path / "include"
+    inc.mkdir()
+    (inc / "CUDADynamics.hpp").write_text(open(os.path.join(HOST, "CUDADynamics.hpp")).read())
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unknown-pragmas", "-DDGCOMP=6", "-DCGDEGREE=2", "-DDGSTRESSCOMP=8",
+           "-I", os.path.join(ROOT, "oracle", "mini_eigen"), "-I", os.path.join(ROOT, "oracle", "mini_boost"),
+           "-I", os.path.join(ROOT, "include"), "-I", str(tmp_path),
+           "-I", os.path.join(ref, "core", "src"), "-I", os.path.join(ref, "core", "src", "modules"),
+           "-I", os.path.join(ref, "physics", "src", "modules"), "-I", os.path.join(ref, "core", "src", "discontinuousgalerkin"),
+           "-I", os.path.join(ref, "dynamics", "src"), os.path.join(HOST, "CUDADynamics.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("rheo", ["mevp", "bbm"])
 def test_cpp_module_reproduces_python_mirror(rheo, cuda_lib, tmp_path):
