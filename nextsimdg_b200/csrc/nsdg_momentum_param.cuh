@@ -272,7 +272,8 @@ __device__ __forceinline__ void gaussDivergence(const GEO& geo, const double (&s
             constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
             constexpr double wq = gaussweight2(3, q);
             const double xeta = geo(6 + qx), yeta = geo(9 + qx);
-            double ax, bx, ay, by, mx = 0.0, my = 0.0;
+            double ax, bx, ay, by;
+            [[maybe_unused]] double mx = 0.0, my = 0.0;
             if constexpr (!SPH) {
                 ax = wq * (yeta * s11[q] - xeta * s12[q]), bx = wq * (xxi * s12[q] - yxi * s11[q]);
                 ay = wq * (yeta * s12[q] - xeta * s22[q]), by = wq * (xxi * s22[q] - yxi * s12[q]);

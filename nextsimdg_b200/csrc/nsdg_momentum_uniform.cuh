@@ -12,7 +12,7 @@
  *    stressUpdateHighOrder equals evaluating the velocity gradient directly in the 9 Gauss points
  *    (two 1-d contractions); the 3 x 8 strain coefficients are never formed;
  *  - everything in updateMomentum that does not change during the subcycles is folded into
- *    seven per-node constants once per timestep (nodeconst_kernel), which removes 4 of 13 node
+ *    six per-node constants once per timestep (nodeconst_kernel), which removes 5 of 13 node
  *    reads and 3 of 4 divisions per node and subcycle.
  *
  * Same sweeps and same results up to rounding (re-association only; tests/test_gpu_parity.py):
