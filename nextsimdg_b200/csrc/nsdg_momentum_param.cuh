@@ -387,11 +387,25 @@ __device__ __forceinline__ bool stripScatter(const GridDims& g, const StripPos& 
 // =====================================================================================================================
 // mEVP
 // =====================================================================================================================
+#ifndef NSDG_PMEVP_DIRECT_ND
+#define NSDG_PMEVP_DIRECT_ND 0 //!< see NSDG_UMEVP_DIRECT_ND
+#endif
+#ifndef NSDG_PBBM_DIRECT_ND
+#define NSDG_PBBM_DIRECT_ND 1 //!< Cartesian BBM kernel only: 4 instead of 3 blocks per SM fit (1.70 -> 1.39 ms at 2048^2); spherical loses
+#endif
+//! node-constant staging rows of a stage struct, absent when the constants are loaded directly
+template <bool DIRECT> struct NodeStage {
+    double2 ND[2][kNodeConsts][32];
+};
+template <> struct NodeStage<true> { };
+template <bool SPH> constexpr bool kPbbmDirectND = !SPH && (NSDG_PBBM_DIRECT_ND != 0);
 template <bool SPH> struct PmevpStage {
     double P[9][32];
     double S[24][32];
     double GEO[geoPlanes(SPH)][32];
+#if !NSDG_PMEVP_DIRECT_ND
     double2 ND[2][kNodeConsts][32];
+#endif
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -477,12 +491,17 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
+#if NSDG_PMEVP_DIRECT_ND
+                for (const double* p : { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm })
+                    prefetchL2(p + n);
+#else
                 cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
                 cpAsync16cg(&st.ND[k][1][lane], a.rx + n);
                 cpAsync16cg(&st.ND[k][2][lane], a.ry + n);
                 cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
                 cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
                 cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
+#endif
             }
         }
         cpAsyncCommit();
@@ -510,21 +529,21 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
         ul[2] = ru;
         vl[2] = rv;
     }
-    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
-    uchar2 nmNext[2];
+    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
+    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         const bool ice = active && (lmNext != 0);
-        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        const unsigned nm[2] = { nmNext[0], nmNext[1] };
         if (ey + 1 < ey1) {
-            lmNext = __ldg(a.landmask + e + g.nxs);
+            lmNext = ldMask1(a.landmask + e + g.nxs);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
         }
         // ---- the two upper node rows of u, v ----
         cpAsyncWait<4>();
@@ -606,9 +625,14 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+#if NSDG_PMEVP_DIRECT_ND
+            auto ld2 = [&](const double* p) { return __ldg(reinterpret_cast<const double2*>(p + n0)); };
+            const double2 cA = ld2(a.cA), rx = ld2(a.rx), ry = ld2(a.ry), uO = ld2(a.uO), vO = ld2(a.vO), ilm = ld2(a.ilm);
+#else
             const double2 cA = st.ND[jy][0][lane], rx = st.ND[jy][1][lane], ry = st.ND[jy][2][lane];
             const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
-            const uchar2 msk = nm[jy];
+#endif
+            const unsigned msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];
@@ -616,7 +640,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
                 sx1 += carryX[1];
                 sy1 += carryY[1];
             }
-            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            const bool d0 = msk & 1u, d1 = msk & 0x100u;
             double2 un, vn;
             momentumNodeUniform(a, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x);
@@ -690,12 +714,11 @@ __global__ void paramgeom_bbm_kernel(GridDims g, PhysParams p, const double* __r
     geo[size_t(base + 7) * g.Npad + e] = 1.0 / (hel * sqrt(2. * (1. + p.nu0) * p.rho_ice));
 }
 
-template <bool SPH> struct PbbmStage {
+template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
     double G[27][32]; //!< h, expC, Pmax in the 9 Gauss points
     double S[24][32];
     double D[6][32];
     double GEO[geoPlanesBBM(SPH)][32];
-    double2 ND[2][kNodeConsts][32];
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -777,12 +800,17 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
-                cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
-                cpAsync16cg(&st.ND[k][1][lane], a.ax + n);
-                cpAsync16cg(&st.ND[k][2][lane], a.ay + n);
-                cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
-                cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
-                cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
+                if constexpr (kPbbmDirectND<SPH>) {
+                    for (const double* p : { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm })
+                        prefetchL2(p + n);
+                } else {
+                    cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
+                    cpAsync16cg(&st.ND[k][1][lane], a.ax + n);
+                    cpAsync16cg(&st.ND[k][2][lane], a.ay + n);
+                    cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
+                    cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
+                    cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
+                }
                 prefetchL2(a.avgU + n); // read-modify-written at the end of the row
                 prefetchL2(a.avgV + n);
             }
@@ -812,21 +840,21 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
         ul[2] = ru;
         vl[2] = rv;
     }
-    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
-    uchar2 nmNext[2];
+    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
+    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         const bool ice = active && (lmNext != 0);
-        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        const unsigned nm[2] = { nmNext[0], nmNext[1] };
         if (ey + 1 < ey1) {
-            lmNext = __ldg(a.landmask + e + g.nxs);
+            lmNext = ldMask1(a.landmask + e + g.nxs);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
         }
         cpAsyncWait<4>();
 #pragma unroll
@@ -964,6 +992,21 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
         component(a.s11, e11);
         component(a.s12, e12);
         component(a.s22, e22);
+        // direct node constants and means: loads issued here, one stress-divergence evaluation ahead of the node update
+        // (pinned: the compiler would sink them to their first use, and cannot move them across the cp.async statements)
+        double2 ndc[2][kNodeConsts], avg0[2][2];
+        if constexpr (kPbbmDirectND<SPH>) {
+#pragma unroll
+            for (int jy = 0; jy < CG; ++jy) {
+                const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+                const double* src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
+#pragma unroll
+                for (int i = 0; i < kNodeConsts; ++i)
+                    ndc[jy][i] = ldPinned2(src[i] + n0);
+                avg0[jy][0] = ldPinned2(a.avgU + n0);
+                avg0[jy][1] = ldPinned2(a.avgV + n0);
+            }
+        }
         issueS(ey + 1);
 
         double Tx[9], Ty[9];
@@ -982,9 +1025,14 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
-            const double2 cA = st.ND[jy][0][lane], ax = st.ND[jy][1][lane], ay = st.ND[jy][2][lane];
-            const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
-            const uchar2 msk = nm[jy];
+            double2 cA, ax, ay, uO, vO, ilm;
+            if constexpr (kPbbmDirectND<SPH>) {
+                cA = ndc[jy][0], ax = ndc[jy][1], ay = ndc[jy][2], uO = ndc[jy][3], vO = ndc[jy][4], ilm = ndc[jy][5];
+            } else {
+                cA = st.ND[jy][0][lane], ax = st.ND[jy][1][lane], ay = st.ND[jy][2][lane];
+                uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
+            }
+            const unsigned msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];
@@ -992,7 +1040,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 sx1 += carryX[1];
                 sy1 += carryY[1];
             }
-            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            const bool d0 = msk & 1u, d1 = msk & 0x100u;
             double2 un, vn, ua, va;
             momentumNodeUniformBBM(a, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
@@ -1004,7 +1052,11 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 if (!skip0) {
                     *reinterpret_cast<double2*>(a.u + n0) = un;
                     *reinterpret_cast<double2*>(a.v + n0) = vn;
-                    double2 au = *reinterpret_cast<const double2*>(a.avgU + n0), av = *reinterpret_cast<const double2*>(a.avgV + n0);
+                    double2 au, av;
+                    if constexpr (kPbbmDirectND<SPH>)
+                        au = avg0[jy][0], av = avg0[jy][1];
+                    else
+                        au = *reinterpret_cast<const double2*>(a.avgU + n0), av = *reinterpret_cast<const double2*>(a.avgV + n0);
                     au.x += ua.x;
                     au.y += ua.y;
                     av.x += va.x;
@@ -1014,8 +1066,13 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 } else {
                     a.u[n0 + 1] = un.y;
                     a.v[n0 + 1] = vn.y;
-                    a.avgU[n0 + 1] += ua.y;
-                    a.avgV[n0 + 1] += va.y;
+                    if constexpr (kPbbmDirectND<SPH>) {
+                        a.avgU[n0 + 1] = avg0[jy][0].y + ua.y;
+                        a.avgV[n0 + 1] = avg0[jy][1].y + va.y;
+                    } else {
+                        a.avgU[n0 + 1] += ua.y;
+                        a.avgV[n0 + 1] += va.y;
+                    }
                 }
             }
         }

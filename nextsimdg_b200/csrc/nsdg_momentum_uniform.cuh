@@ -74,6 +74,33 @@ struct UnitOps {
 };
 inline constexpr UnitOps kUnitOps {};
 
+/*
+ * Mask bytes travel one element row ahead in registers.  A typed byte / uchar2 load is unpacked right behind the load
+ * (PRMT), which makes every warp wait out the global latency at the top of each row (7 % of all stall samples of the
+ * BBM strip kernel, profiles/r1_strip_bbm_d2_ldslaw.txt); a load into a plain 32-bit register has no consumer until the
+ * word is decoded a row later.
+ */
+__device__ __forceinline__ unsigned ldMask1(const uint8_t* p)
+{
+    unsigned v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ldMask2(const uint8_t* p) //!< bytes p[0] | p[1] << 8 (p 2-byte aligned)
+{
+    unsigned v;
+    asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+//! 16-byte global load that stays where it is written (a plain or __ldg load is sunk to its first use by the compiler)
+__device__ __forceinline__ double2 ldPinned2(const double* p)
+{
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
 //! pull the line holding `p` into L2 (no register, no scoreboard): used one element row ahead
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -257,10 +284,21 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("c
  * Four groups are always in flight; cp.async groups retire in order, so "wait_group 3" before each
  * region's first read is exactly "the group issued one row ago has landed".
  */
+/*
+ * NSDG_*_DIRECT_ND = 1: the per-node constants are not staged but loaded where the node update uses them (their lines
+ * are pulled into L2 one row ahead).  6-8 KB less shared memory per warp moves the SM's carve-out one step towards L1,
+ * which is what bounds the bytes in flight of the per-lane 8-byte cp.async.ca copies (they allocate L1 lines while they
+ * wait): BBM strip kernel 1.16 -> 1.06 ms at 2048^2.  Kernels whose planes travel by cp.async.cg do not gain.
+ */
+#ifndef NSDG_UMEVP_DIRECT_ND
+#define NSDG_UMEVP_DIRECT_ND 0
+#endif
 struct UmevpStage {
     double P[9][32];
     double S[24][32];
+#if !NSDG_UMEVP_DIRECT_ND
     double2 ND[2][kNodeConsts][32];
+#endif
     double2 UV[2][2][32];
     double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
     double pad[2];
@@ -336,12 +374,17 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
+#if NSDG_UMEVP_DIRECT_ND
+                for (const double* p : { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm })
+                    prefetchL2(p + n);
+#else
                 cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
                 cpAsync16cg(&st.ND[k][1][lane], a.rx + n);
                 cpAsync16cg(&st.ND[k][2][lane], a.ry + n);
                 cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
                 cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
                 cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
+#endif
             }
         }
         cpAsyncCommit();
@@ -372,21 +415,21 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 
     // mask bytes travel one element row ahead in registers (their use right after the load cost 18 % of the
     // stall samples, profiles/r1_strip_v3_cpasync.txt)
-    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
-    uchar2 nmNext[2];
+    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
+    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         const bool ice = active && (lmNext != 0);
-        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        const unsigned nm[2] = { nmNext[0], nmNext[1] };
         if (ey + 1 < ey1) {
-            lmNext = __ldg(a.landmask + e + g.nxs);
+            lmNext = ldMask1(a.landmask + e + g.nxs);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
         }
         // ---- the two upper node rows of u, v from the staging buffer ----
         cpAsyncWait<3>();
@@ -573,9 +616,14 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+#if NSDG_UMEVP_DIRECT_ND
+            auto ld2 = [&](const double* p) { return __ldg(reinterpret_cast<const double2*>(p + n0)); };
+            const double2 cA = ld2(a.cA), rx = ld2(a.rx), ry = ld2(a.ry), uO = ld2(a.uO), vO = ld2(a.vO), ilm = ld2(a.ilm);
+#else
             const double2 cA = st.ND[jy][0][lane], rx = st.ND[jy][1][lane], ry = st.ND[jy][2][lane];
             const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
-            const uchar2 msk = nm[jy];
+#endif
+            const unsigned msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];
@@ -583,7 +631,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
                 sx1 += carryX[1];
                 sy1 += carryY[1];
             }
-            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            const bool d0 = msk & 1u, d1 = msk & 0x100u;
             double2 un, vn;
             momentumNodeUniform(a, cA.x, rx.x, ry.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x);

@@ -121,11 +121,17 @@ __device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, 
     }
 }
 
+#ifndef NSDG_UBBM_DIRECT_ND
+#define NSDG_UBBM_DIRECT_ND 1 //!< node constants and means loaded where they are used (see NSDG_UMEVP_DIRECT_ND): 1.16 -> 1.06 ms
+#endif
 struct UbbmStage {
     double G[27][32]; //!< h, expC, Pmax in the 9 Gauss points
     double S[24][32];
     double D[6][32];
+#if !NSDG_UBBM_DIRECT_ND
     double2 ND[2][kNodeConsts][32];
+    double2 AVG[2][2][32]; //!< avgU, avgV of the row's two node lines (read-modify-written by the node update)
+#endif
     double2 UV[2][2][32];
     double UVr[2][2];
     double pad[2];
@@ -139,6 +145,13 @@ constexpr int kUbbmWarps = NSDG_UBBM_WARPS;
 #define NSDG_COOP_UBBM 0
 #endif
 constexpr bool kCoopUbbm = NSDG_COOP_UBBM != 0; //!< plane rows staged cooperatively (cp.async.cg) or per lane
+#ifndef NSDG_UBBM_ND_HOIST
+#define NSDG_UBBM_ND_HOIST 2 //!< (measured best of 0..3: 1.075 -> 1.010 ms) how many stress projections ahead of the node update the direct node loads are issued (0..3)
+#endif
+#ifndef NSDG_COOP_UBBM_G
+#define NSDG_COOP_UBBM_G 0
+#endif
+constexpr bool kCoopUbbmG = kCoopUbbm || NSDG_COOP_UBBM_G != 0; //!< the read-only Gauss-point planes alone
 constexpr size_t kUbbmSmemBytes = sizeof(UbbmStage) * kUbbmWarps;
 
 template <int DUMMY = 0>
@@ -182,12 +195,12 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         cpAsyncCommit();
     };
     auto issueG = [&](int row) {
-        stageBarrier<kCoopUbbm>();
+        stageBarrier<kCoopUbbmG>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
-            stagePlanes<9, kCoopUbbm>(st.G, a.gH, Npad, first, lane);
-            stagePlanes<9, kCoopUbbm>(st.G + 9, a.gE, Npad, first, lane);
-            stagePlanes<9, kCoopUbbm>(st.G + 18, a.gP, Npad, first, lane);
+            stagePlanes<9, kCoopUbbmG>(st.G, a.gH, Npad, first, lane);
+            stagePlanes<9, kCoopUbbmG>(st.G + 9, a.gE, Npad, first, lane);
+            stagePlanes<9, kCoopUbbmG>(st.G + 18, a.gP, Npad, first, lane);
         }
         cpAsyncCommit();
     };
@@ -207,14 +220,26 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + k) * g.cgs + col0;
+#if NSDG_UBBM_DIRECT_ND
+                prefetchL2(a.cA + n);
+                prefetchL2(a.ax + n);
+                prefetchL2(a.ay + n);
+                prefetchL2(a.uO + n);
+                prefetchL2(a.vO + n);
+                prefetchL2(a.ilm + n);
+                prefetchL2(a.avgU + n);
+                prefetchL2(a.avgV + n);
+                continue;
+#else
                 cpAsync16cg(&st.ND[k][0][lane], a.cA + n);
                 cpAsync16cg(&st.ND[k][1][lane], a.ax + n);
                 cpAsync16cg(&st.ND[k][2][lane], a.ay + n);
                 cpAsync16cg(&st.ND[k][3][lane], a.uO + n);
                 cpAsync16cg(&st.ND[k][4][lane], a.vO + n);
                 cpAsync16cg(&st.ND[k][5][lane], a.ilm + n);
-                prefetchL2(a.avgU + n); // read-modify-written at the end of the row
-                prefetchL2(a.avgV + n);
+                cpAsync16cg(&st.AVG[k][0][lane], a.avgU + n); // each node's mean is touched by exactly one lane and
+                cpAsync16cg(&st.AVG[k][1][lane], a.avgV + n); // iteration of this launch, so staging a row ahead is safe
+#endif
             }
         }
         cpAsyncCommit();
@@ -243,21 +268,21 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
     }
 
     // mask bytes travel one element row ahead in registers
-    uint8_t lmNext = __ldg(a.landmask + size_t(ey0) * g.nxs + ex);
-    uchar2 nmNext[2];
+    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
+    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0));
+        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         const bool ice = active && (lmNext != 0);
-        const uchar2 nm[2] = { nmNext[0], nmNext[1] };
+        const unsigned nm[2] = { nmNext[0], nmNext[1] };
         if (ey + 1 < ey1) {
-            lmNext = __ldg(a.landmask + e + g.nxs);
+            lmNext = ldMask1(a.landmask + e + g.nxs);
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-                nmNext[k] = __ldg(reinterpret_cast<const uchar2*>(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0));
+                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
         }
         cpAsyncWait<3>();
 #pragma unroll
@@ -343,7 +368,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
             for (int j = 0; j < DGA; ++j)
                 dc[j] = st.D[j][lane];
             cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
-            stageBarrier<kCoopUbbm>();
+            stageBarrier<kCoopUbbmG>();
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
                 double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
@@ -443,9 +468,40 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 });
             }
         };
+#if NSDG_UBBM_DIRECT_ND
+        // node constants and means of the row's two node lines: the loads are issued NSDG_UBBM_ND_HOIST projections
+        // ahead of the node update (they cannot be moved across the cp.async statements by the compiler)
+        double2 ndc[2][kNodeConsts], avg0[2][2];
+        auto loadND = [&]() {
+#pragma unroll
+            for (int jy = 0; jy < CG; ++jy) {
+                const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+                const double* src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
+#pragma unroll
+                for (int i = 0; i < kNodeConsts; ++i)
+                    ndc[jy][i] = ldPinned2(src[i] + n0);
+                avg0[jy][0] = ldPinned2(a.avgU + n0);
+                avg0[jy][1] = ldPinned2(a.avgV + n0);
+            }
+        };
+        if constexpr (NSDG_UBBM_ND_HOIST == 3)
+            loadND();
+#endif
         component(a.s11, e11, std::integral_constant<int, 0> {});
+#if NSDG_UBBM_DIRECT_ND
+        if constexpr (NSDG_UBBM_ND_HOIST == 2)
+            loadND();
+#endif
         component(a.s12, e12, std::integral_constant<int, 1> {});
+#if NSDG_UBBM_DIRECT_ND
+        if constexpr (NSDG_UBBM_ND_HOIST == 1)
+            loadND();
+#endif
         component(a.s22, e22, std::integral_constant<int, 2> {});
+#if NSDG_UBBM_DIRECT_ND
+        if constexpr (NSDG_UBBM_ND_HOIST == 0)
+            loadND();
+#endif
         issueS(ey + 1);
         issueG(ey + 1);
 
@@ -497,9 +553,15 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
+#if NSDG_UBBM_DIRECT_ND
+            const double2 cA = ndc[jy][0], ax = ndc[jy][1], ay = ndc[jy][2], uO = ndc[jy][3], vO = ndc[jy][4], ilm = ndc[jy][5];
+            const double2 avgU0 = avg0[jy][0], avgV0 = avg0[jy][1];
+#else
             const double2 cA = st.ND[jy][0][lane], ax = st.ND[jy][1][lane], ay = st.ND[jy][2][lane];
             const double2 uO = st.ND[jy][3][lane], vO = st.ND[jy][4][lane], ilm = st.ND[jy][5][lane];
-            const uchar2 msk = nm[jy];
+            const double2 avgU0 = st.AVG[jy][0][lane], avgV0 = st.AVG[jy][1][lane];
+#endif
+            const unsigned msk = nm[jy];
             double sx0 = Tx[jy * NR], sy0 = Ty[jy * NR], sx1 = Tx[jy * NR + 1], sy1 = Ty[jy * NR + 1];
             if (jy == 0) {
                 sx0 += carryX[0];
@@ -507,7 +569,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 sx1 += carryX[1];
                 sy1 += carryY[1];
             }
-            const bool d0 = msk.x & 1, d1 = msk.y & 1;
+            const bool d0 = msk & 1u, d1 = msk & 0x100u;
             double2 un, vn, ua, va;
             momentumNodeUniformBBM(a, cA.x, ax.x, ay.x, uO.x, vO.x, ilm.x, d0, ul[jy * NR], vl[jy * NR], d0 ? 0.0 : -sx0,
                 d0 ? 0.0 : -sy0, un.x, vn.x, ua.x, va.x);
@@ -519,7 +581,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 if (!skip0) {
                     *reinterpret_cast<double2*>(a.u + n0) = un;
                     *reinterpret_cast<double2*>(a.v + n0) = vn;
-                    double2 au = *reinterpret_cast<const double2*>(a.avgU + n0), av = *reinterpret_cast<const double2*>(a.avgV + n0);
+                    double2 au = avgU0, av = avgV0;
                     au.x += ua.x;
                     au.y += ua.y;
                     av.x += va.x;
@@ -529,8 +591,8 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 } else {
                     a.u[n0 + 1] = un.y;
                     a.v[n0 + 1] = vn.y;
-                    a.avgU[n0 + 1] += ua.y;
-                    a.avgV[n0 + 1] += va.y;
+                    a.avgU[n0 + 1] = avgU0.y + ua.y;
+                    a.avgV[n0 + 1] = avgV0.y + va.y;
                 }
             }
         }
