@@ -279,6 +279,7 @@ public:
         d_dirmask.alloc(Npad);
         NSDG_CUDA_CHECK(cudaMemcpy2D(d_landmask, g.nxs, landmask.data(), nx, nx, ny, cudaMemcpyHostToDevice));
         NSDG_CUDA_CHECK(cudaMemcpy2D(d_dirmask, g.nxs, hdirmask.data(), nx, nx, ny, cudaMemcpyHostToDevice));
+        legacySync(); // a pageable H2D copy may return before the DMA has landed; `stream` does not wait for the legacy stream
         d_nodemask.alloc(ncg);
         nodemask_kernel<CG><<<blocksFor(N), 128, 0, stream>>>(g, d_dirmask, d_nodemask);
 
@@ -354,6 +355,7 @@ public:
             pull(h.D1, oD1, ND * DGs);
             pull(h.D2, oD2, ND * DGs);
             NSDG_CUDA_CHECK(cudaMemcpyToSymbol(c_mops, &h, sizeof(h)));
+            legacySync();
         }
 
         // ---- strips and deferred-line buffers ----
@@ -1527,6 +1529,7 @@ public:
             for (int r = 0; r < g.cgny; ++r)
                 std::copy(host + size_t(r) * g.cgnx, host + size_t(r + 1) * g.cgnx, tmp.begin() + size_t(r) * g.cgs);
             NSDG_CUDA_CHECK(cudaMemcpy(in.ptr, tmp.data(), ncg * 8, cudaMemcpyHostToDevice));
+            legacySync();
         } else if (in.kind == Internal::DGF) {
             if (count != N * in.comps)
                 throw std::runtime_error("nsdg_set_internal: wrong size for " + name);
@@ -1535,6 +1538,7 @@ public:
                 for (int c = 0; c < in.comps; ++c)
                     tmp[size_t(c) * g.Npad + (d / g.nx) * g.nxs + d % g.nx] = host[d * in.comps + c];
             NSDG_CUDA_CHECK(cudaMemcpy(in.ptr, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
+            legacySync();
         } else
             throw std::runtime_error("nsdg_set_internal: array is read-only: " + name);
     }

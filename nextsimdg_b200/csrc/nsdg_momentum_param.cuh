@@ -407,6 +407,7 @@ template <bool SPH> struct PmevpStage {
     double2 ND[2][kNodeConsts][32];
 #endif
     double2 UV[2][2][32];
+    MaskStage M;
     double UVr[2][2];
     double pad[2];
 };
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
     // ---- the five staging groups of element row `row`, issued in the order UV, P, S, GEO, ND ----
     auto issueUV = [&](int row) {
         if (row < ey1) {
+            stageMasks(st.M, a.landmask, a.nodemask, g, row, sx, lane);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
@@ -529,24 +531,14 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
         ul[2] = ru;
         vl[2] = rv;
     }
-    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
-    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (lmNext != 0);
-        const unsigned nm[2] = { nmNext[0], nmNext[1] };
-        if (ey + 1 < ey1) {
-            lmNext = ldMask1(a.landmask + e + g.nxs);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
-        }
         // ---- the two upper node rows of u, v ----
         cpAsyncWait<4>();
+        __syncwarp(); // the mask bytes were staged by other lanes
+        const bool ice = active && (st.M.LM[lane] != 0);
+        const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
@@ -562,6 +554,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
             ul[3 * (k + 1) + 2] = ru;
             vl[3 * (k + 1) + 2] = rv;
         }
+        __syncwarp(); // every lane has read its mask bytes
         issueUV(ey + 1);
 
         // ---- strain in the 9 Gauss points ----
@@ -720,6 +713,7 @@ template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
     double D[6][32];
     double GEO[geoPlanesBBM(SPH)][32];
     double2 UV[2][2][32];
+    MaskStage M;
     double UVr[2][2];
     double pad[2];
 };
@@ -755,6 +749,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
     // staging groups, issued in the order UV, S(+D), G, GEO, ND
     auto issueUV = [&](int row) {
         if (row < ey1) {
+            stageMasks(st.M, a.landmask, a.nodemask, g, row, sx, lane);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
@@ -840,23 +835,13 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
         ul[2] = ru;
         vl[2] = rv;
     }
-    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
-    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (lmNext != 0);
-        const unsigned nm[2] = { nmNext[0], nmNext[1] };
-        if (ey + 1 < ey1) {
-            lmNext = ldMask1(a.landmask + e + g.nxs);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
-        }
         cpAsyncWait<4>();
+        __syncwarp(); // the mask bytes were staged by other lanes
+        const bool ice = active && (st.M.LM[lane] != 0);
+        const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
@@ -872,6 +857,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
             ul[3 * (k + 1) + 2] = ru;
             vl[3 * (k + 1) + 2] = rv;
         }
+        __syncwarp(); // every lane has read its mask bytes
         issueUV(ey + 1);
 
         // ---- strain in the 9 Gauss points ----

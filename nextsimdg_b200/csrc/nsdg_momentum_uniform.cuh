@@ -75,22 +75,34 @@ struct UnitOps {
 inline constexpr UnitOps kUnitOps {};
 
 /*
- * Mask bytes travel one element row ahead in registers.  A typed byte / uchar2 load is unpacked right behind the load
- * (PRMT), which makes every warp wait out the global latency at the top of each row (7 % of all stall samples of the
- * BBM strip kernel, profiles/r1_strip_bbm_d2_ldslaw.txt); a load into a plain 32-bit register has no consumer until the
- * word is decoded a row later.
+ * Mask bytes (land mask of the element row, Dirichlet bytes of its two node lines) travel with the u, v staging group:
+ * copied global -> shared by cp.async one element row ahead and read at the top of the row.  Typed register loads a row
+ * ahead do not work: the compiler unpacks the bytes (PRMT) or evaluates `mask != 0` into a predicate right behind the
+ * load, and every warp waits out the global latency at the top of each row (7 % of the stall samples of the BBM strip
+ * kernel, 17 % of the parametric mEVP kernel).  An asynchronous copy has no register consumer.
  */
-__device__ __forceinline__ unsigned ldMask1(const uint8_t* p)
+struct MaskStage {
+    uint8_t LM[32]; //!< land mask of the strip's 32 elements
+    uint8_t NM[2][64]; //!< node bytes of node lines 2 row, 2 row + 1, columns [64 sx, 64 sx + 64)
+};
+__device__ __forceinline__ void cpAsync4(void* dst, const void* src)
 {
-    unsigned v;
-    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
 }
-__device__ __forceinline__ unsigned ldMask2(const uint8_t* p) //!< bytes p[0] | p[1] << 8 (p 2-byte aligned)
+//! lanes 0-15 / 16-31 copy the node bytes of the two node lines (4 bytes each), lanes 0-7 the land mask; rows are padded
+//! (cgs to 16, nxs to 32), so a 4-byte chunk lies inside the row or is skipped as a whole
+__device__ __forceinline__ void stageMasks(MaskStage& m, const uint8_t* landmask, const uint8_t* nodemask, const GridDims& g, int row, int sx, int lane)
 {
-    unsigned v;
-    asm("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
+    const int k = lane >> 4, j = 4 * (lane & 15), c = 64 * sx + j;
+    if (c < g.cgs)
+        cpAsync4(&m.NM[k][j], nodemask + size_t(2 * row + k) * g.cgs + c);
+    if (lane < 8 && 32 * sx + 4 * lane < g.nxs)
+        cpAsync4(&m.LM[4 * lane], landmask + size_t(row) * g.nxs + 32 * sx + 4 * lane);
+}
+//! Dirichlet bytes of the lane's two nodes of node line k: byte 0 = column 2 ex, byte 1 = column 2 ex + 1
+__device__ __forceinline__ unsigned nodeMaskWord(const MaskStage& m, int k, int lane)
+{
+    return *reinterpret_cast<const unsigned short*>(&m.NM[k][2 * lane]);
 }
 
 //! 16-byte global load that stays where it is written (a plain or __ldg load is sunk to its first use by the compiler)
@@ -300,6 +312,7 @@ struct UmevpStage {
     double2 ND[2][kNodeConsts][32];
 #endif
     double2 UV[2][2][32];
+    MaskStage M;
     double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
     double pad[2];
 };
@@ -340,6 +353,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     // ---- issue functions of the four staging groups for element row `row` (empty group past the strip) ----
     auto issueUV = [&](int row) {
         if (row < ey1) {
+            stageMasks(st.M, a.landmask, a.nodemask, g, row, sx, lane);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
@@ -415,24 +429,14 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 
     // mask bytes travel one element row ahead in registers (their use right after the load cost 18 % of the
     // stall samples, profiles/r1_strip_v3_cpasync.txt)
-    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
-    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (lmNext != 0);
-        const unsigned nm[2] = { nmNext[0], nmNext[1] };
-        if (ey + 1 < ey1) {
-            lmNext = ldMask1(a.landmask + e + g.nxs);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
-        }
         // ---- the two upper node rows of u, v from the staging buffer ----
         cpAsyncWait<3>();
+        __syncwarp(); // the mask bytes were staged by other lanes
+        const bool ice = active && (st.M.LM[lane] != 0);
+        const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
@@ -448,6 +452,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
             ul[3 * (k + 1) + 2] = ru;
             vl[3 * (k + 1) + 2] = rv;
         }
+        __syncwarp(); // every lane has read its mask bytes
         issueUV(ey + 1);
 
         // ---- velocity gradient in the 9 Gauss points by two 1-d contractions ----

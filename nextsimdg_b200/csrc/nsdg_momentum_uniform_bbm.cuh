@@ -133,6 +133,7 @@ struct UbbmStage {
     double2 AVG[2][2][32]; //!< avgU, avgV of the row's two node lines (read-modify-written by the node update)
 #endif
     double2 UV[2][2][32];
+    MaskStage M;
     double UVr[2][2];
     double pad[2];
 };
@@ -146,7 +147,7 @@ constexpr int kUbbmWarps = NSDG_UBBM_WARPS;
 #endif
 constexpr bool kCoopUbbm = NSDG_COOP_UBBM != 0; //!< plane rows staged cooperatively (cp.async.cg) or per lane
 #ifndef NSDG_UBBM_ND_HOIST
-#define NSDG_UBBM_ND_HOIST 2 //!< (measured best of 0..3: 1.075 -> 1.010 ms) how many stress projections ahead of the node update the direct node loads are issued (0..3)
+#define NSDG_UBBM_ND_HOIST 1 //!< (0: 1.075, 1: 1.018, 2: 1.010 with a spill, 3: 1.031 ms) how many stress projections ahead of the node update the direct node loads are issued (0..3)
 #endif
 #ifndef NSDG_COOP_UBBM_G
 #define NSDG_COOP_UBBM_G 0
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 
     auto issueUV = [&](int row) {
         if (row < ey1) {
+            stageMasks(st.M, a.landmask, a.nodemask, g, row, sx, lane);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const size_t n = size_t(CG * row + 1 + k) * g.cgs + col0;
@@ -267,24 +269,13 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         vl[2] = rv;
     }
 
-    // mask bytes travel one element row ahead in registers
-    unsigned lmNext = ldMask1(a.landmask + size_t(ey0) * g.nxs + ex);
-    unsigned nmNext[2]; // two node bytes per word, decoded where they are used
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        nmNext[k] = ldMask2(a.nodemask + size_t(CG * ey0 + k) * g.cgs + col0);
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        const bool ice = active && (lmNext != 0);
-        const unsigned nm[2] = { nmNext[0], nmNext[1] };
-        if (ey + 1 < ey1) {
-            lmNext = ldMask1(a.landmask + e + g.nxs);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-                nmNext[k] = ldMask2(a.nodemask + size_t(CG * (ey + 1) + k) * g.cgs + col0);
-        }
         cpAsyncWait<3>();
+        __syncwarp(); // the mask bytes were staged by other lanes
+        const bool ice = active && (st.M.LM[lane] != 0);
+        const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double2 tu = st.UV[0][k][lane], tv = st.UV[1][k][lane];
@@ -300,6 +291,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
             ul[3 * (k + 1) + 2] = ru;
             vl[3 * (k + 1) + 2] = rv;
         }
+        __syncwarp(); // every lane has read its mask bytes
         issueUV(ey + 1);
 
         // ---- velocity gradient in the 9 Gauss points (as in the mEVP kernel) ----

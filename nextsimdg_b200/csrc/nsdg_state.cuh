@@ -65,6 +65,9 @@ struct GridDims {
 };
 
 //! simple owning device buffer
+//! wait for the legacy default stream (synchronous cudaMemcpy / cudaMemset work); the handles run on non-blocking streams
+inline void legacySync() { NSDG_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy)); }
+
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -86,8 +89,13 @@ template <typename T> struct DevBuf {
         if (count == 0)
             return;
         NSDG_CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
-        if (zero)
-            NSDG_CUDA_CHECK(cudaMemset(p, 0, count * sizeof(T)));
+        if (zero) {
+            // cudaMemset of device memory is asynchronous and runs on the legacy default stream, which the handles'
+            // non-blocking streams do not wait for: without the synchronisation a kernel could read the buffer before it
+            // is zeroed (or be overwritten by the late memset) whenever cudaMalloc hands back used memory
+            NSDG_CUDA_CHECK(cudaMemsetAsync(p, 0, count * sizeof(T), cudaStreamLegacy));
+            legacySync();
+        }
     }
     operator T*() const { return p; }
 };

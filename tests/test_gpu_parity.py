@@ -275,6 +275,45 @@ def test_restart_state_resumes_bitwise(rheo):
         other.set_state(state)
 
 
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_fresh_handle_does_not_depend_on_device_heap_contents(rheo):
+    """Regression: buffers were zeroed by cudaMemset on the legacy stream, which the handle's non-blocking stream does not
+    wait for; once cudaMalloc handed back used memory, a new handle could read garbage (or lose data to the late memset)
+    and two identical runs differed.  Handles of other sizes are created and destroyed in between to dirty the heap."""
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, synthetic
+
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    nx, ny, dt = 40, 33, 900.0
+    ms = synthetic.para_state(nx, ny, distort=0.04, irregular_mask=True)
+    f = synthetic.smooth_forcing(nx, ny, seed=1)
+
+    def churn(i):
+        n = 24 + 7 * (i % 5)
+        d = (CUDABBMDynamics if i % 2 else CUDAMEVPDynamics)(nsteps=3)
+        m = synthetic.benchmark_box(n)
+        d.setData(m)
+        d.shared = {"hice": m["hice"].copy(), "cice": m["cice"].copy(), **{a: b.copy() for a, b in synthetic.benchmark_forcing(n, 0.0).items()}}
+        d.update(120.0)
+        d.close()
+
+    def run():
+        d = cls(nsteps=60)
+        d.setData(ms)
+        d.shared = {"hice": np.array(ms["hice"][..., 0], order="C", copy=True), "cice": np.array(ms["cice"][..., 0], order="C", copy=True)}
+        d.shared.update({n: v.copy() for n, v in f.items()})
+        d.update(dt)
+        out = {n: d.internal(n) for n in ("s11", "s12", "s22", "cg_u", "cg_v", "hice", "cice")}
+        d.close()
+        return out
+
+    first = run()
+    for it in range(8):
+        churn(it)
+        again = run()
+        for name, v in first.items():
+            assert np.array_equal(v, again[name]), (it, name)
+
+
 def test_constant_healing_on_device():
     """nsdg_heal_damage (N4) against the restatement of ConstantHealing::updateElement, bit-exact arithmetic."""
     from oracle.healing import constant_healing
