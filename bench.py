@@ -261,10 +261,14 @@ def run_gpu(args):
                 "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_alg,
                 "peak_source": peak_src,
                 "dram_gbs_strip": (traffic / (strip_ms.value * 1e-3) / 1e9) if traffic else None,
-                "note": "achieved uses SURVEY 8(d)'s algorithmic bytes (960 B per element-subcycle for uniform mEVP, counting 13 node "
-                        "reads); the kernels fold those into 6 per-node constants, so the measured DRAM traffic per strip launch "
-                        "(`traffic`, ncu) is lower than `algorithmic_bytes_per_launch` and frac can exceed 1; dram_gbs_strip = "
-                        "traffic / strip_ms is the real DRAM throughput of the dominant kernel"}
+                "note": ("achieved uses SURVEY 8(d)'s algorithmic bytes (960 B per element-subcycle for uniform mEVP, counting 13 node "
+                         "reads); the kernels fold those into 6 per-node constants, so the measured DRAM traffic per strip launch "
+                         "(`traffic`, ncu) is lower than `algorithmic_bytes_per_launch` and frac can exceed 1; dram_gbs_strip = "
+                         "traffic / strip_ms is the real DRAM throughput of the dominant kernel") if rheo == "mevp" else
+                        ("achieved uses SURVEY 8(d)'s algorithmic bytes (1120 B per element-subcycle for uniform BBM); the kernel "
+                         "additionally reads 27 per-step Gauss-point constants per element (h, exp(C(1-a)), Pmax) instead of "
+                         "recomputing exp/pow in every subcycle, so `traffic` (ncu, strip kernel) is slightly above "
+                         "`algorithmic_bytes_per_launch`; dram_gbs_strip = traffic / strip_ms")}
 
     # ---- end-to-end arm: host buffers in, host buffers out, every step ----
     for _ in range(min(args.warmup, 2)):
