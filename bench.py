@@ -39,6 +39,9 @@ DT = 120.0  # run/config_benchmark.cfg:5
 NSTEPS = 100  # DynamicsKernel.hpp:187
 # algorithmic bytes per element-subcycle, SURVEY.md 8(d) / BASELINE.md 3
 B_ALG = {("mevp", True): 960, ("mevp", False): 3840, ("bbm", True): 1120, ("bbm", False): 4432}
+# bytes per element-subcycle the kernels are designed to move: operators folded / factored
+B_DESIGN = {("mevp", True): 784, ("mevp", False): 992, ("bbm", True): 1144, ("bbm", False): 1360}
+MESH = "rect"  # --mesh: "rect" (BASELINE.json's headline configuration) or "distorted" (parametric mesh, factored operators)
 
 
 def peaks():
@@ -106,6 +109,8 @@ def make_inputs(n: int, rheo: str):
     # not reproducible by ANY implementation; the arithmetic per element is the same at every cell size.
     L = 4000.0 * n
     ms = synthetic.benchmark_box(n, L=L)
+    if MESH == "distorted":  # parametric variant: the distortion of Advection_test.cpp:214-217 (amplitude 0.02)
+        ms["coords"] = synthetic.distort_coords(ms["coords"], 0.02)
     forcing = synthetic.benchmark_forcing(n, 0.0, L=L)
     return ms, forcing
 
@@ -166,7 +171,8 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return f"{args.rheology}_rect{args.n}x{args.n}_dg2cg2_nsteps{NSTEPS}"
+    kind = "rect" if MESH == "rect" else "para_distorted"
+    return f"{args.rheology}_{kind}{args.n}x{args.n}_dg2cg2_nsteps{NSTEPS}"
 
 
 def run_gpu(args):
@@ -259,6 +265,8 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_alg * local_elems, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
                 "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_alg,
+                "design_bytes_per_element_subcycle": B_DESIGN[(rheo, uniform)],
+                "frac_design_bytes": B_DESIGN[(rheo, uniform)] * local_elems / (pair_ms * 1e-3) / 1e9 / peak,
                 "peak_source": peak_src,
                 "dram_gbs_strip": (traffic / (strip_ms.value * 1e-3) / 1e9) if traffic else None,
                 "note": ("achieved uses SURVEY 8(d)'s algorithmic bytes (960 B per element-subcycle for uniform mEVP, counting 13 node "
@@ -300,7 +308,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(args), "grid_per_gpu": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
-                   "operators": "uniform rectangular (shared, __constant__)" if uniform else "per-element (streamed)",
+                   "operators": "uniform rectangular (shared, compile-time)" if uniform else "parametric mesh: factored from per-element geometry planes (not streamed)",
                    "l2": "working set (~3 GB) is larger than the 126 MB L2; no flush needed",
                    "parallelism": "single domain" if world == 1 else f"2-D boxes x{world}, NVLink halo exchange"},
         "roofline": roofline,
@@ -331,13 +339,22 @@ def main():
     ap.add_argument("--cpu-nsteps", type=int, default=100)
     ap.add_argument("--ref-n", type=int, default=512, help="grid size of the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mesh", default="rect", choices=["rect", "distorted"],
+                    help="rect: the headline configuration; distorted: the same box on a parametric (distorted) mesh")
     args = ap.parse_args()
+    global MESH
+    MESH = args.mesh
     if args.warmup < 3:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_gpu(args)
+        try:
+            run_gpu(args)
+        finally:
+            d = sys.modules.get("torch.distributed")
+            if d is not None and d.is_available() and d.is_initialized():
+                d.destroy_process_group()
 
 
 if __name__ == "__main__":
