@@ -159,7 +159,7 @@ def run_reference(args):
     ms_per_step = r["seconds"] / args.steps * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample_grid": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
                    "note": "each step is a bounded sample (smaller grid) of the workload; throughput per element-subcycle is size-independent on the CPU"},
@@ -202,8 +202,10 @@ def run_gpu(args):
         dyn = cls(nsteps=NSTEPS, device=local_rank, pin_host_buffers=True)
         dyn.setData(ms)
     else:
+        if MESH != "rect":
+            raise SystemExit("--mesh distorted is a single-GPU arm (the partitioned inputs are generated per window for the rectangle)")
         dyn, ms, forcing = part.make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=NSTEPS,
-                                                      make_inputs=make_inputs)
+                                                      make_inputs=make_inputs, strong=(args.scaling == "strong"))
     N_owned = dyn.owned_elements() if hasattr(dyn, "owned_elements") else n * n
 
     def barrier():
@@ -305,9 +307,9 @@ def run_gpu(args):
     ms_per_step = dev_ms / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "grid_per_gpu": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
+        "config": {"workload": workload_name(args), "grid_per_gpu": f"{dyn.partition.nx}x{dyn.partition.ny}" if world > 1 else f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
                    "operators": "uniform rectangular (shared, compile-time)" if uniform else "parametric mesh: factored from per-element geometry planes (not streamed)",
                    "l2": "working set (~3 GB) is larger than the 126 MB L2; no flush needed",
                    "parallelism": "single domain" if world == 1 else f"2-D boxes x{world}, NVLink halo exchange"},
@@ -339,6 +341,8 @@ def main():
     ap.add_argument("--cpu-nsteps", type=int, default=100)
     ap.add_argument("--ref-n", type=int, default=512, help="grid size of the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = --n x --n elements per GPU (default, the driver's scaling run); strong = --n x --n in total")
     ap.add_argument("--mesh", default="rect", choices=["rect", "distorted"],
                     help="rect: the headline configuration; distorted: the same box on a parametric (distorted) mesh")
     args = ap.parse_args()

@@ -182,9 +182,10 @@ def benchmark_window(part: Partition, L: float, t: float = 0.0):
     return ms, forcing
 
 
-def make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=100, make_inputs=None, cell=4000.0):
-    """bench.py helper: this rank's box of the weak-scaling run (n x n owned elements per GPU)."""
-    part = Partition.weak(rank, world, n)
+def make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=100, make_inputs=None, cell=4000.0, strong=False):
+    """bench.py helper: this rank's box of the weak-scaling run (n x n owned elements per GPU) or, with strong=True,
+    of the strong-scaling run (n x n elements in total, split into px x py boxes)."""
+    part = Partition.strong(rank, world, n, n) if strong else Partition.weak(rank, world, n)
     L = cell * part.global_nx
     ms, forcing = benchmark_window(part, L)
     dyn = cls(nsteps=nsteps, device=local_rank, pin_host_buffers=True, partition=part)
