@@ -15,7 +15,9 @@
  *    (core/src/include/ModelArray.hpp:92), element index i + nx*j (x fastest).
  *  - a handle is not re-entrant; calls are synchronous (results are complete on return),
  *    matching the single model thread that calls IDynamics::update
- *    (core/src/PrognosticData.cpp:95).
+ *    (core/src/PrognosticData.cpp:95).  Several handles may live in one process and be used
+ *    alternately, but from one thread at a time: handles with a uniform mesh share a
+ *    per-device constant-memory operator set that each re-uploads when it is not its owner.
  *  - there is no CPU fallback: every call fails with an error if no CUDA device is usable.
  */
 #ifndef NSDG_H

@@ -140,6 +140,8 @@ public:
     }
     ~Handle() override
     {
+        if (constOpsOwner(cfg.device) == this)
+            constOpsOwner(cfg.device) = nullptr; // a later handle may be allocated at the same address
         if (graphExec)
             cudaGraphExecDestroy(graphExec);
         closePeers();
@@ -343,8 +345,9 @@ public:
         lumpedmass_kernel<CG, CGGP><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(g, g.cgnx, g.cgny, g.cgs, vx, vy, lmass);
         lumpedmass_kernel<1, 2><<<blocksFor(size_t(nx + 1) * (ny + 1)), 128, 0, stream>>>(g, nx + 1, ny + 1, cg1s, vx, vy, mass1);
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
-        if (uniform) { // the single operator set goes to __constant__ memory for the subcycle kernels
-            MomentumOps h {};
+        if (uniform) { // the single operator set goes to __constant__ memory for the generic subcycle kernel
+            MomentumOps& h = hostMops;
+            h = MomentumOps {};
             auto pull = [&](double* dst, const DevBuf<double>& src, size_t n) {
                 NSDG_CUDA_CHECK(cudaMemcpy(dst, src.p, n * 8, cudaMemcpyDeviceToHost));
             };
@@ -354,8 +357,7 @@ public:
             pull(h.Bd, oBd, DGA * Q);
             pull(h.D1, oD1, ND * DGs);
             pull(h.D2, oD2, ND * DGs);
-            NSDG_CUDA_CHECK(cudaMemcpyToSymbol(c_mops, &h, sizeof(h)));
-            legacySync();
+            constOpsOwner(cfg.device) = nullptr; // uploaded again by ensureConstOps before the next kernel that reads it
         }
 
         // ---- strips and deferred-line buffers ----
@@ -1031,8 +1033,29 @@ public:
         subcycle_lines<CG, RHEO><<<blocksFor(nLine), 128, 0, stream>>>(a);
     }
 
+    /*
+     * c_mops is ONE __constant__ symbol per device, but every handle with a uniform mesh has its own operator set
+     * (other cell sizes, the other CG/DG build): the generic uniform kernel reads whatever the last upload left there.
+     * Each handle keeps its set on the host and re-uploads it, stream-ordered, whenever another handle (or nobody) owns the
+     * symbol.  Handles are driven from one thread at a time (nsdg.h), so two streams never need different sets at once.
+     */
+    MomentumOps hostMops {};
+    static const void*& constOpsOwner(int device)
+    {
+        static const void* owner[64] = {};
+        return owner[device >= 0 && device < 64 ? device : 0];
+    }
+    void ensureConstOps()
+    {
+        if (!uniform || constOpsOwner(cfg.device) == this)
+            return;
+        NSDG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_mops, &hostMops, sizeof(hostMops), 0, cudaMemcpyHostToDevice, stream));
+        constOpsOwner(cfg.device) = this;
+    }
+
     void runSubcycles(int n, double deltaT)
     {
+        ensureConstOps();
         const SubcycleArgs a = makeArgs(deltaT);
         const UniformArgs ua = makeUniformArgs(deltaT);
         const UniformBBMArgs ba = makeUniformBBMArgs(deltaT);
@@ -1155,6 +1178,7 @@ public:
     void timeKernels(int n, float* stripMs, float* linesMs) override
     {
         requireMesh();
+        ensureConstOps();
         const SubcycleArgs a = makeArgs(lastDeltaT);
         const UniformArgs ua = makeUniformArgs(lastDeltaT);
         const unsigned nwarps = unsigned(nsx) * nsy, nbStrip = (nwarps + 3) / 4;

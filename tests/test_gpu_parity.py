@@ -314,6 +314,44 @@ def test_fresh_handle_does_not_depend_on_device_heap_contents(rheo):
             assert np.array_equal(v, again[name]), (it, name)
 
 
+def test_interleaved_handles_with_different_uniform_meshes():
+    """Regression: the generic uniform kernel reads its operator set from ONE __constant__ symbol per device; a second
+    live handle with another cell size (or the other CG/DG build) used to overwrite the first one's operators.  Two
+    DG1/CG1 handles (always on the generic kernel) with different cell sizes are stepped alternately and must reproduce
+    their solo runs bit for bit."""
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, dt = 32, 120.0
+
+    def make(L):
+        ms = synthetic.benchmark_box(n, L=L)
+        d = CUDAMEVPDynamics(dgadv=3, cgdegree=1, nsteps=30)
+        d.setData(ms)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
+        return d
+
+    def advance(d, L, k):
+        d.shared.update({a: b.copy() for a, b in synthetic.benchmark_forcing(n, k * dt, L=L).items()})
+        d.update(dt)
+
+    sizes = (512000.0, 200000.0)
+    solo = []
+    for L in sizes:
+        d = make(L)
+        for k in range(2):
+            advance(d, L, k)
+        solo.append((d.uice.copy(), d.vice.copy()))
+        d.close()
+    both = [make(L) for L in sizes]
+    for k in range(2):
+        for d, L in zip(both, sizes):
+            advance(d, L, k)
+    for d, (u, v) in zip(both, solo):
+        assert np.array_equal(d.uice, u) and np.array_equal(d.vice, v)
+        assert np.abs(u).max() > 0
+        d.close()
+
+
 def test_constant_healing_on_device():
     """nsdg_heal_damage (N4) against the restatement of ConstantHealing::updateElement, bit-exact arithmetic."""
     from oracle.healing import constant_healing
