@@ -18,6 +18,7 @@
  *    (core/src/PrognosticData.cpp:95).  Several handles may live in one process and be used
  *    alternately, but from one thread at a time: handles with a uniform mesh share a
  *    per-device constant-memory operator set that each re-uploads when it is not its owner.
+ *    Every entry point makes the handle's device current (cudaSetDevice) and leaves it so.
  *  - there is no CPU fallback: every call fails with an error if no CUDA device is usable.
  */
 #ifndef NSDG_H

@@ -1599,7 +1599,10 @@ static HandleBase* H(nsdg_handle h)
 {
     if (!h)
         throw std::runtime_error("nsdg: null handle");
-    return reinterpret_cast<HandleBase*>(h);
+    HandleBase* b = reinterpret_cast<HandleBase*>(h);
+    // every entry point works on the handle's own device, whatever the caller (or another handle) made current
+    NSDG_CUDA_CHECK(cudaSetDevice(b->cfg.device));
+    return b;
 }
 
 extern "C" {

@@ -352,6 +352,41 @@ def test_interleaved_handles_with_different_uniform_meshes():
         d.close()
 
 
+def test_handles_on_two_devices_in_one_process():
+    """Every entry point selects the handle's own device: two handles on different GPUs driven alternately from one
+    process reproduce the single-device run bit for bit (needs 2 GPUs)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, dt = 48, 120.0
+    ms = synthetic.benchmark_box(n)
+
+    def make(dev):
+        d = CUDAMEVPDynamics(nsteps=40, device=dev)
+        d.setData(ms)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
+        return d
+
+    def advance(d, k):
+        d.shared.update({a: b.copy() for a, b in synthetic.benchmark_forcing(n, k * dt).items()})
+        d.update(dt)
+
+    solo = make(0)
+    for k in range(2):
+        advance(solo, k)
+    both = [make(0), make(1)]
+    for k in range(2):
+        for d in both:
+            advance(d, k)
+    for d in both:
+        assert np.array_equal(d.uice, solo.uice) and np.array_equal(d.vice, solo.vice)
+        d.close()
+    solo.close()
+
+
 def test_constant_healing_on_device():
     """nsdg_heal_damage (N4) against the restatement of ConstantHealing::updateElement, bit-exact arithmetic."""
     from oracle.healing import constant_healing
