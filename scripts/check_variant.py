@@ -10,6 +10,8 @@ n, dt, nsteps = 64, 120.0, 20
 worst = 0.0
 for cls, rheo in ((CUDAMEVPDynamics, "mevp"), (CUDABBMDynamics, "bbm")):
     ms = synthetic.benchmark_box(n)
+    if os.environ.get("QB_DISTORT"):  # parametric kernels
+        ms["coords"] = synthetic.distort_coords(ms["coords"], 0.02)
     gpu = cls(nsteps=nsteps)
     ref = oracle.OracleDynamics(rheo, nsteps=nsteps, impl="port")
     gpu.setData(ms); ref.setData(ms)
