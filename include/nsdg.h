@@ -155,7 +155,7 @@ int nsdg_get_internal(nsdg_handle h, const char* name, double* host, size_t capa
 int nsdg_set_internal(nsdg_handle h, const char* name, const double* host, size_t count);
 
 /* Damage healing on the device: Nextsim::ConstantHealing::updateElement
- * (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:60-80) applied to the DG0 damage of a BBM handle, so that
+ * (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:53-72) applied to the DG0 damage of a BBM handle, so that
  * the damage can stay resident between nsdg_step calls:
  *   damage = (damage (cice - g) + g) / cice,  g = max(0, delta_cice);  damage = min(1, damage + dt / td).
  * delta_cice: host array of nx*ny lateral concentration growth from the thermodynamics, or NULL for none.

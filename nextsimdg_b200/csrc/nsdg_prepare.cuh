@@ -290,7 +290,7 @@ __global__ void freedrift_kernel(GridDims g, PhysParams p, const double* __restr
 }
 
 /*
- * IDamageHealing::ConstantHealing::updateElement (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:60-80) on
+ * IDamageHealing::ConstantHealing::updateElement (physics/src/modules/DamageHealingModule/ConstantHealing.cpp:53-72) on
  * the DG0 damage and concentration:  lateral ice formation is undamaged, then linear healing with time scale tD.
  * deltaCi may be null (no thermodynamic growth, as with DummyIceThermodynamics).
  */

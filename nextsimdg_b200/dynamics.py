@@ -151,7 +151,7 @@ class CUDADynamicsBase:
         check(self._lib.nsdg_set_internal(self._h, name.encode(), as_c(a), a.size))
 
     def heal_damage(self, dt: float, td_seconds: float = 15 * 86400.0, delta_cice: np.ndarray | None = None):
-        """Nextsim::ConstantHealing on the device-resident DG0 damage (ConstantHealing.cpp:60-80); BBM handles only."""
+        """Nextsim::ConstantHealing on the device-resident DG0 damage (ConstantHealing.cpp:53-72); BBM handles only."""
         ptr = None
         if delta_cice is not None:
             self._dci = np.ascontiguousarray(delta_cice, dtype=np.float64)

@@ -5,7 +5,7 @@
  * so that tests/ can pin the oracle against the L2 errors stored in the reference tests.
  *
  * Reference: dynamics/test/Advection_test.cpp:44-308          (rotating bump, box mesh)
- *            dynamics/test/AdvectionPeriodicBC_test.cpp:35-300 (ring mesh, periodic + limiter)
+ *            dynamics/test/AdvectionPeriodicBC_test.cpp:35-298 (ring mesh, periodic + limiter)
  */
 #include "nsdg_transport.hpp"
 
