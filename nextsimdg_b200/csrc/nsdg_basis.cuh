@@ -9,7 +9,8 @@
  *             (y-1/2)((x-1/2)^2-1/12), (x-1/2)((y-1/2)^2-1/12)}   dynamics/codegeneration/basisfunctions.py:28-52
  *   Lagrange Q1/Q2 CG basis, x-fastest local numbering            basisfunctions.py:107-166
  *   Gauss rules on [0,1]                                          gaussquadrature.py:6-22
- *   table shapes PSI<DG,GP>, PHI<CG,GP>, PSIe_w<DG,GP,E>          dynamics/src/include/codeGenerationDGinGauss.hpp:105-981
+ *   table shapes PSI<DG,GP>, PSIe_w<DG,GP,E>                      dynamics/src/include/codeGenerationDGinGauss.hpp:105-981
+ *                PHI<CG,GP>, PHIx, PHIy, PHI1d                      dynamics/src/include/codeGenerationCGinGauss.hpp:14-461
  */
 #pragma once
 

@@ -461,7 +461,8 @@ public:
             throw std::runtime_error("nsdg: mesh not set (call nsdg_set_mesh first)");
     }
 
-    //! host AoS (N x ncomp) -> device planes (nplanes), DGModelArray::ma2dg semantics (quirk Q4)
+    //! host AoS (N x ncomp) -> device planes (nplanes), DGModelArray::ma2dg semantics (dynamics/src/include/DGModelArray.hpp:20-32;
+    //! quirk Q4: a one-component source fills component 0 and zeroes the others); downloadPlanes = dg2ma (:34-48)
     void uploadPlanes(const double* host, int ncomp, int nplanes, double* planes)
     {
         if (ncomp != 1 && ncomp != nplanes)

@@ -31,6 +31,8 @@
  * byte mask built once from the sorted Dirichlet lists: the stress divergence is zeroed there
  * before the momentum update and u,v after it, as in the reference's sweep order.
  * Quirk Q8: strain and divergence skip land elements, the stress update does not.
+ * The periodic averaging at the end of stressDivergence (CGAveragePeriodic, dynamics/src/include/VectorManipulations.hpp:26-65)
+ * has no device counterpart: IDynamics never marks periodic edges (DynamicsKernel.hpp:54), the lists are always empty.
  */
 #pragma once
 #include "nsdg_state.cuh"
