@@ -55,3 +55,19 @@ def test_product_arm_json_line_small_grid():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_committed_ncu_traffic_covers_the_bench_workloads():
+    """bench.py's roofline.traffic comes from profiles/ncu_traffic.json, keyed by the workload name of the default runs."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    for rheo in ("mevp", "bbm"):
+        name = bench.workload_name(argparse.Namespace(rheology=rheo, n=2048))
+        assert name in table and table[name]["dram_bytes_per_launch"] > 1e9, name
+        src = table[name]["source"].split(" ")[0]
+        assert os.path.exists(os.path.join(ROOT, src)), src
