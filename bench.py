@@ -170,9 +170,257 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    kind = "rect" if MESH == "rect" else "para_distorted"
-    return f"{args.rheology}_{kind}{args.n}x{args.n}_dg2cg2_nsteps{NSTEPS}"
+def workload_name(args, rheo=None, mesh=None, n=None):
+    kind = "rect" if (mesh or MESH) == "rect" else "para_distorted"
+    n = n or args.n
+    return f"{rheo or args.rheology}_{kind}{n}x{n}_dg2cg2_nsteps{NSTEPS}"
+
+
+def _export_fields(dyn, rheo):
+    out = {"u": dyn.uice, "v": dyn.vice, "hice": dyn.shared["hice"], "cice": dyn.shared["cice"], "taux": dyn.taux, "tauy": dyn.tauy}
+    if rheo == "bbm":
+        out["damage"] = dyn.damage
+    return out
+
+
+def finite_check(dyn, rheo, mask):
+    """Every field the module exports after the timed steps is finite on the ice elements and the ice moves: a NaN or an
+    all-zero state would bench at the same speed, so the bench refuses to report one."""
+    ice = np.asarray(mask).astype(bool)
+    bad = [k for k, v in _export_fields(dyn, rheo).items() if not np.isfinite(np.asarray(v)[ice]).all()]
+    umax = float(np.abs(dyn.uice[ice]).max()) if not bad else float("nan")
+    return {"ok": (not bad) and umax > 0.0, "non_finite_fields": bad, "max_abs_u": umax}
+
+
+def parity_probe_single(rheo, mesh, n, device):
+    """N = 1: the 96 x 96 crop property of tests/test_gpu_parity.py::test_locality_and_determinism_at_full_size on THIS
+    arm's grid.  Information travels one element per subcycle, so after k subcycles a window far from the crop edge of the
+    full-size GPU run equals the same window of the CHECKER (the reference's own kernels, oracle/_ref; else the
+    restatement) run on the crop alone.  The oracle is used here as the checker only."""
+    import oracle
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, synthetic
+
+    crop = 96
+    if n < 4 * crop:
+        return None
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    k, dt = (12, 120.0) if rheo == "mevp" else (10, 12.0)  # BBM keeps the reference's 1.2 s sub-step (DESIGN.md, conditioning)
+    L = 4000.0 * n
+    ms = synthetic.benchmark_box(n, L=L, ring_mask=False)
+    if mesh == "distorted":
+        ms["coords"] = synthetic.distort_coords(ms["coords"], 0.02)
+    f = synthetic.benchmark_forcing(n, 0.0, L=L)
+    d = cls(nsteps=k, device=device)
+    d.setData(ms)
+    d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{a: b.copy() for a, b in f.items()}}
+    d.update(dt)
+    big = {"u": d.uice.copy(), "v": d.vice.copy(), "hice": d.shared["hice"].copy()}
+    d.close()
+    i0, j0 = n // 2 - 24, n // 3 + 17
+    sl = (slice(j0, j0 + crop), slice(i0, i0 + crop))
+    z = np.zeros((crop, crop))
+    msc = {"coords": np.ascontiguousarray(ms["coords"][j0:j0 + crop + 1, i0:i0 + crop + 1] - ms["coords"][j0, i0]),
+           "mask": np.ones((crop, crop)), "x": z, "y": z, "hice": np.ascontiguousarray(ms["hice"][sl]),
+           "cice": np.ascontiguousarray(ms["cice"][sl]), "u": z.copy(), "v": z.copy()}
+    impl = "reference" if oracle.have_ref(2) else "port"
+    ref = oracle.OracleDynamics(rheo, 6, 2, k, impl=impl)
+    ref.setData(msc)
+    ref.shared = {"hice": msc["hice"].copy(), "cice": msc["cice"].copy(), **{a: np.ascontiguousarray(b[sl]) for a, b in f.items()}}
+    ref.update(dt)
+    m = k + 6  # margin: k subcycles + the advection / DG2CG stencils
+    inner = (slice(m, crop - m), slice(m, crop - m))
+    errs = {}
+    for name, want in (("u", ref.uice), ("v", ref.vice), ("hice", ref.shared["hice"])):
+        got = big[name][sl][inner]
+        errs[name] = float(np.abs(got - want[inner]).max() / max(np.abs(want[inner]).max(), 1e-300))
+    worst = max(errs.values())
+    return {"max_rel_err": worst, "ok": bool(worst < 1e-10), "tolerance": 1e-10, "checker": "oracle/_ref (the reference's own kernels)" if impl == "reference" else "oracle port",
+            "what": f"{crop}x{crop} crop of the {n}x{n} {rheo} {mesh} GPU run after {k} subcycles vs the checker on the crop alone, inner window",
+            "fields": errs}
+
+
+def parity_probe_partitioned(rheo, rank, world, device, dist):
+    """N > 1: the probe cases of tests/mgpu_parity.py on the bench's own ranks -- boxes with halo exchange against the same
+    problem as one domain on rank 0's GPU, and that single-domain result against the reference's kernels on the host."""
+    from nextsimdg_b200 import partition as part
+
+    gather = part.torch_all_gather(dist)
+    worst, ref_worst, cases = 0.0, None, []
+    for r, kind in ((rheo, "uniform"), (rheo, "distorted"), ("mevp", "spherical")):
+        errs = part.partition_probe(r, kind, rank, world, device, gather, nsteps=40, nts=2)
+        if rank == 0:
+            single = errs.pop("single")
+            e = max(errs.values()) if all(np.isfinite(list(errs.values()))) else float("nan")
+            worst = e if not (e <= worst) else worst
+            cases.append({"case": f"{r}_{kind}", "max_rel_err_vs_single_domain": e})
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import mgpu_parity
+
+                rr = mgpu_parity.reference_check(r, kind, single, 40, 2)
+                if rr is not None:
+                    cases[-1]["single_domain_vs_reference"] = rr
+                    ref_worst = rr if ref_worst is None or not (rr <= ref_worst) else ref_worst
+            except Exception as ex:  # the checker is optional on the box; its absence is reported, not hidden
+                cases[-1]["single_domain_vs_reference"] = f"unavailable: {ex}"
+    if rank != 0:
+        return None
+    ok = bool(worst < 1e-10) and (ref_worst is None or bool(ref_worst < 1e-9))
+    return {"max_rel_err": worst, "ok": ok, "tolerance": 1e-10, "single_domain_vs_reference_max": ref_worst,
+            "what": f"{world} boxes with NVLink halo exchange vs the same problem on one GPU (nextsimdg_b200.partition.partition_probe), 2 updates of 40 subcycles",
+            "cases": cases}
+
+
+def measure_arm(args, rheo, mesh, n, steps, warmup, e2e_steps, rank, local_rank, world, dist, label=None, ms_override=None,
+                nsteps=NSTEPS, dt=DT):
+    """One workload through the device-resident arm, the kernel-pair roofline and the end-to-end arm."""
+    global MESH
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, capi
+    from nextsimdg_b200 import partition as part
+
+    MESH = mesh
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    if world == 1:
+        ms, forcing = ms_override if ms_override is not None else make_inputs(n, rheo)
+        dyn = cls(nsteps=nsteps, device=local_rank, pin_host_buffers=True)
+        dyn.setData(ms)
+    else:
+        if mesh != "rect":
+            raise SystemExit("--mesh distorted is a single-GPU arm (the partitioned inputs are generated per window for the rectangle)")
+        dyn, ms, forcing = part.make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=nsteps,
+                                                      make_inputs=make_inputs, strong=(args.scaling == "strong"))
+    N_owned = dyn.owned_elements() if hasattr(dyn, "owned_elements") else dyn.nx * dyn.ny
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ranks(flag: bool) -> bool:
+        return max_over_ranks(0.0 if flag else 1.0) == 0.0
+
+    # ---- device-resident arm ----
+    dg0 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64)[..., 0] if np.asarray(a).ndim == 3 else a)  # noqa: E731
+    dyn.shared = {"hice": dg0(ms["hice"]).copy(), "cice": dg0(ms["cice"]).copy(), **{k: v.copy() for k, v in forcing.items()}}
+    dyn.update(dt)  # uploads every input once; state is resident from here on
+    for _ in range(warmup):
+        dyn.step(dt)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    dev_ms, adv_ms, prep_ms, sub_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dyn.step(dt)
+        t = dyn.timing()
+        dev_ms += t.total_ms
+        adv_ms += t.advection_ms
+        prep_ms += t.prepare_ms
+        sub_ms += t.subcycle_ms
+        launches += t.kernel_launches
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = max_over_ranks(dev_ms)
+    units = float(N_owned) * nsteps * steps * world
+    value = units / (dev_ms * 1e-3)
+    uniform = bool(dyn.timing().uniform_path)
+    spherical = "longitude" in ms
+
+    # ---- roofline of the subcycle kernel pair, timed live with CUDA events on the launching stream ----
+    strip_ms = ctypes.c_float()
+    lines_ms = ctypes.c_float()
+    capi.check(dyn._lib.nsdg_time_kernels(dyn._h, 20, ctypes.byref(strip_ms), ctypes.byref(lines_ms)))
+    peak, peak_src = peaks()
+    wl = label or workload_name(args, rheo, mesh, n)
+    local_elems = dyn.nx * dyn.ny
+    pair_ms = strip_ms.value + lines_ms.value
+    b_survey = B_ALG[(rheo, uniform)] if not spherical else {"mevp": 4992, "bbm": 4432 + 1152}[rheo]
+    b_design = B_DESIGN[(rheo, uniform)] if not spherical else {"mevp": 1136, "bbm": 1504}[rheo]
+    # uniform rectangle: SURVEY 8(d)'s algorithmic bytes.  Parametric / spherical meshes: SURVEY counts 360 - 558 operator
+    # doubles per element that this design does not stream (they are factored from 22 - 48 geometry doubles, DESIGN 3.4),
+    # so the fraction is quoted on the bytes the kernel is designed to move; the SURVEY figure is a side key.
+    b_used = b_survey if uniform else b_design
+    achieved = b_used * local_elems / (pair_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # per-launch DRAM bytes of the strip kernel from the committed ncu --set full capture of this workload
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[wl]["dram_bytes_per_launch"]
+        if local_elems != n * n:
+            traffic = traffic * local_elems / float(n * n)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": b_used * local_elems,
+                "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
+                "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_used,
+                "bytes_basis": "SURVEY 8(d) algorithmic bytes" if uniform else "design bytes: state + factored geometry planes (operators are not streamed)",
+                "design_bytes_per_element_subcycle": b_design,
+                "frac_design_bytes": b_design * local_elems / (pair_ms * 1e-3) / 1e9 / peak,
+                "peak_source": peak_src,
+                "dram_gbs_strip": (traffic / (strip_ms.value * 1e-3) / 1e9) if traffic else None,
+                "frac_measured_traffic": (traffic / (strip_ms.value * 1e-3) / 1e9 / peak) if traffic else None}
+    if not uniform:
+        roofline["survey_streamed_operator_bytes_per_element_subcycle"] = b_survey
+        roofline["speedup_vs_streaming_at_peak"] = b_survey / b_design
+    if uniform and rheo == "mevp":
+        roofline["note"] = ("achieved uses SURVEY 8(d)'s 960 B per element-subcycle (13 node reads); the kernel folds those into 6 "
+                            "per-node constants (784 B), so `traffic` (ncu, strip kernel) is below `algorithmic_bytes_per_launch` and frac can "
+                            "exceed 1; frac_measured_traffic = traffic / strip_ms / peak is the real DRAM throughput of the dominant kernel")
+    elif uniform:
+        roofline["note"] = ("achieved uses SURVEY 8(d)'s 1120 B per element-subcycle; the kernel additionally reads 27 per-step Gauss-point "
+                            "constants per element instead of recomputing exp/pow every subcycle, so `traffic` is slightly above it")
+
+    # ---- end-to-end arm: host buffers in, host buffers out, every step ----
+    for _ in range(min(warmup, 2)):
+        dyn.update(dt)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dyn.update(dt)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = float(N_owned) * nsteps * e2e_steps * world / e2e_s
+    nin = 8 if rheo == "bbm" else 7
+    nout = 7 if rheo == "bbm" else 6
+    field_bytes = dyn.nx * dyn.ny * 8
+    fin = finite_check(dyn, rheo, ms["mask"])
+    fin["ok"] = all_ranks(fin["ok"])
+    ms_per_step = dev_ms / steps
+    res = {
+        "workload": wl, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nin * field_bytes, "d2h_bytes_per_step": nout * field_bytes,
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "phases_ms_per_step": {"advection": adv_ms / steps, "prepare": prep_ms / steps, "subcycles": sub_ms / steps},
+        "subcycle_loop_only": float(N_owned) * nsteps * steps * world / (sub_ms * 1e-3),
+        "us_per_subcycle": sub_ms / steps / nsteps * 1e3,
+        "model_days_per_wall_hour": 3600.0 / (ms_per_step * 1e-3 * (86400.0 / dt)),
+        "finite_check": fin, "wall_s_timed_region": wall, "uniform": uniform,
+        "grid": f"{dyn.partition.nx}x{dyn.partition.ny}" if world > 1 else f"{dyn.nx}x{dyn.ny}",
+    }
+    dyn.close()
+    return res
+
+
+def small_grid_inputs(kind):
+    """BASELINE.json configs[2] / configs[3]: the 256 x 256 benchmark box (BBM) and the TOPAZ-like 128 x 128 spherical grid (mEVP)."""
+    from nextsimdg_b200 import synthetic
+
+    if kind == "topaz128":
+        return synthetic.topaz_like_spherical(128), synthetic.smooth_forcing(128, 128)
+    return synthetic.benchmark_box(256), synthetic.benchmark_forcing(256, 0.0)
 
 
 def run_gpu(args):
@@ -192,107 +440,34 @@ def run_gpu(args):
         dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_
 
-    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, capi
-    from nextsimdg_b200 import partition as part
+    n, rheo, mesh = args.n, args.rheology, MESH
+    main = measure_arm(args, rheo, mesh, n, args.steps, args.warmup, args.e2e_steps, rank, local_rank, world, dist)
 
-    n, rheo = args.n, args.rheology
-    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    # ---- correctness where speed is measured ----
     if world == 1:
-        ms, forcing = make_inputs(n, rheo)
-        dyn = cls(nsteps=NSTEPS, device=local_rank, pin_host_buffers=True)
-        dyn.setData(ms)
+        parity = None if args.no_parity_check else parity_probe_single(rheo, mesh, n, local_rank)
     else:
-        if MESH != "rect":
-            raise SystemExit("--mesh distorted is a single-GPU arm (the partitioned inputs are generated per window for the rectangle)")
-        dyn, ms, forcing = part.make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=NSTEPS,
-                                                      make_inputs=make_inputs, strong=(args.scaling == "strong"))
-    N_owned = dyn.owned_elements() if hasattr(dyn, "owned_elements") else n * n
+        parity = parity_probe_partitioned(rheo, rank, world, local_rank, dist)
 
-    def barrier():
-        if dist is not None:
-            import torch
-
-            torch.cuda.synchronize()
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident arm ----
-    dyn.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{k: v.copy() for k, v in forcing.items()}}
-    dyn.update(DT)  # uploads every input once; state is resident from here on
-    for _ in range(args.warmup):
-        dyn.step(DT)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    dev_ms, adv_ms, prep_ms, sub_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dyn.step(DT)
-        t = dyn.timing()
-        dev_ms += t.total_ms
-        adv_ms += t.advection_ms
-        prep_ms += t.prepare_ms
-        sub_ms += t.subcycle_ms
-        launches += t.kernel_launches
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop() if sampler else None
-    dev_ms = max_over_ranks(dev_ms)
-    units = float(N_owned) * NSTEPS * args.steps * world
-    value = units / (dev_ms * 1e-3)
-    uniform = bool(dyn.timing().uniform_path)
-
-    # ---- roofline of the subcycle kernel pair, timed live with CUDA events on the launching stream ----
-    strip_ms = ctypes.c_float()
-    lines_ms = ctypes.c_float()
-    capi.check(dyn._lib.nsdg_time_kernels(dyn._h, 20, ctypes.byref(strip_ms), ctypes.byref(lines_ms)))
-    peak, peak_src = peaks()
-    b_alg = B_ALG[(rheo, uniform)]
-    local_elems = dyn.nx * dyn.ny
-    pair_ms = strip_ms.value + lines_ms.value
-    achieved = b_alg * local_elems / (pair_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # per-launch DRAM bytes of the strip kernel from the committed ncu --set full capture of this workload
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload_name(args)]["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": b_alg * local_elems, "kernel": "subcycle_strip + subcycle_lines (one subcycle)", "strip_ms": strip_ms.value,
-                "lines_ms": lines_ms.value, "halo_ms": dyn.timing().halo_ms, "alg_bytes_per_element_subcycle": b_alg,
-                "design_bytes_per_element_subcycle": B_DESIGN[(rheo, uniform)],
-                "frac_design_bytes": B_DESIGN[(rheo, uniform)] * local_elems / (pair_ms * 1e-3) / 1e9 / peak,
-                "peak_source": peak_src,
-                "dram_gbs_strip": (traffic / (strip_ms.value * 1e-3) / 1e9) if traffic else None,
-                "note": ("achieved uses SURVEY 8(d)'s algorithmic bytes (960 B per element-subcycle for uniform mEVP, counting 13 node "
-                         "reads); the kernels fold those into 6 per-node constants, so the measured DRAM traffic per strip launch "
-                         "(`traffic`, ncu) is lower than `algorithmic_bytes_per_launch` and frac can exceed 1; dram_gbs_strip = "
-                         "traffic / strip_ms is the real DRAM throughput of the dominant kernel") if rheo == "mevp" else
-                        ("achieved uses SURVEY 8(d)'s algorithmic bytes (1120 B per element-subcycle for uniform BBM); the kernel "
-                         "additionally reads 27 per-step Gauss-point constants per element (h, exp(C(1-a)), Pmax) instead of "
-                         "recomputing exp/pow in every subcycle, so `traffic` (ncu, strip kernel) is slightly above "
-                         "`algorithmic_bytes_per_launch`; dram_gbs_strip = traffic / strip_ms")}
-
-    # ---- end-to-end arm: host buffers in, host buffers out, every step ----
-    for _ in range(min(args.warmup, 2)):
-        dyn.update(DT)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        dyn.update(DT)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = float(N_owned) * NSTEPS * args.e2e_steps * world / e2e_s
-    nin = 8 if rheo == "bbm" else 7
-    nout = 7 if rheo == "bbm" else 6
-    field_bytes = dyn.nx * dyn.ny * 8
+    # ---- the other north-star arms (N = 1 only): BBM, parametric meshes, the small-grid configurations ----
+    secondary = {}
+    if world == 1 and not args.no_secondary and (rheo, mesh, n) == ("mevp", "rect", 2048):
+        for r2, m2 in (("bbm", "rect"), ("mevp", "distorted"), ("bbm", "distorted")):
+            a = measure_arm(args, r2, m2, n, 3, 3, 2, rank, local_rank, world, dist)
+            if not args.no_parity_check:
+                a["parity_check"] = parity_probe_single(r2, m2, n, local_rank)
+            for k in ("clocks", "wall_s_timed_region"):
+                a.pop(k, None)
+            secondary[a["workload"]] = a
+        for kind, r2, dt2, label in (("topaz128", "mevp", 600.0, "mevp_topaz128x128_spherical_dg2cg2_nsteps100"),
+                                     ("box256", "bbm", 120.0, "bbm_rect256x256_dg2cg2_nsteps100")):
+            a = measure_arm(args, r2, "rect", 128 if kind == "topaz128" else 256, 10, 3, 3, rank, local_rank, world, dist, label=label,
+                            ms_override=small_grid_inputs(kind), dt=dt2)
+            for k in ("clocks", "wall_s_timed_region"):
+                a.pop(k, None)
+            a["launch_latency_floor_us_per_subcycle"] = 2 * 2.0  # two kernels per subcycle, ~2 us per graph node
+            secondary[label] = a
+    MESH_restore(mesh)
 
     if rank != 0:
         return
@@ -304,28 +479,39 @@ def run_gpu(args):
             port = cpu_oracle_run(args.cpu_n, rheo, args.cpu_nsteps, 1, 1, impl="port")
             cpu["port_value"] = port["value"]
             cpu["port_subcycle_loop_only"] = port["subcycle_loop_only"]
-    ms_per_step = dev_ms / args.steps
+    uniform = main["uniform"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "grid_per_gpu": f"{dyn.partition.nx}x{dyn.partition.ny}" if world > 1 else f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
+        "config": {"workload": workload_name(args), "grid_per_gpu": main["grid"], "nsteps": NSTEPS, "dt": DT,
                    "operators": "uniform rectangular (shared, compile-time)" if uniform else "parametric mesh: factored from per-element geometry planes (not streamed)",
                    "l2": "working set (~3 GB) is larger than the 126 MB L2; no flush needed",
                    "parallelism": "single domain" if world == 1 else f"2-D boxes x{world}, NVLink halo exchange"},
-        "roofline": roofline,
+        "roofline": main["roofline"],
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nin * field_bytes, "d2h_bytes_per_step": nout * field_bytes,
-                "steps": args.e2e_steps, "ms_per_step": e2e_s / args.e2e_steps * 1e3},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "phases_ms_per_step": {"advection": adv_ms / args.steps, "prepare": prep_ms / args.steps, "subcycles": sub_ms / args.steps},
-        "subcycle_loop_only": float(N_owned) * NSTEPS * args.steps * world / (sub_ms * 1e-3),
-        "model_days_per_wall_hour": 3600.0 / (ms_per_step * 1e-3 * (86400.0 / DT)),
-        "wall_s_timed_region": wall,
+        "e2e": main["e2e"],
+        "gpu_launches": main["gpu_launches"],
+        "clocks": main["clocks"],
+        "parity_check": parity,
+        "finite_check": main["finite_check"],
+        "phases_ms_per_step": main["phases_ms_per_step"],
+        "subcycle_loop_only": main["subcycle_loop_only"],
+        "model_days_per_wall_hour": main["model_days_per_wall_hour"],
+        "wall_s_timed_region": main["wall_s_timed_region"],
     }
+    if secondary:
+        line["secondary"] = secondary
+    bad = (not main["finite_check"]["ok"]) or (parity is not None and not parity["ok"])
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if bad:
+        raise SystemExit("bench: the timed state failed its correctness check (finite_check / parity_check): the number above is void")
+
+
+def MESH_restore(mesh):
+    global MESH
+    MESH = mesh
 
 
 def main():
@@ -341,6 +527,8 @@ def main():
     ap.add_argument("--cpu-nsteps", type=int, default=100)
     ap.add_argument("--ref-n", type=int, default=512, help="grid size of the --impl reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the BBM / parametric / small-grid arms of the default N=1 run")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the crop-vs-checker probe (N=1)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = --n x --n elements per GPU (default, the driver's scaling run); strong = --n x --n in total")
     ap.add_argument("--mesh", default="rect", choices=["rect", "distorted"],

@@ -16,8 +16,9 @@
  *  - a handle is not re-entrant; calls are synchronous (results are complete on return),
  *    matching the single model thread that calls IDynamics::update
  *    (core/src/PrognosticData.cpp:95).  Several handles may live in one process and be used
- *    alternately, but from one thread at a time: handles with a uniform mesh share a
- *    per-device constant-memory operator set that each re-uploads when it is not its owner.
+ *    alternately, but from one thread at a time: handles that run the generic kernel on a uniform
+ *    mesh (either CG/DG build) share one per-device constant-memory operator set that each
+ *    re-uploads when it is not its owner.
  *    Every entry point makes the handle's device current (cudaSetDevice) and leaves it so.
  *  - there is no CPU fallback: every call fails with an error if no CUDA device is usable.
  */
@@ -103,7 +104,9 @@ int nsdg_destroy(nsdg_handle h);
  *               pi/180 first, MEVPDynamics.cpp:43-46)
  *   mask      : nx*ny doubles, 1.0 = ocean/ice element (ParametricMesh.cpp:221)
  * With a partition in the config, nx, ny, coords and mask describe the box INCLUDING its
- * one-element overlap ring where a neighbour exists. */
+ * one-element overlap ring where a neighbour exists.  Calling it again on a box whose halos are connected
+ * disconnects them (the arena its neighbours mapped is reallocated): every box of the partition must then
+ * repeat nsdg_halo_export / nsdg_halo_connect / nsdg_halo_ready. */
 int nsdg_set_mesh(nsdg_handle h, int nx, int ny, const double* coords_xy, const double* mask, int spherical);
 
 /* Replaces: DynamicsKernel::setData(name, ModelArray) (DynamicsKernel.hpp:92-112,
@@ -164,8 +167,9 @@ int nsdg_heal_damage(nsdg_handle h, double dt_seconds, double td_seconds, const 
 
 /* ---- restart state --------------------------------------------------------------------------------
  * Everything the dynamics carries from one timestep to the next, in the reference's layouts, as one flat buffer of
- * doubles: an 8-double header {magic, version, rheology, dgadv, cgdegree, nx, ny, nfields}, then per field its
- * length followed by its data.  Fields: hice, cice [, damage] (N x DGadv, the prognostic DG fields a restart file
+ * doubles: a 10-double header {magic, version, rheology, dgadv, cgdegree, nx, ny, nfields, box_x0, box_y0}, then per
+ * field its length followed by its data (nsdg_set_state validates every header entry and length: a corrupted, truncated
+ * or foreign buffer -- other mesh size, other partition box -- is rejected, never read out of bounds).  Fields: hice, cice [, damage] (N x DGadv, the prognostic DG fields a restart file
  * holds, BBMDynamics.cpp:104-132), the CG velocity u, v and the DG stresses s11, s12, s22 -- which the reference does
  * NOT checkpoint (CGDynamicsKernel.cpp:57 TODO; its restarts begin from zero stress) -- and, for BBM, the running-mean
  * velocity that advects the next step (BrittleCGDynamicsKernel.hpp:89).  get -> set on a fresh handle with the same
@@ -199,7 +203,9 @@ int nsdg_get_timing(nsdg_handle h, nsdg_timing* t);
 int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handle /* NSDG_IPC_HANDLE_BYTES */);
 /* map the arena of the neighbour across `side` (enum nsdg_side) */
 int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handle);
-/* all neighbour sides connected: from now on nsdg_step / nsdg_update / nsdg_subcycles exchange halos */
+/* all neighbour sides connected: from now on nsdg_step / nsdg_update / nsdg_subcycles exchange halos.
+ * A box whose neighbour does not deliver within 30 s of wall-clock time (device %globaltimer) gives up; the entry
+ * point then returns an error ("halo exchange timed out") instead of a result computed on stale ring data. */
 int nsdg_halo_ready(nsdg_handle h);
 
 const char* nsdg_last_error(void);

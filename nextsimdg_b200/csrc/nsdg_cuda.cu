@@ -30,6 +30,14 @@ namespace nsdg {
 static thread_local std::string g_lastError;
 
 static inline unsigned blocksFor(size_t n, unsigned bs = 128) { return unsigned((n + bs - 1) / bs); }
+
+//! Which handle's operator set currently sits in the per-device __constant__ symbol c_mops.  ONE table for every
+//! Handle<CG, DGA> instantiation: the (6,2) and the (3,1) build upload into the same symbol.
+static const void*& constOpsOwner(int device)
+{
+    static const void* owner[64] = {};
+    return owner[device >= 0 && device < 64 ? device : 0];
+}
 static inline size_t alignUp(size_t n, size_t a) { return (n + a - 1) / a * a; }
 
 //! type-erased handle
@@ -227,6 +235,10 @@ public:
             cudaGraphExecDestroy(graphExec);
             graphExec = nullptr;
         }
+        // a new mesh frees the halo arena the neighbours have mapped and restarts the exchange epochs: drop my own peer
+        // mappings; every box of the partition has to go through export / connect / ready again
+        haloActive = false;
+        closePeers();
         g.nx = nx;
         g.ny = ny;
         g.N = nx * ny;
@@ -337,7 +349,8 @@ public:
         odY.alloc(16 * opN);
         streamedOpsBuilt = false;
         mop = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, odX, odY, opN, uniform ? 0 : 1 };
-        if (factored)
+        // free drift runs no subcycle kernel at all: the SSH matrices alone (the rest only on demand, nsdg_get_internal)
+        if (factored || cfg.rheology == NSDG_FREEDRIFT)
             setup_momentum_kernel<CG, DGA><<<blocksFor(nel, 64), 64, 0, stream>>>(g, vx, vy, mop, nel, false);
         else
             ensureStreamedOps();
@@ -345,7 +358,7 @@ public:
         lumpedmass_kernel<CG, CGGP><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(g, g.cgnx, g.cgny, g.cgs, vx, vy, lmass);
         lumpedmass_kernel<1, 2><<<blocksFor(size_t(nx + 1) * (ny + 1)), 128, 0, stream>>>(g, nx + 1, ny + 1, cg1s, vx, vy, mass1);
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
-        if (uniform) { // the single operator set goes to __constant__ memory for the generic subcycle kernel
+        if (uniform && streamedOpsBuilt) { // the single operator set goes to __constant__ memory for the generic subcycle kernel
             MomentumOps& h = hostMops;
             h = MomentumOps {};
             auto pull = [&](double* dst, const DevBuf<double>& src, size_t n) {
@@ -772,14 +785,21 @@ public:
         double* f[1] = { planes };
         exchange(f, ncomp, g.Npad, false);
     }
+    //! Called after the final stream synchronisation of every entry point that exchanges halos: a box whose neighbour
+    //! never delivered (halo_unpack_kernel's wall-clock timeout) has NOT unpacked, so its ring holds stale data and the
+    //! call must fail instead of returning success.  The flag is cleared once reported.
     void checkHaloError()
     {
         if (!haloActive)
             return;
         int e = 0;
-        NSDG_CUDA_CHECK(cudaMemcpy(&e, haloError.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (e)
-            throw std::runtime_error("nsdg: halo exchange timed out waiting for a neighbour box");
+        NSDG_CUDA_CHECK(cudaMemcpyAsync(&e, haloError.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (e) {
+            NSDG_CUDA_CHECK(cudaMemsetAsync(haloError.p, 0, sizeof(int), stream));
+            NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+            throw std::runtime_error("nsdg: halo exchange timed out waiting for a neighbour box; this box's ring data are stale");
+        }
     }
 
     // ------------------------------------------------------------------------------------
@@ -1038,17 +1058,15 @@ public:
      * c_mops is ONE __constant__ symbol per device, but every handle with a uniform mesh has its own operator set
      * (other cell sizes, the other CG/DG build): the generic uniform kernel reads whatever the last upload left there.
      * Each handle keeps its set on the host and re-uploads it, stream-ordered, whenever another handle (or nobody) owns the
-     * symbol.  Handles are driven from one thread at a time (nsdg.h), so two streams never need different sets at once.
+     * symbol (constOpsOwner: one table at namespace scope, shared by both template instantiations).  Handles are driven from one thread at a time (nsdg.h), so two streams never need different sets at once.
      */
     MomentumOps hostMops {};
-    static const void*& constOpsOwner(int device)
-    {
-        static const void* owner[64] = {};
-        return owner[device >= 0 && device < 64 ? device : 0];
-    }
+    //! only the generic kernel on a uniform mesh reads c_mops (the fast kernels carry compile-time unit operators,
+    //! free drift runs no subcycle kernel)
+    bool readsConstOps() const { return uniform && !fastMEVP() && !fastBBM() && cfg.rheology != NSDG_FREEDRIFT; }
     void ensureConstOps()
     {
-        if (!uniform || constOpsOwner(cfg.device) == this)
+        if (!readsConstOps() || constOpsOwner(cfg.device) == this)
             return;
         NSDG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_mops, &hostMops, sizeof(hostMops), 0, cudaMemcpyHostToDevice, stream));
         constOpsOwner(cfg.device) = this;
@@ -1165,6 +1183,7 @@ public:
         runSubcycles(n, deltaT);
         NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        checkHaloError();
         float t = 0;
         NSDG_CUDA_CHECK(cudaEventElapsedTime(&t, ev[0], ev[1]));
         if (ms)
@@ -1216,6 +1235,7 @@ public:
             tl += y;
             th += z;
         }
+        checkHaloError();
         *stripMs = float(ts / n);
         *linesMs = float(tl / n);
         timing.halo_ms = float(th / n);
@@ -1316,6 +1336,7 @@ public:
     {
         stepAsync(dt);
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        checkHaloError();
         finishTiming();
     }
 
@@ -1393,6 +1414,7 @@ public:
         if (overlap)
             NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evCopyDone, 0));
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        checkHaloError();
         finishTiming();
     }
 
@@ -1749,6 +1771,17 @@ int nsdg_heal_damage(nsdg_handle h, double dt_seconds, double td_seconds, const 
 }
 namespace {
 constexpr double kStateMagic = 1314079815.0; // 'NSDG'
+constexpr double kStateVersion = 2.0; // 2: the header carries the partition box origin
+constexpr size_t kStateHeader = 10;
+//! a double of a state buffer that must be a small non-negative integer (a corrupted buffer may hold anything, and
+//! converting NaN / negative / huge doubles to an integer type is undefined behaviour)
+bool stateInt(double v, double maxv, size_t* out)
+{
+    if (!(v >= 0.0) || !(v <= maxv) || v != std::floor(v))
+        return false;
+    *out = size_t(v);
+    return true;
+}
 std::vector<std::string> stateFields(const nsdg_config& c)
 {
     std::vector<std::string> f = { "hice", "cice" };
@@ -1768,7 +1801,7 @@ int nsdg_get_state(nsdg_handle h, double* host, size_t capacity, size_t* count)
     NSDG_TRY
     HandleBase* hb = H(h);
     const auto fields = stateFields(hb->cfg);
-    size_t total = 8;
+    size_t total = kStateHeader;
     std::vector<size_t> len(fields.size());
     for (size_t i = 0; i < fields.size(); ++i) {
         hb->getInternal(fields[i], nullptr, 0, &len[i]);
@@ -1783,10 +1816,11 @@ int nsdg_get_state(nsdg_handle h, double* host, size_t capacity, size_t* count)
     }
     int nx = 0, ny = 0;
     hb->dims(&nx, &ny);
-    const double hdr[8] = { kStateMagic, 1.0, double(hb->cfg.rheology), double(hb->cfg.dgadv), double(hb->cfg.cgdegree), double(nx),
-        double(ny), double(fields.size()) };
-    std::copy(hdr, hdr + 8, host);
-    size_t off = 8;
+    const double hdr[kStateHeader] = { kStateMagic, kStateVersion, double(hb->cfg.rheology), double(hb->cfg.dgadv),
+        double(hb->cfg.cgdegree), double(nx), double(ny), double(fields.size()), double(hb->cfg.global_nx > 0 ? hb->cfg.box_x0 : 0),
+        double(hb->cfg.global_nx > 0 ? hb->cfg.box_y0 : 0) };
+    std::copy(hdr, hdr + kStateHeader, host);
+    size_t off = kStateHeader;
     for (size_t i = 0; i < fields.size(); ++i) {
         host[off++] = double(len[i]);
         size_t got = 0;
@@ -1802,18 +1836,27 @@ int nsdg_set_state(nsdg_handle h, const double* host, size_t count)
     const auto fields = stateFields(hb->cfg);
     int nx = 0, ny = 0;
     hb->dims(&nx, &ny);
-    if (!host || count < 8 || host[0] != kStateMagic || host[1] != 1.0)
+    if (!host || count < kStateHeader || host[0] != kStateMagic || host[1] != kStateVersion)
         throw std::runtime_error("nsdg_set_state: not a state buffer of this library version");
-    if (int(host[2]) != hb->cfg.rheology || int(host[3]) != hb->cfg.dgadv || int(host[4]) != hb->cfg.cgdegree || int(host[5]) != nx
-        || int(host[6]) != ny || size_t(host[7]) != fields.size())
-        throw std::runtime_error("nsdg_set_state: state was written for a different configuration or mesh");
-    size_t off = 8;
+    size_t hv[8] = {};
+    for (int i = 0; i < 8; ++i)
+        if (!stateInt(host[2 + i], 1e9, &hv[i]))
+            throw std::runtime_error("nsdg_set_state: corrupted header");
+    const size_t bx = hb->cfg.global_nx > 0 ? size_t(hb->cfg.box_x0) : 0, by = hb->cfg.global_nx > 0 ? size_t(hb->cfg.box_y0) : 0;
+    if (hv[0] != size_t(hb->cfg.rheology) || hv[1] != size_t(hb->cfg.dgadv) || hv[2] != size_t(hb->cfg.cgdegree) || hv[3] != size_t(nx)
+        || hv[4] != size_t(ny) || hv[5] != fields.size() || hv[6] != bx || hv[7] != by)
+        throw std::runtime_error("nsdg_set_state: state was written for a different configuration, mesh or partition box");
+    size_t off = kStateHeader;
     for (const std::string& f : fields) {
         if (off >= count)
             throw std::runtime_error("nsdg_set_state: truncated buffer");
-        const size_t len = size_t(host[off++]);
-        if (off + len > count)
-            throw std::runtime_error("nsdg_set_state: truncated buffer");
+        size_t len = 0, expect = 0;
+        const double lenField = host[off++];
+        if (!stateInt(lenField, double(count - off), &len)) // finite, integral, and off + len <= count without wrapping
+            throw std::runtime_error("nsdg_set_state: corrupted or truncated buffer (field " + f + ")");
+        hb->getInternal(f, nullptr, 0, &expect);
+        if (len != expect)
+            throw std::runtime_error("nsdg_set_state: field " + f + " has the wrong length for this mesh");
         hb->setInternal(f, host + off, len);
         off += len;
     }

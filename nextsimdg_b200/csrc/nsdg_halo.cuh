@@ -41,6 +41,17 @@ __device__ __forceinline__ unsigned ldAcquireSys(const unsigned* p)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+//! how long a box waits for a neighbour's message before it gives up and raises the handle's halo error (the host
+//! reports it after the next stream synchronisation: Handle::checkHaloError).  Long enough for first-launch skew
+//! between ranks (module load, graph instantiation), short enough not to look like a hung GPU.
+constexpr unsigned long long kHaloTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+
 //! one direction of one exchange: which lines of which fields go where
 struct HaloLineDesc {
     int nFields; //!< number of arrays (node fields: 2; DG field: ncomp planes)
@@ -114,10 +125,10 @@ __global__ void __launch_bounds__(256) halo_unpack_kernel(const __grid_constant_
     __shared__ int ok;
     if (threadIdx.x == 0) {
         ok = 1;
-        const long long t0 = clock64();
+        const unsigned long long t0 = globalTimerNs();
         // flags only ever grow: >= tolerates a neighbour that is already one phase ahead
         while (int(ldAcquireSys(a.myFlag[side]) - a.epoch[side]) < 0) {
-            if (clock64() - t0 > 20000000000LL) { // ~10 s: the neighbour died; do not hang the GPU
+            if (globalTimerNs() - t0 > kHaloTimeoutNs) { // wall clock, independent of the SM clock: the neighbour died; do not hang the GPU
                 ok = 0;
                 *a.errorFlag = 1;
                 break;

@@ -194,3 +194,76 @@ def make_weak_scaling_box(cls, n, rheo, rank, world, local_rank, dist, nsteps=10
     dyn.partition = part
     dyn.owned_elements = lambda: part.nx * part.ny
     return dyn, ms, forcing
+
+
+# -- self-consistency probe: partitioned boxes against the same problem on one GPU ------------------------------------
+PROBE_CASES = (("mevp", "uniform"), ("mevp", "distorted"), ("mevp", "spherical"), ("bbm", "uniform"), ("bbm", "distorted"))
+
+
+def probe_inputs(kind: str):
+    """Seeded small problems for the partition probe: a 96 x 64 para24x30-shaped box (uniform / distorted, irregular land
+    mask) or the 64 x 64 TOPAZ-like spherical grid (run/init_topaz128x128.py:106-121 at half resolution)."""
+    from . import synthetic
+
+    if kind == "spherical":
+        ms = synthetic.topaz_like_spherical(64)
+        return ms, synthetic.smooth_forcing(64, 64)
+    ms = synthetic.para_state(96, 64, dxy=8000.0, distort=0.04 if kind == "distorted" else 0.0, irregular_mask=True)
+    return ms, synthetic.smooth_forcing(96, 64)
+
+
+def _dg0(a):
+    a = np.asarray(a, dtype=np.float64)
+    return np.ascontiguousarray(a[..., 0] if a.ndim == 3 else a)
+
+
+def partition_probe(rheo: str, kind: str, rank: int, world: int, device: int, all_gather, nsteps: int = 40, nts: int = 2):
+    """Run one probe case as `world` boxes with halo exchange AND (on rank 0) as a single domain on the same GPU.
+
+    Returns on rank 0 {field: norm-wise relative error over ice elements of the gathered owned boxes against the
+    single-domain result} plus "single" = the single-domain exports (so that a caller can check THEM against an
+    independent checker); None on the other ranks.  The reference has no distributed dynamics: equality
+    with the single-domain result is what multi-GPU parity means here."""
+    from .dynamics import CUDABBMDynamics, CUDAMEVPDynamics
+
+    # BBM is an explicit elastic scheme: keep c_elastic * dt_sub / dx well below 1, otherwise rounding noise is amplified
+    # and no two summation orders agree (DESIGN.md, 'conditioning'); on the sphere its damage time scale blows up within
+    # a few subcycles in the reference itself (BBMStressUpdateStep.hpp:158), hence mEVP only there
+    dt = 120.0 if rheo == "bbm" else 600.0
+    ms, forc = probe_inputs(kind)
+    gny, gnx = np.asarray(ms["mask"]).shape
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+
+    def drive(dyn, state, window):
+        dyn.shared = {"hice": np.ascontiguousarray(_dg0(state["hice"])[window]), "cice": np.ascontiguousarray(_dg0(state["cice"])[window]),
+                      **{k: np.ascontiguousarray(v[window]) for k, v in forc.items()}}
+        for _ in range(nts):
+            dyn.update(dt)
+        out = {"u": dyn.uice, "v": dyn.vice, "hice": dyn.shared["hice"], "cice": dyn.shared["cice"], "taux": dyn.taux, "tauy": dyn.tauy}
+        if rheo == "bbm":
+            out["damage"] = dyn.damage
+        return out
+
+    part = Partition.strong(rank, world, gnx, gny)
+    dyn = cls(nsteps=nsteps, device=device, partition=part)
+    dyn.setData(part.crop_state(ms))
+    connect_halos(dyn, part, all_gather)
+    ow = part.owned_in_local()
+    mine = {k: np.ascontiguousarray(v[ow]) for k, v in drive(dyn, ms, part.local_window()).items()}
+    everyone = all_gather((part.owned_window(), mine))
+    dyn.close()
+    if rank != 0:
+        return None
+    ref = cls(nsteps=nsteps, device=device)
+    ref.setData(ms)
+    full = {k: v.copy() for k, v in drive(ref, ms, (slice(None), slice(None))).items()}
+    ref.close()
+    ice = np.asarray(ms["mask"]).astype(bool)
+    errs = {}
+    for name, whole in full.items():
+        got = np.full_like(whole, np.nan)
+        for win, fields in everyone:
+            got[win] = fields[name]
+        errs[name] = float(np.abs(got - whole)[ice].max() / max(np.abs(whole[ice]).max(), 1e-300))  # NaN if a box is missing
+    errs["single"] = full
+    return errs

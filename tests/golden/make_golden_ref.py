@@ -26,7 +26,7 @@ def main():
         out[f"{name}/digest"] = np.frombuffer(bytes.fromhex(refcases.inputs_digest(ms, forcings)), dtype=np.uint8)
         for rheo, nsteps in rheos.items():
             d = oracle.OracleDynamics(rheo, dg, cg, nsteps, impl="reference")
-            res = refcases.run_case(d, ms, forcings, dt)
+            res = refcases.run_case(d, ms, forcings, dt, keep=refcases.KEEP.get(name, "all"))
             for k, v in res.items():
                 out[f"{name}/{rheo}/{k}"] = v
             print(name, rheo, {k: float(np.abs(v).max()) for k, v in res.items() if k in ("uice", "hice")})

@@ -15,6 +15,11 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref
 # internals that carry over to the next step
 EXPORTS = ("uice", "vice", "taux", "tauy", "hice", "cice")
 INTERNALS = ("cg_u", "cg_v", "s11", "s12", "s22")
+# full-DG exports: DynamicsKernel::getDGData (DynamicsKernel.hpp:134-156), the path BBMDynamics::getState uses (BBMDynamics.cpp:104-117)
+DG_EXPORTS = ("hice", "cice", "damage")
+# how much of a case's outputs the golden file keeps (the 128 x 128 cases would otherwise add ~20 MB of fixtures):
+#   "all" = exports + full-DG exports + CG velocity + stresses; "cg" = exports + CG velocity; "exports" = module exports only
+KEEP = {"topaz128_spherical": "cg", "topaz128_spherical_nsteps120": "exports", "topaz128_spherical_nsteps200": "exports"}
 
 
 def _trim(ms, dg):
@@ -45,6 +50,15 @@ def cases():
         "dg1cg2_distorted_land": (_trim(S.para_state(22, 18, distort=0.04, irregular_mask=True), 3), [S.smooth_forcing(22, 18)], 900.0,
                                   (3, 2), {"mevp": 30, "bbm": 30}),
         "dg0cg2_uniform": (_trim(S.para_state(20, 16), 1), [S.smooth_forcing(20, 16)], 900.0, (1, 2), {"mevp": 30}),
+        # BASELINE.json configs[3]: the TOPAZ-like 128 x 128 spherical grid (run/init_topaz128x128.py:106-121,152-154: polar
+        # azimuthal-equidistant vertices, X, Y = linspace(-20, 20, 129) degrees), land south of 72 N, dt = 600 s, with the
+        # reference's 100 subcycles and the "100+" variants of SURVEY 8(d).  mEVP only: the reference's BBM is unstable on
+        # spherical meshes (damage time scale from smesh.h(i) in radians, BBMStressUpdateStep.hpp:158; |u| reaches 11 m/s
+        # after two subcycles at this resolution), where no two summation orders agree -- the 32 x 32 "spherical" case above
+        # covers the spherical BBM code path while it is still finite
+        "topaz128_spherical": (S.topaz_like_spherical(128), [S.smooth_forcing(128, 128)], 600.0, (6, 2), {"mevp": 100}),
+        "topaz128_spherical_nsteps120": (S.topaz_like_spherical(128), [S.smooth_forcing(128, 128)], 600.0, (6, 2), {"mevp": 120}),
+        "topaz128_spherical_nsteps200": (S.topaz_like_spherical(128), [S.smooth_forcing(128, 128)], 600.0, (6, 2), {"mevp": 200}),
     }
     return c
 
@@ -60,7 +74,7 @@ def inputs_digest(ms, forcings):
     return h.hexdigest()
 
 
-def run_case(d, ms, forcings, dt):
+def run_case(d, ms, forcings, dt, keep="all"):
     """Drive a dynamics object (CUDA module mirror or oracle.OracleDynamics) the way the model does."""
     ny, nx = np.asarray(ms["mask"]).shape
     d.setData(ms)
@@ -76,7 +90,12 @@ def run_case(d, ms, forcings, dt):
         # FreeDriftDynamics::update never exports the ice-ocean stress (FreeDriftDynamics.hpp:39-58)
         out.pop("taux"), out.pop("tauy")
     for n in INTERNALS:
-        out[n] = d.internal(n)
+        if keep == "all" or (keep == "cg" and n in ("cg_u", "cg_v")):
+            out[n] = d.internal(n)
+    if keep == "all" and d.dgadv > 1:
+        for n in DG_EXPORTS:
+            if n != "damage" or "damage" in out:
+                out[n + "_dg"] = d.getDGData(n)
     return {k: np.array(v, dtype=np.float64, copy=True) for k, v in out.items() if v is not None}
 
 

@@ -273,6 +273,17 @@ def test_restart_state_resumes_bitwise(rheo):
         other = CUDAMEVPDynamics(nsteps=1) if rheo == "bbm" else CUDABBMDynamics(nsteps=1)
         other.setData(ms)
         other.set_state(state)
+    # corrupted / truncated buffers are rejected, never read out of bounds (round-1 review): NaN, negative and huge
+    # field lengths, a wrong length for this mesh, a foreign mesh size in the header, a cut-off tail
+    for mutate in (lambda s: s.__setitem__(10, np.nan), lambda s: s.__setitem__(10, -5.0), lambda s: s.__setitem__(10, 1e300),
+                   lambda s: s.__setitem__(10, s[10] - 6.0), lambda s: s.__setitem__(5, s[5] + 1.0), lambda s: s.__setitem__(8, 3.0)):
+        bad = state.copy()
+        mutate(bad)
+        with pytest.raises(NsdgError):
+            c.set_state(bad)
+    with pytest.raises(NsdgError):
+        c.set_state(state[: state.size // 2].copy())
+    c.set_state(state)  # and the intact one is still accepted afterwards
 
 
 @pytest.mark.parametrize("rheo", ["mevp", "bbm"])
@@ -350,6 +361,53 @@ def test_interleaved_handles_with_different_uniform_meshes():
         assert np.array_equal(d.uice, u) and np.array_equal(d.vice, v)
         assert np.abs(u).max() > 0
         d.close()
+
+
+def test_interleaved_handles_of_both_builds_share_the_constant_operator_symbol(monkeypatch):
+    """Regression (round-1 review): the owner table of the per-device __constant__ operator set was a static member of
+    the class TEMPLATE, one table per (CG, DG) build, while both builds upload into the same symbol.  A DG1/CG1 handle, a
+    DG2/CG2 handle on the generic kernel and a DG2/CG2 handle on the fast kernel (which must not touch the symbol at all)
+    are stepped alternately and must reproduce their solo runs bit for bit."""
+    import os
+
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, dt = 32, 120.0
+    kinds = [("dg1cg1", 512000.0), ("dg2cg2_generic", 300000.0), ("dg2cg2_fast", 200000.0)]
+
+    def make(kind, L):
+        ms = synthetic.benchmark_box(n, L=L)
+        if kind == "dg1cg1":
+            d = CUDAMEVPDynamics(dgadv=3, cgdegree=1, nsteps=30)
+        else:
+            d = CUDAMEVPDynamics(nsteps=30)
+        if kind == "dg2cg2_generic":  # testing knob read by nsdg_set_mesh: generic strip kernel on the uniform operator set
+            monkeypatch.setenv("NSDG_NO_FAST_UNIFORM", "1")
+        d.setData(ms)
+        monkeypatch.delenv("NSDG_NO_FAST_UNIFORM", raising=False)
+        d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
+        return d
+
+    def advance(d, L, k):
+        d.shared.update({a: b.copy() for a, b in synthetic.benchmark_forcing(n, k * dt, L=L).items()})
+        d.update(dt)
+
+    solo = []
+    for kind, L in kinds:
+        d = make(kind, L)
+        for k in range(2):
+            advance(d, L, k)
+        solo.append((d.uice.copy(), d.vice.copy()))
+        d.close()
+    both = [make(kind, L) for kind, L in kinds]
+    for k in range(2):
+        for d, (kind, L) in zip(both, kinds):
+            advance(d, L, k)
+    for d, (u, v), (kind, _) in zip(both, solo, kinds):
+        assert np.array_equal(d.uice, u) and np.array_equal(d.vice, v), kind
+        assert np.abs(u).max() > 0
+        d.close()
+    assert "NSDG_NO_FAST_UNIFORM" not in os.environ
 
 
 def test_handles_on_two_devices_in_one_process():

@@ -52,7 +52,7 @@ def test_cuda_reproduces_reference_golden_outputs(case, rheo, golden, table, cud
     ms, forcings, dt, (dg, cg), rheos = table[case]
     assert bytes(golden[f"{case}/digest"]).hex() == refcases.inputs_digest(ms, forcings)
     d = _module(rheo, dg, cg, rheos[rheo])
-    got = refcases.run_case(d, ms, forcings, dt)
+    got = refcases.run_case(d, ms, forcings, dt, keep=refcases.KEEP.get(case, "all"))
     d.close()
     want = {k.split("/")[2]: golden[k] for k in golden.files if k.startswith(f"{case}/{rheo}/")}
     worst, bad = refcases.compare(got, want, ms["mask"], TOL_STEP, TOL_STRESS)
@@ -86,3 +86,97 @@ def test_cuda_matches_live_reference_over_five_steps(rheo, cuda_lib):
         errs.append(max(e))
     print("drift vs reference", rheo, errs)
     assert max(errs) < 10 * TOL_STEP
+
+
+@pytest.mark.parametrize("case,rheo", [(c, r) for c, r in _params() if refcases.cases()[c][3] == (6, 2) and r != "freedrift"][:6])
+def test_getDGData_matches_reference_golden(case, rheo, golden, table, cuda_lib):
+    """nsdg_get_field(..., ncomp = dgadv) = DynamicsKernel::getDGData (DynamicsKernel.hpp:134-156), the full-DG export
+    BBMDynamics::getState makes (BBMDynamics.cpp:104-117): all six components of hice, cice (and damage) after update()."""
+    ms, forcings, dt, (dg, cg), rheos = table[case]
+    keys = [k for k in golden.files if k.startswith(f"{case}/{rheo}/") and k.endswith("_dg")]
+    if not keys:
+        pytest.skip("the golden file keeps module exports only for this case")
+    d = _module(rheo, dg, cg, rheos[rheo])
+    got = refcases.run_case(d, ms, forcings, dt)
+    st = d.getState() if rheo == "bbm" else None
+    d.close()
+    ice = np.asarray(ms["mask"]).astype(bool).ravel()
+    for k in keys:
+        name = k.split("/")[2]
+        g, w = got[name].reshape(ice.size, -1)[ice], golden[k].reshape(ice.size, -1)[ice]
+        assert g.shape[1] == dg
+        # component-wise: the higher moments are orders of magnitude smaller than the mean and must be right on their own scale
+        for c in range(dg):
+            scale = max(np.abs(w[:, c]).max(), 1e-12 * np.abs(w[:, 0]).max(), 1e-300)
+            assert np.abs(g[:, c] - w[:, c]).max() / scale < 1e-8, (name, c)
+        assert np.abs(g - w).max() / np.abs(w).max() < TOL_STEP, name
+    if st is not None:  # the module's getState hands out exactly these arrays
+        assert np.array_equal(st["hice"].reshape(-1), got["hice_dg"].reshape(-1))
+        assert np.array_equal(st["damage"].reshape(-1), got["damage_dg"].reshape(-1))
+
+
+@pytest.mark.parametrize("nsteps", [100, 120, 200])
+def test_topaz128_spherical_against_live_reference(nsteps, cuda_lib):
+    """BASELINE.json configs[3] at full size: the TOPAZ-like 128 x 128 spherical grid with land, 100 / 120 / 200 subcycles,
+    two updates, against the reference's own kernels run on the box's host cores."""
+    import oracle
+    from nextsimdg_b200 import synthetic
+
+    if not oracle.have_ref(2):
+        pytest.skip("oracle/_ref/libnsdg_ref_cg2.so did not travel with the snapshot")
+    oracle.load_ref(2).nso_set_threads(1)  # ssh != 0: quirk Q15
+    ms, f = synthetic.topaz_like_spherical(128), synthetic.smooth_forcing(128, 128)
+    gpu, ref = _module("mevp", 6, 2, nsteps), oracle.OracleDynamics("mevp", 6, 2, nsteps, impl="reference")
+    got = refcases.run_case(gpu, ms, [f, f], 600.0, keep="cg")
+    want = refcases.run_case(ref, ms, [f, f], 600.0, keep="cg")
+    gpu.close()
+    worst, bad = refcases.compare(got, want, ms["mask"], TOL_STEP)
+    print("topaz128", nsteps, {k: f"{v:.1e}" for k, v in worst.items()})
+    assert not bad, bad
+    assert np.abs(want["uice"]).max() > 1e-3
+
+
+def test_drift_over_100_steps_against_live_reference(cuda_lib):
+    """SURVEY 8(c) tolerance plan: 'drift over N = 100 steps reported'.  100 updates of the 32 x 32 cyclone box with the
+    moving forcing, mEVP and BBM, against the reference's own kernels; the record goes to gpurun_out/drift100.json (copied
+    to profiles/ by hand) and the drift must stay bounded."""
+    import json
+    import os
+
+    import oracle
+    from nextsimdg_b200 import synthetic
+
+    if not oracle.have_ref(2):
+        pytest.skip("oracle/_ref/libnsdg_ref_cg2.so did not travel with the snapshot")
+    L = oracle.load_ref(2)
+    L.nso_set_threads(max(1, min(16, L.nso_max_threads())))  # ssh = 0 here: the Q15 race is harmless
+    n, dt, record = 32, 120.0, {}
+    for rheo in ("mevp", "bbm"):
+        ms = synthetic.benchmark_box(n)
+        gpu, ref = _module(rheo, 6, 2, 100), oracle.OracleDynamics(rheo, 6, 2, 100, impl="reference")
+        for d in (gpu, ref):
+            d.setData(ms)
+            d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
+        ice = ms["mask"].astype(bool)
+        errs = []
+        for k in range(100):
+            f = synthetic.benchmark_forcing(n, k * dt)
+            for d in (gpu, ref):
+                d.shared.update({a: b.copy() for a, b in f.items()})
+                d.update(dt)
+            pairs = [(gpu.uice, ref.uice), (gpu.vice, ref.vice), (gpu.shared["hice"], ref.shared["hice"]), (gpu.shared["cice"], ref.shared["cice"])]
+            if rheo == "bbm":
+                pairs.append((gpu.damage, ref.damage))
+            errs.append(max(float(np.abs(a - b)[ice].max() / np.abs(b[ice]).max()) for a, b in pairs))
+        gpu.close()
+        record[rheo] = {"grid": f"{n}x{n} benchmark box", "steps": 100, "nsteps": 100, "dt": dt, "max_rel_err_per_step": errs,
+                        "after_1": errs[0], "after_10": errs[9], "after_100": errs[-1], "max": max(errs)}
+        print("drift100", rheo, f"1: {errs[0]:.2e}  10: {errs[9]:.2e}  100: {errs[-1]:.2e}  max: {max(errs):.2e}")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump(record, open(os.path.join(out, "drift100.json"), "w"), indent=1)
+    except OSError:
+        pass
+    for rheo in record:
+        assert record[rheo]["max"] < 1e-7, (rheo, record[rheo]["max"])  # bounded: no growth beyond ~1e3 x the per-step tolerance
