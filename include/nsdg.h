@@ -124,6 +124,31 @@ int nsdg_step(nsdg_handle h, double dt_seconds);
  * and getDGData(name) (ncomp == dgadv; DynamicsKernel.hpp:134-156). */
 int nsdg_get_field(nsdg_handle h, int field, double* host, int ncomp);
 
+/* Replaces: assigning ParametricMesh::dirichlet[4] / ParametricMesh::periodic (dynamics/src/include/ParametricMesh.hpp:76-79),
+ * which the reference fills from a version-2.0 .smesh file (dynamics/src/ParametricMesh.cpp:79-178) or, in its advection
+ * tests, by hand (dynamics/test/Advection_test.cpp:222-240, AdvectionPeriodicBC_test.cpp:228-249).  IDynamics itself never
+ * sets periodic edges (DynamicsKernel.hpp:54).
+ *   dirichlet[e], ndirichlet[e] : element list of edge e (0 bottom, 1 right, 2 top, 3 left); a NULL list keeps the one
+ *                                 derived from the mask by nsdg_set_mesh; dirichlet == NULL keeps all four
+ *   periodic                    : all segments back to back, 4 longs per entry {type, c1, c2, edge}: type 0 = X-edge
+ *                                 (c1 below, c2 above), 1 = Y-edge (c1 left of the edge, c2 right of it), edge = index of
+ *                                 the edge whose normal velocity the flux uses (DGTransport.cpp:466-481)
+ *   periodic_segment_sizes      : entries per segment (VectorManipulations::CGAveragePeriodic works segment by segment)
+ * Effect: the advection applies upwind fluxes across the periodic edges (DGTransport.cpp:466-481) and prepareIteration
+ * averages cgH, cgA across the seam (CGDynamicsKernel.cpp:264-266).  Not available on partition boxes. */
+int nsdg_set_boundaries(nsdg_handle h, const long* const* dirichlet, const size_t* ndirichlet, const long* periodic,
+    const size_t* periodic_segment_sizes, size_t nsegments);
+
+/* Replaces: the time loop of a DGTransport object used on its own -- nsteps x { DGTransport::reinitnormalvelocity
+ * (dynamics/src/DGTransport.cpp:158-252); DGTransport::step with settimesteppingscheme("rk1" | "rk2" | "rk3")
+ * (DGTransport.cpp:514-566); LimitMax / LimitMin (dynamics/src/include/dgLimit.hpp:16-84) } -- on one advected DG field
+ * of the handle (NSDG_HICE, NSDG_CICE, NSDG_DAMAGE), with the DG velocity currently in the transport object
+ * (nsdg_set_internal "velx" / "vely" = DGTransport::GetVx / GetVy; or the one the last nsdg_step projected).
+ *   rk_order   : 1, 2, 3
+ *   limit_mode : bit 0 = LimitMax(maxv), bit 1 = LimitMin(minv) after every step; 0 = none */
+int nsdg_advect_field(nsdg_handle h, int field, double dt_seconds, int rk_order, int nsteps, int limit_mode, double maxv,
+    double minv);
+
 /* Device-resident synthetic forcing: evaluates the reference's benchmark atmosphere and ocean
  * (physics/src/modules/AtmosphereBoundaryModule/BenchmarkAtmosphere.cpp:38-74: moving cyclone;
  *  physics/src/modules/OceanBoundaryModule/BenchmarkOcean.cpp:27-36: steady gyre, ssh = 0; cell-corner

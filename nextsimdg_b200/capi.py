@@ -53,6 +53,8 @@ SIGNATURES = {
     "nsdg_set_field": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "nsdg_step": (c_int, [c_void_p, c_double]),
     "nsdg_get_field": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "nsdg_set_boundaries": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "nsdg_advect_field": (c_int, [c_void_p, c_int, c_double, c_int, c_int, c_int, c_double, c_double]),
     "nsdg_set_benchmark_forcing": (c_int, [c_void_p, c_double, c_double, c_double]),
     "nsdg_update": (c_int, [c_void_p, POINTER(UpdateIO), c_double]),
     "nsdg_get_landmask": (c_int, [c_void_p, c_void_p]),

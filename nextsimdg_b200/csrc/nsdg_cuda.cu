@@ -13,6 +13,7 @@
  * There is no CPU fallback: without a usable CUDA device every entry point fails.
  */
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +57,8 @@ public:
     virtual void benchmarkForcing(double elapsed, double Lx, double Ly) = 0;
     virtual void dims(int* nx, int* ny) = 0;
     virtual void healDamage(double dt, double td, const double* deltaCi) = 0;
+    virtual void setBoundaries(const long* const* dir, const size_t* ndir, const long* per, const size_t* segSizes, size_t nseg) = 0;
+    virtual void advectField(int field, double dt, int order, int nsteps, int limitMode, double maxv, double minv) = 0;
     virtual void haloExport(unsigned char* handle) = 0;
     virtual void haloConnect(int side, const unsigned char* handle) = 0;
     virtual void haloReady() = 0;
@@ -92,8 +95,12 @@ public:
     DevBuf<uint8_t> d_landmask, d_dirmask, d_nodemask;
     // element fields
     DevBuf<double> hice, cice, damage, ssh, s11, s12, s22, gaussA, gaussB, helem;
-    DevBuf<double> velx, vely, tmp1, tmp2, nvX, nvY; // DGA transport
-    DevBuf<double> velxS, velyS, tmp1S, tmp2S, nvXS, nvYS; // DGs transport (BBM)
+    DevBuf<double> velx, vely, tmp1, tmp2, tmp3, nvX, nvY; // DGA transport (tmp3: third field of a pass, or rk3)
+    DevBuf<double> velxS, velyS, tmp1S, tmp2S, tmp3S, nvXS, nvYS; // DGs transport (BBM)
+    DevBuf<int> perNbr, perEdge; //!< periodic edges (nsdg_set_boundaries): [4][Npad] neighbour element / edge index, else empty
+    std::vector<std::array<long, 4>> periodic; //!< ParametricMesh::periodic, flattened: {type, c1, c2, edge}
+    std::vector<std::pair<size_t, size_t>> periodicSegs; //!< (first entry, count) of every periodic segment
+    DevBuf<long> d_periodic; //!< the flattened list on the device (CGAveragePeriodic)
     DevBuf<double> scratchDG; // DGA planes scratch (set/get via DG2CG / CG2DG)
     // operators
     DevBuf<double> tAdvX, tAdvY, tiMass, sAdvX, sAdvY, siMass;
@@ -283,6 +290,11 @@ public:
         for (size_t i = 0; i < N; ++i) // landmaskFromModelArray, ParametricMesh.cpp:217-223 (quirk Q10)
             landmask[i] = (mask[i] == 1.) ? 1 : 0;
         buildDirichlet();
+        periodic.clear();
+        periodicSegs.clear();
+        perNbr.release();
+        perEdge.release();
+        d_periodic.release();
         uniform = detectUniform();
 
         vx.alloc(nnodes);
@@ -312,8 +324,9 @@ public:
         nvX.alloc(EDA * pX);
         nvY.alloc(EDA * pY);
         if (bbm) {
-            for (auto* f : { &velxS, &velyS, &tmp1S, &tmp2S })
+            for (auto* f : { &velxS, &velyS, &tmp1S, &tmp2S, &tmp3S })
                 f->alloc(size_t(DGs) * Npad);
+            tmp3.alloc(size_t(DGA) * Npad);
             nvXS.alloc(EDS * pX);
             nvYS.alloc(EDS * pY);
         }
@@ -808,35 +821,218 @@ public:
     template <int DG>
     void prepareAdvection(const double* cgU, const double* cgV, TransportOpPtrs op, double* vxd, double* vyd, double* nX, double* nY)
     {
-        const size_t pX = alignUp(size_t(g.nx) * (g.ny + 1), 32), pY = alignUp(size_t(g.nx + 1) * g.ny, 32);
         cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgU, op, vxd);
         cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgV, op, vyd);
-        const size_t nEdges = size_t(g.nx) * (g.ny + 1) + size_t(g.nx + 1) * g.ny;
-        normalvel_kernel<DG><<<blocksFor(nEdges), 128, 0, stream>>>(g, vx, vy, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY);
-        launches += 3;
+        launches += 2;
+        normalVelocity<DG>(vxd, vyd, nX, nY);
     }
-    //! DGTransport::step_rk2, DGTransport.cpp:521-532
+    template <int DG> void launchStage(const TransportStageArgs& a, int nf)
+    {
+        const dim3 grid((g.nx + 127) / 128, g.ny);
+        if (nf == 1)
+            transport_stage_kernel<DG, 1><<<grid, 128, 0, stream>>>(a);
+        else if (nf == 2)
+            transport_stage_kernel<DG, 2><<<grid, 128, 0, stream>>>(a);
+        else
+            transport_stage_kernel<DG, 3><<<grid, 128, 0, stream>>>(a);
+        launches += 1;
+    }
+    struct LimitSpec {
+        int mode = 0; //!< bit 1: LimitMax(maxv), bit 2: LimitMin(minv)
+        double maxv = 0, minv = 0;
+    };
+    /*
+     * DGTransport::step (DGTransport.cpp:514-566) for up to three fields that share the transport object (operators,
+     * velocities, edge normal velocities): one fused kernel per Runge-Kutta stage (nsdg_transport.cuh), the limiters of
+     * DynamicsKernel::advectionAndLimits (DynamicsKernel.hpp:160-172) in the last one.  order = 1, 2, 3 (rk1, rk2, rk3);
+     * the module path uses rk2 (DynamicsKernel.hpp:61).  tmp[s][f]: stage buffers (order - 1 ... at least `order` of them
+     * for rk3, one for rk1 / rk2).  Partitioned boxes exchange the ring elements of every stage value.
+     */
     template <int DG>
-    void transportStep(double dt, TransportOpPtrs op, const double* vxd, const double* vyd, const double* nX, const double* nY,
-        double* phi, double* t1, double* t2)
+    void transportFields(double dt, TransportOpPtrs op, const double* vxd, const double* vyd, const double* nX, const double* nY,
+        int order, int nf, double* const* phi, double* const (*tmp)[kTransportMaxFields], const LimitSpec* lim)
+    {
+        TransportStageArgs a {};
+        a.g = g;
+        a.dt = dt;
+        a.landmask = d_landmask;
+        a.dirmask = d_dirmask;
+        a.velx = vxd;
+        a.vely = vyd;
+        a.nvX = nX;
+        a.nvY = nY;
+        a.pitchX = alignUp(size_t(g.nx) * (g.ny + 1), 32);
+        a.pitchY = alignUp(size_t(g.nx + 1) * g.ny, 32);
+        a.op = op;
+        // parametric fast paths: the cell-term operators come from the geometry planes (DG6 and DG8 share the 3 x 3 Gauss points)
+        a.geo = (fastParamMEVP || fastParamBBM) && !std::getenv("NSDG_NO_FACTORED_TRANSPORT") ? geo.p : nullptr;
+        a.perNbr = perNbr.p;
+        a.perEdge = perEdge.p;
+        auto stage = [&](double* const* in, double* const* base, double* const* out, int epi, double c0, double c1, bool last) {
+            for (int f = 0; f < nf; ++f) {
+                a.in[f] = in[f];
+                a.base[f] = base[f];
+                a.out[f] = out[f];
+                a.limitMode[f] = last ? lim[f].mode : 0;
+                a.maxv[f] = lim[f].maxv;
+                a.minv[f] = lim[f].minv;
+            }
+            a.epi = epi;
+            a.c0 = c0;
+            a.c1 = c1;
+            launchStage<DG>(a, nf);
+            for (int f = 0; f < nf; ++f)
+                exchangePlanes(out[f], DG); // ring elements of the stage value come from their owners
+        };
+        if (order == 1) { // step_rk1: phi += k(phi); the stage cannot run in place (neighbours read phi)
+            stage(phi, phi, tmp[0], 0, 0, 0, true);
+            for (int f = 0; f < nf; ++f)
+                NSDG_CUDA_CHECK(cudaMemcpyAsync(phi[f], tmp[0][f], size_t(DG) * g.Npad * 8, cudaMemcpyDeviceToDevice, stream));
+        } else if (order == 2) { // step_rk2 (Heun): phi1 = phi + k1; phi = phi1 + (k2 - k1) / 2
+            stage(phi, phi, tmp[0], 0, 0, 0, false);
+            stage(tmp[0], phi, phi, 1, 0, 0, true);
+        } else { // step_rk3: tmp1 = phi + k(phi); tmp2 = (tmp1 + k(tmp1)) / 4 + 3 phi / 4; phi = phi / 3 + 2 (tmp2 + k(tmp2)) / 3
+            stage(phi, phi, tmp[0], 0, 0, 0, false);
+            stage(tmp[0], phi, tmp[1], 2, 0.75, 0.25, false);
+            stage(tmp[1], phi, phi, 2, 1.0 / 3.0, 2.0 / 3.0, true);
+        }
+    }
+    //! DGTransport::reinitnormalvelocity (DGTransport.cpp:158-252) from the DG velocity currently in (vxd, vyd)
+    template <int DG> void normalVelocity(const double* vxd, const double* vyd, double* nX, double* nY)
     {
         const size_t pX = alignUp(size_t(g.nx) * (g.ny + 1), 32), pY = alignUp(size_t(g.nx + 1) * g.ny, 32);
-        const size_t n = size_t(DG) * g.Npad;
-        const unsigned nb = blocksFor(g.N);
-        // parametric fast paths: the cell-term operators come from the geometry planes (DG6 and DG8 share the 3 x 3 Gauss points)
-        const double* gp = (fastParamMEVP || fastParamBBM) && !std::getenv("NSDG_NO_FACTORED_TRANSPORT") ? geo.p : nullptr;
-        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, gp, phi, t1);
-        add_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t1);
-        exchangePlanes(phi, DG); // ring elements of the RK stage value come from their owners
-        transport_kernel<DG><<<nb, 128, 0, stream>>>(g, dt, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY, op, gp, phi, t2);
-        heun_kernel<<<blocksFor(n, 256), 256, 0, stream>>>(n, phi, t2, t1);
-        exchangePlanes(phi, DG);
-        launches += 4;
-    }
-    void limit(double* f, int mode, double maxv, double minv)
-    {
-        limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, mode, maxv, minv);
+        const size_t nEdges = size_t(g.nx) * (g.ny + 1) + size_t(g.nx + 1) * g.ny;
+        normalvel_kernel<DG><<<blocksFor(nEdges), 128, 0, stream>>>(g, vx, vy, d_landmask, d_dirmask, vxd, vyd, nX, pX, nY, pY);
         launches += 1;
+    }
+
+    /*
+     * Replace the boundary lists of the mesh: ParametricMesh::dirichlet[4] and ParametricMesh::periodic
+     * (ParametricMesh.hpp:76-79), which the .smesh 2.0 reader fills from a file (ParametricMesh.cpp:79-178) and the
+     * reference's advection tests assign by hand (Advection_test.cpp:222-240, AdvectionPeriodicBC_test.cpp:228-249).
+     * Periodic entries are {type (0: X-edge, bottom/top; 1: Y-edge, left/right), c1 = element left of / below the edge,
+     * c2 = element right of / above it, edge = index of the edge whose normal velocity the flux uses}.
+     */
+    void setBoundaries(const long* const* dir, const size_t* ndir, const long* per, const size_t* segSizes, size_t nseg) override
+    {
+        requireMesh();
+        if (cfg.global_nx > 0)
+            throw std::runtime_error("nsdg_set_boundaries: not available on a partition box (its artificial edges are halo lines)");
+        const long N = g.N, nx = g.nx, ny = g.ny;
+        for (int edge = 0; edge < 4; ++edge) {
+            if (!dir || !dir[edge])
+                continue; // keep the list derived from the mask
+            for (size_t i = 0; i < ndir[edge]; ++i) {
+                const long el = dir[edge][i];
+                if (el < 0 || el >= N)
+                    throw std::runtime_error("nsdg_set_boundaries: Dirichlet element index out of range");
+            }
+            dirichlet[edge].assign(dir[edge], dir[edge] + ndir[edge]);
+        }
+        hdirmask.assign(size_t(N), 0);
+        for (int edge = 0; edge < 4; ++edge)
+            for (long el : dirichlet[edge])
+                hdirmask[size_t(el)] |= uint8_t(1 << edge);
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        NSDG_CUDA_CHECK(cudaMemcpy2D(d_dirmask, g.nxs, hdirmask.data(), nx, nx, ny, cudaMemcpyHostToDevice));
+        legacySync();
+        NSDG_CUDA_CHECK(cudaMemsetAsync(d_nodemask, 0, ncg, stream));
+        nodemask_kernel<CG><<<blocksFor(size_t(N)), 128, 0, stream>>>(g, d_dirmask, d_nodemask);
+        periodic.clear();
+        periodicSegs.clear();
+        perNbr.release();
+        perEdge.release();
+        d_periodic.release();
+        size_t total = 0;
+        for (size_t sgm = 0; sgm < nseg; ++sgm) {
+            periodicSegs.emplace_back(total, segSizes[sgm]);
+            total += segSizes[sgm];
+        }
+        if (total > 0) {
+            if (!per)
+                throw std::runtime_error("nsdg_set_boundaries: periodic list missing");
+            std::vector<int> hn(size_t(4) * g.Npad, -1), he(size_t(4) * g.Npad, 0);
+            auto plane = [&](long el) { return size_t(el / nx) * g.nxs + size_t(el % nx); };
+            for (size_t i = 0; i < total; ++i) {
+                const long type = per[4 * i], c1 = per[4 * i + 1], c2 = per[4 * i + 2], edge = per[4 * i + 3];
+                const long nEdges = type == 0 ? nx * (ny + 1) : (nx + 1) * ny;
+                if ((type != 0 && type != 1) || c1 < 0 || c1 >= N || c2 < 0 || c2 >= N || edge < 0 || edge >= nEdges)
+                    throw std::runtime_error("nsdg_set_boundaries: bad periodic entry (DGTransport.cpp:475-478 aborts likewise)");
+                // the flux is taken where the regular neighbour is missing: c1's top / right side and c2's bottom / left side
+                // must lie on the edge of the domain
+                const bool ok = type == 0 ? (c1 / nx == ny - 1 && c2 / nx == 0) : (c1 % nx == nx - 1 && c2 % nx == 0);
+                if (!ok)
+                    throw std::runtime_error("nsdg_set_boundaries: periodic edges must connect opposite edges of the domain");
+                const int s1 = type == 0 ? NSDG_TOP : NSDG_RIGHT, s2 = type == 0 ? NSDG_BOTTOM : NSDG_LEFT;
+                hn[size_t(s1) * g.Npad + plane(c1)] = int(plane(c2));
+                he[size_t(s1) * g.Npad + plane(c1)] = int(edge);
+                hn[size_t(s2) * g.Npad + plane(c2)] = int(plane(c1));
+                he[size_t(s2) * g.Npad + plane(c2)] = int(edge);
+                periodic.push_back(std::array<long, 4> { type, c1, c2, edge });
+            }
+            perNbr.alloc(hn.size());
+            perEdge.alloc(he.size());
+            d_periodic.alloc(4 * total);
+            NSDG_CUDA_CHECK(cudaMemcpy(perNbr, hn.data(), hn.size() * sizeof(int), cudaMemcpyHostToDevice));
+            NSDG_CUDA_CHECK(cudaMemcpy(perEdge, he.data(), he.size() * sizeof(int), cudaMemcpyHostToDevice));
+            NSDG_CUDA_CHECK(cudaMemcpy(d_periodic, per, 4 * total * sizeof(long), cudaMemcpyHostToDevice));
+            legacySync();
+        }
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    //! VectorManipulations::CGAveragePeriodic (VectorManipulations.hpp:26-65) on a CG field: segments one after the other
+    //! as in the reference; within a segment the node pairs j = 0 .. CG-1 of all entries at once, then the pairs j = CG
+    //! (the pair an entry shares with the next one along the seam has then been averaged already: idempotent)
+    void averagePeriodic(double* v)
+    {
+        for (const auto& sgm : periodicSegs) {
+            if (sgm.second == 0)
+                continue;
+            const long* list = d_periodic.p + 4 * sgm.first;
+            cg_average_periodic_kernel<CG><<<blocksFor(sgm.second * CG), 128, 0, stream>>>(g, list, long(sgm.second), 0, CG, v);
+            cg_average_periodic_kernel<CG><<<blocksFor(sgm.second), 128, 0, stream>>>(g, list, long(sgm.second), CG, 1, v);
+            launches += 2;
+        }
+    }
+    /*
+     * DGTransport::reinitnormalvelocity + DGTransport::step (+ LimitMax / LimitMin) on ONE named DG field, nsteps times,
+     * with the DG velocity currently in the transport object (nsdg_set_internal "velx" / "vely" = DGTransport::GetVx /
+     * GetVy, or the last prepareAdvection): the time loop of the reference's advection tests
+     * (Advection_test.cpp:150-154, AdvectionPeriodicBC_test.cpp:186-192).
+     */
+    void advectField(int field, double dt, int order, int nsteps, int limitMode, double maxv, double minv) override
+    {
+        requireMesh();
+        if (order < 1 || order > 3)
+            throw std::runtime_error("nsdg_advect_field: the time stepping scheme must be 1 (rk1), 2 (rk2) or 3 (rk3) (DGTransport.cpp:553-565 aborts otherwise)");
+        if (nsteps < 0)
+            throw std::runtime_error("nsdg_advect_field: nsteps must not be negative");
+        double* f = field == NSDG_HICE ? hice.p : field == NSDG_CICE ? cice.p : (field == NSDG_DAMAGE ? damage.p : nullptr);
+        if (!f)
+            throw std::runtime_error("nsdg_advect_field: the field must be one of the advected DG fields of this handle (hice, cice, damage)");
+        launches = 0;
+        double* phi[kTransportMaxFields] = { f, nullptr, nullptr };
+        double* const tmp[2][kTransportMaxFields] = { { tmp1, nullptr, nullptr }, { tmp2, nullptr, nullptr } };
+        const LimitSpec lim[kTransportMaxFields] = { { limitMode, maxv, minv }, {}, {} };
+        for (int i = 0; i < nsteps; ++i) {
+            normalVelocity<DGA>(velx, vely, nvX, nvY);
+            transportFields<DGA>(dt, topA, velx, vely, nvX, nvY, order, 1, phi, tmp, lim);
+        }
+        NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        checkHaloError();
+        timing.kernel_launches = launches;
+    }
+
+    //! DynamicsKernel::advectionAndLimits (DynamicsKernel.hpp:160-172): cice and hice (BBM: and the damage,
+    //! BrittleCGDynamicsKernel.hpp:103-106) with the DGadvection transport object, in ONE pass per Runge-Kutta stage --
+    //! the fields are independent of each other and share operators and velocities -- with their limiters:
+    //! cice in [0, 1], hice >= 0, damage in [1e-12, 1]
+    void advectTracers(double dt, bool withDamage)
+    {
+        double* phi[kTransportMaxFields] = { cice, hice, damage };
+        double* const tmp[1][kTransportMaxFields] = { { tmp1, tmp2, tmp3 } };
+        const LimitSpec lim[kTransportMaxFields] = { { 3, 1.0, 0.0 }, { 2, 0.0, 0.0 }, { 3, 1.0, 1e-12 } };
+        transportFields<DGA>(dt, topA, velx, vely, nvX, nvY, 2, withDamage ? 3 : 2, phi, tmp, lim);
     }
 
     // ------------------------------------------------------------------------------------
@@ -847,6 +1043,18 @@ public:
         const unsigned nb = blocksFor(size_t(g.cgnx) * g.cgny);
         dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, hice, cgH, 1.e-4, INFINITY);
         dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, cice, cgA, 1.e-4, 1.0);
+        if (!periodicSegs.empty()) {
+            // CGDynamicsKernel.cpp:264-266 averages across the seam BEFORE the clamps of :272-275, which dg2cg_kernel fuses:
+            // the clamps are monotone and the seam average of two clamped values is again inside the clamp range, but it is
+            // not the clamp of the average -- redo both in the reference's order
+            dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, hice, cgH, -INFINITY, INFINITY);
+            dg2cg_kernel<CG, DGA><<<nb, 128, 0, stream>>>(g, cice, cgA, -INFINITY, INFINITY);
+            averagePeriodic(cgH);
+            averagePeriodic(cgA);
+            clamp_kernel<<<blocksFor(ncg, 256), 256, 0, stream>>>(ncg, cgH, 1.e-4, INFINITY);
+            clamp_kernel<<<blocksFor(ncg, 256), 256, 0, stream>>>(ncg, cgA, 1.e-4, 1.0);
+            launches += 4;
+        }
         // ComputeGradientOfSeaSurfaceHeight
         GridDims g1 = g;
         g1.CG = 1;
@@ -1257,10 +1465,7 @@ public:
             NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
             exchangeNodes(u, v);
             prepareAdvection<DGA>(u, v, topA, velx, vely, nvX, nvY);
-            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, cice, tmp1, tmp2);
-            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, hice, tmp1, tmp2);
-            limit(cice, 3, 1.0, 0.0);
-            limit(hice, 2, 0.0, 0.0);
+            advectTracers(dt, false);
             NSDG_CUDA_CHECK(cudaEventRecord(ev[2], stream));
             NSDG_CUDA_CHECK(cudaEventRecord(ev[3], stream));
             return;
@@ -1270,17 +1475,13 @@ public:
         if (bbm)
             exchangeNodes(avgU, avgV);
         prepareAdvection<DGA>(bbm ? avgU : u, bbm ? avgV : v, topA, velx, vely, nvX, nvY);
-        transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, cice, tmp1, tmp2);
-        transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, hice, tmp1, tmp2);
-        limit(cice, 3, 1.0, 0.0);
-        limit(hice, 2, 0.0, 0.0);
-        if (bbm) { // BrittleCGDynamicsKernel.hpp:97-106
+        advectTracers(dt, bbm);
+        if (bbm) { // BrittleCGDynamicsKernel.hpp:97-106: the three stresses with the DG8 transport object
             prepareAdvection<DGs>(avgU, avgV, topS, velxS, velyS, nvXS, nvYS);
-            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s11, tmp1S, tmp2S);
-            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s12, tmp1S, tmp2S);
-            transportStep<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, s22, tmp1S, tmp2S);
-            transportStep<DGA>(dt, topA, velx, vely, nvX, nvY, damage, tmp1, tmp2);
-            limit(damage, 3, 1.0, 1e-12);
+            double* phiS[kTransportMaxFields] = { s11, s12, s22 };
+            double* const tmpS[1][kTransportMaxFields] = { { tmp1S, tmp2S, tmp3S } };
+            const LimitSpec none[kTransportMaxFields] = {};
+            transportFields<DGs>(dt, topS, velxS, velyS, nvXS, nvYS, 2, 3, phiS, tmpS, none);
         }
         NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
         if (forcingPending) { // update(): the forcing fields were uploaded on the copy stream while the advection ran
@@ -1767,6 +1968,21 @@ int nsdg_heal_damage(nsdg_handle h, double dt_seconds, double td_seconds, const 
 {
     NSDG_TRY
     H(h)->healDamage(dt_seconds, td_seconds, delta_cice);
+    NSDG_CATCH
+}
+int nsdg_set_boundaries(nsdg_handle h, const long* const* dirichlet, const size_t* ndirichlet, const long* periodic,
+    const size_t* periodic_segment_sizes, size_t nsegments)
+{
+    NSDG_TRY
+    if ((dirichlet && !ndirichlet) || (nsegments > 0 && !periodic_segment_sizes))
+        throw std::runtime_error("nsdg_set_boundaries: list sizes missing");
+    H(h)->setBoundaries(dirichlet, ndirichlet, periodic, periodic_segment_sizes, nsegments);
+    NSDG_CATCH
+}
+int nsdg_advect_field(nsdg_handle h, int field, double dt_seconds, int rk_order, int nsteps, int limit_mode, double maxv, double minv)
+{
+    NSDG_TRY
+    H(h)->advectField(field, dt_seconds, rk_order, nsteps, limit_mode, maxv, minv);
     NSDG_CATCH
 }
 namespace {

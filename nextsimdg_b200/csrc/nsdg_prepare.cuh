@@ -349,4 +349,38 @@ __global__ void planes2aos_kernel(GridDims g, int ncomp, const double* __restric
         aos[d * ncomp + c] = planes[size_t(c) * g.Npad + e];
 }
 
+//! VectorManipulations::CGAveragePeriodic (dynamics/src/include/VectorManipulations.hpp:26-65): for every periodic entry
+//! {type, c1 = right/top element id, c2 = left/bottom element id, edge} and j in [jFirst, jFirst + jCount) the node pair
+//! (i1 on c2's left/bottom edge, i2 on c1's right/top edge) becomes the mean of the two.  One thread per (entry, j).
+template <int CG>
+__global__ void cg_average_periodic_kernel(GridDims g, const long* __restrict__ list, long count, int jFirst, int jCount, double* __restrict__ v)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= count * jCount)
+        return;
+    const long i = t / jCount;
+    const int j = jFirst + int(t % jCount);
+    const long type = list[4 * i], rt = list[4 * i + 1], lb = list[4 * i + 2];
+    const size_t n0lb = size_t(CG * (lb / g.nx)) * g.cgs + size_t(CG * (lb % g.nx));
+    const size_t n0rt = size_t(CG * (rt / g.nx)) * g.cgs + size_t(CG * (rt % g.nx));
+    size_t i1, i2;
+    if (type == 0) { // X-edge: bottom line of the lower-boundary element, top line of the upper-boundary element
+        i1 = n0lb + j;
+        i2 = n0rt + size_t(CG) * g.cgs + j;
+    } else {
+        i1 = n0lb + size_t(j) * g.cgs;
+        i2 = n0rt + CG + size_t(j) * g.cgs;
+    }
+    const double m = 0.5 * (v[i1] + v[i2]);
+    v[i1] = m;
+    v[i2] = m;
+}
+
+__global__ void clamp_kernel(size_t n, double* __restrict__ v, double lo, double hi)
+{
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+        v[i] = fmin(fmax(v[i], lo), hi);
+}
+
 } // namespace nsdg

@@ -5,16 +5,16 @@
  *   cg2dg_kernel          Interpolations::CG2DG             dynamics/src/Interpolations.cpp:74-122
  *   dg2cg_kernel          Interpolations::DG2CG             dynamics/src/Interpolations.cpp:129-204
  *   normalvel_kernel      DGTransport::reinitnormalvelocity dynamics/src/DGTransport.cpp:158-252
- *   transport_kernel      DGTransport::DGTransportOperator  dynamics/src/DGTransport.cpp:272-512
- *                         (cell_term + edge_term_X/Y + boundary_* + inverse mass)
- *   axpy kernels          DGTransport::step_rk2             dynamics/src/DGTransport.cpp:521-532
- *   limit_kernel          LimitMax / LimitMin               dynamics/src/include/dgLimit.hpp:16-84
+ *   transport_stage_kernel DGTransport::DGTransportOperator dynamics/src/DGTransport.cpp:272-512
+ *                         (cell_term + edge_term_X/Y + periodic + boundary_* + inverse mass), fused with the stage
+ *                         update of DGTransport::step_rk1 / rk2 / rk3 (DGTransport.cpp:514-566) and, in the last
+ *                         stage, LimitMax / LimitMin (dynamics/src/include/dgLimit.hpp:16-84); several fields per pass
  *
  * The reference scatters edge fluxes into both neighbours; here every element gathers the flux
  * through its own four edges (each interior edge flux is evaluated twice, identically), in the
  * reference's accumulation order: cell, left, right, bottom, top, then Dirichlet sides 0..3.
- * Periodic edges are not reachable through IDynamics (DynamicsKernel.hpp:54 leaves them TODO),
- * so they are not implemented on the device.
+ * Periodic edges (DGTransport.cpp:466-481) are not reachable through IDynamics (DynamicsKernel.hpp:54 leaves them TODO);
+ * they are set through nsdg_set_boundaries, the way the reference's own advection test assigns ParametricMesh::periodic.
  */
 #pragma once
 #include "nsdg_setup.cuh"
@@ -207,225 +207,12 @@ __global__ void normalvel_kernel(GridDims g, const double* __restrict__ vx, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// The transport operator: phiup = M^-1 [ dt * cell term - dt * sum over edges of upwind flux ]
+// Limiters (dgLimit.hpp:16-84) on the coefficients of one element.  mode bits: 1 = LimitMax(maxv)
+// then 2 = LimitMin(minv), in this order (the reference always calls LimitMax before LimitMin on
+// the same field).
 // ------------------------------------------------------------------------------------------
-template <int DG>
-__global__ void __launch_bounds__(128) transport_kernel(GridDims g, double dt, const uint8_t* __restrict__ landmask,
-    const uint8_t* __restrict__ dirmask, const double* __restrict__ velx, const double* __restrict__ vely,
-    const double* __restrict__ nvX, size_t pitchX, const double* __restrict__ nvY, size_t pitchY, TransportOpPtrs op,
-    const double* __restrict__ geo, const double* __restrict__ phi, double* __restrict__ phiup)
+template <int DG> __device__ __forceinline__ void limitDG(double (&d)[DG], int mode, double maxv, double minv)
 {
-    constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
-    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t_ >= size_t(g.N))
-        return;
-    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
-    const size_t e = size_t(iy) * g.nxs + ix;
-    const size_t Npad = g.Npad;
-    const bool ice = isIce(landmask, e);
-    double up[DG];
-#pragma unroll
-    for (int j = 0; j < DG; ++j)
-        up[j] = 0.0;
-    double ph[DG];
-#pragma unroll
-    for (int j = 0; j < DG; ++j)
-        ph[j] = phi[size_t(j) * Npad + e];
-
-    const size_t eo = e * op.estride;
-    // ---- cell term (DGTransport.cpp:278-303) ----
-    if (DG > 1 && ice) {
-        double vxg[Q], vyg[Q], pg[Q];
-#pragma unroll
-        for (int q = 0; q < Q; ++q)
-            vxg[q] = vyg[q] = pg[q] = 0.0;
-#pragma unroll
-        for (int j = 0; j < DG; ++j) {
-            const double a = velx[size_t(j) * Npad + e], b = vely[size_t(j) * Npad + e];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const double w = PSI(G, j, q);
-                if (w != 0.0) {
-                    vxg[q] = fma(a, w, vxg[q]);
-                    vyg[q] = fma(b, w, vyg[q]);
-                    pg[q] = fma(ph[j], w, pg[q]);
-                }
-            }
-        }
-        if (G == 3 && geo != nullptr) {
-            // AdvectionCellTermX/Y (ParametricMap.cpp:13-66) are w (PSIx dyT_1 - PSIy dxT_1) and w (PSIy dxT_0 - PSIx dyT_0):
-            // formed from the 12 element-map values of the factored-operator path (nsdg_momentum_param.cuh, planes 0..11)
-            // instead of streaming 2 x DG x 9 doubles per element
-            double m[12];
-#pragma unroll
-            for (int k = 0; k < 12; ++k)
-                m[k] = __ldg(geo + size_t(k) * Npad + e);
-            double aq[Q], bq[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int qx = q % 3, qy = q / 3;
-                const double wp = (dt * gaussweight2(3, q)) * pg[q];
-                aq[q] = wp * (m[9 + qx] * vxg[q] - m[6 + qx] * vyg[q]); // yeta vx - xeta vy
-                bq[q] = wp * (m[0 + qy] * vyg[q] - m[3 + qy] * vxg[q]); // xxi vy - yxi vx
-            }
-#pragma unroll
-            for (int j = 0; j < DG; ++j) {
-                double s = 0;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const double px = PSIx(G, j, q), py = PSIy(G, j, q);
-                    if (px != 0.0)
-                        s = fma(px, aq[q], s);
-                    if (py != 0.0)
-                        s = fma(py, bq[q], s);
-                }
-                up[j] += s;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < DG; ++j) {
-                double s = 0;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const double ax = __ldg(op.AdvX + (j * Q + q) * op.pitch + eo);
-                    const double ay = __ldg(op.AdvY + (j * Q + q) * op.pitch + eo);
-                    s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
-                }
-                up[j] += s;
-            }
-        }
-    }
-    // ---- interior edges (DGTransport.cpp:390-433) ----
-    // side: 0 bottom, 1 right, 2 top, 3 left.  Order of the reference accumulation: left, right, bottom, top.
-    auto edgeFlux = [&](int side) {
-        const int nix = ix + (side == 1 ? 1 : (side == 3 ? -1 : 0));
-        const int niy = iy + (side == 2 ? 1 : (side == 0 ? -1 : 0));
-        if (nix < 0 || nix >= g.nx || niy < 0 || niy >= g.ny)
-            return;
-        const size_t en = size_t(niy) * g.nxs + nix;
-        if (!ice || !isIce(landmask, en))
-            return;
-        // c1 = left/bottom element, c2 = right/top element of the edge
-        const bool meFirst = (side == 1 || side == 2);
-        double nv[ED];
-        if (side == 0 || side == 2) {
-            const size_t ie = size_t(side == 2 ? iy + 1 : iy) * g.nx + ix;
-            for (int k = 0; k < ED; ++k)
-                nv[k] = nvX[size_t(k) * pitchX + ie];
-        } else {
-            const size_t ie = size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix);
-            for (int k = 0; k < ED; ++k)
-                nv[k] = nvY[size_t(k) * pitchY + ie];
-        }
-        double tme[ED], tnb[ED];
-        edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
-        edgeofcell<DG>([&](int k) { return phi[size_t(k) * Npad + en]; }, (side + 2) & 3, tnb);
-        double tmp[G];
-#pragma unroll
-        for (int q = 0; q < G; ++q) {
-            double vg = 0, g1 = 0, g2 = 0;
-#pragma unroll
-            for (int k = 0; k < ED; ++k) {
-                vg += nv[k] * PSIe(G, k, q);
-                g1 += (meFirst ? tme[k] : tnb[k]) * PSIe(G, k, q);
-                g2 += (meFirst ? tnb[k] : tme[k]) * PSIe(G, k, q);
-            }
-            tmp[q] = fmax(vg, 0.) * g1 + fmin(vg, 0.) * g2;
-        }
-        const double sdt = meFirst ? -dt : dt;
-#pragma unroll
-        for (int j = 0; j < DG; ++j) {
-            double s = 0;
-#pragma unroll
-            for (int q = 0; q < G; ++q)
-                s += (sdt * tmp[q]) * PSIew(G, side, q, j);
-            up[j] += s;
-        }
-    };
-    edgeFlux(3);
-    edgeFlux(1);
-    edgeFlux(0);
-    edgeFlux(2);
-    // ---- Dirichlet edges: outflow only (DGTransport.cpp:306-351), sides in list order 0,1,2,3 ----
-    const uint8_t dm = dirmask[e];
-    if (dm)
-        for (int side = 0; side < 4; ++side) {
-            if (!(dm & (1 << side)))
-                continue;
-            double nv[ED];
-            if (side == 0 || side == 2) {
-                const size_t ie = size_t(side == 2 ? iy + 1 : iy) * g.nx + ix;
-                for (int k = 0; k < ED; ++k)
-                    nv[k] = nvX[size_t(k) * pitchX + ie];
-            } else {
-                const size_t ie = size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix);
-                for (int k = 0; k < ED; ++k)
-                    nv[k] = nvY[size_t(k) * pitchY + ie];
-            }
-            double tme[ED];
-            edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
-            const double sg = (side == 0 || side == 3) ? -1.0 : 1.0;
-            double tmp[G];
-            for (int q = 0; q < G; ++q) {
-                double vg = 0, g1 = 0;
-                for (int k = 0; k < ED; ++k) {
-                    vg += nv[k] * PSIe(G, k, q);
-                    g1 += tme[k] * PSIe(G, k, q);
-                }
-                tmp[q] = g1 * fmax(sg * vg, 0.);
-            }
-            for (int j = 0; j < DG; ++j) {
-                double s = 0;
-                for (int q = 0; q < G; ++q) {
-                    const double w = side == 0 ? PSIew(G, 0, q, j)
-                        : side == 1            ? PSIew(G, 1, q, j)
-                        : side == 2            ? PSIew(G, 2, q, j)
-                                               : PSIew(G, 3, q, j);
-                    s += (-dt * tmp[q]) * w;
-                }
-                up[j] += s;
-            }
-        }
-    // ---- inverse mass (DGTransport.cpp:509-511) ----
-#pragma unroll
-    for (int i = 0; i < DG; ++i) {
-        double s = 0;
-#pragma unroll
-        for (int j = 0; j < DG; ++j)
-            s += __ldg(op.iMass + (i * DG + j) * op.pitch + eo) * up[j];
-        phiup[size_t(i) * Npad + e] = s;
-    }
-}
-
-//! y += x        (step_rk2: phi += tmp1)
-__global__ void add_kernel(size_t n, double* __restrict__ y, const double* __restrict__ x)
-{
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n)
-        y[i] += x[i];
-}
-//! y += 0.5*(b - a)  (step_rk2: phi += 0.5*(tmp2 - tmp1))
-__global__ void heun_kernel(size_t n, double* __restrict__ y, const double* __restrict__ b, const double* __restrict__ a)
-{
-    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n)
-        y[i] += 0.5 * (b[i] - a[i]);
-}
-
-// ------------------------------------------------------------------------------------------
-// Limiters (dgLimit.hpp:16-84).  mode bits: 1 = LimitMax(maxv) then 2 = LimitMin(minv), in this
-// order (the reference always calls LimitMax before LimitMin on the same field).
-// ------------------------------------------------------------------------------------------
-template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ f, int mode, double maxv, double minv)
-{
-    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t_ >= size_t(g.N))
-        return;
-    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
-    double d[DG];
-#pragma unroll
-    for (int j = 0; j < DG; ++j)
-        d[j] = f[size_t(j) * g.Npad + e];
     if (mode & 1) {
         d[0] = fmin(maxv, d[0]);
         if constexpr (DG == 3) {
@@ -482,9 +269,321 @@ template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ 
             }
         }
     }
+}
+
+template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ f, int mode, double maxv, double minv)
+{
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const size_t e = size_t(t_ / g.nx) * g.nxs + (t_ % g.nx);
+    double d[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        d[j] = f[size_t(j) * g.Npad + e];
+    limitDG<DG>(d, mode, maxv, minv);
 #pragma unroll
     for (int j = 0; j < DG; ++j)
         f[size_t(j) * g.Npad + e] = d[j];
+}
+
+// ------------------------------------------------------------------------------------------
+// One Runge-Kutta STAGE of the DG transport for up to three fields at once:
+//     k   = M^-1 [ dt * cell term - dt * sum over edges of upwind flux ]        (DGTransportOperator, DGTransport.cpp:436-512)
+//     out = epilogue(in, k, base)                                                 (step_rk1/rk2/rk3,    DGTransport.cpp:514-566)
+//     out = limiter(out)   where asked                                            (LimitMax / LimitMin, dgLimit.hpp:16-84)
+// The fields of one launch share everything that does not depend on them -- the velocity in the Gauss points, the four
+// edge normal velocities, the element-map values (or AdvectionCellTermX/Y) and the inverse mass matrix -- which is most of
+// the traffic: hice and cice (and the BBM damage) advance in one pass, the three stresses in another.
+//
+// One thread per element, one warp = 32 consecutive elements of a row.  The trace a neighbour needs from me is a linear map
+// of my own coefficients (edgeofcell), so left / right neighbour traces travel by warp shuffle (lanes 0 / 31 and periodic
+// seams load the neighbour's coefficients instead); bottom / top neighbours are read from the adjacent rows (L2 hits: the
+// rows are in flight in neighbouring blocks).  Every interior edge flux is evaluated twice, identically, by its two
+// elements; accumulation order per element as in the reference: cell, left, right, bottom, top, periodic, Dirichlet 0..3.
+//
+// Epilogues (epi):
+//   0  EULER    out = in + k                                (rk1; first stage of rk2 and rk3: tmp1 = phi + k1)
+//   1  HEUN     out = in + 0.5 (k - (in - base))            (rk2, second stage: phi1 + 0.5 (k2 - k1) with k1 = phi1 - phi0
+//                                                            recomputed instead of stored: 1 ulp of phi, 6 doubles less traffic)
+//   2  COMBINE  out = c1 (in + k) + c0 base                 (rk3: 0.25 (tmp1 + k) + 0.75 phi, then phi / 3 + 2/3 (tmp2 + k))
+// `out` may alias `base` (each thread reads base[e] before it writes out[e]; neighbours read `in` only), never `in`.
+//
+// Periodic edges (DGTransport.cpp:466-481; lists of {type, c1, c2, edge}, ParametricMesh.hpp:79): per[side] holds, for the
+// elements named in the lists, the element across the periodic edge and the edge whose normal velocity the list names (the
+// reference's ring-mesh test names an INTERIOR edge of the same row, AdvectionPeriodicBC_test.cpp:244-248; kept verbatim).
+// ------------------------------------------------------------------------------------------
+constexpr int kTransportMaxFields = 3;
+struct TransportStageArgs {
+    GridDims g;
+    double dt;
+    const uint8_t *landmask, *dirmask;
+    const double *velx, *vely, *nvX, *nvY;
+    size_t pitchX, pitchY;
+    TransportOpPtrs op;
+    const double* geo; //!< element-map planes of the factored-operator path (G = 3 only) or nullptr
+    const int* perNbr; //!< [4][Npad] element (plane index) across a periodic edge on that side, -1 = none; nullptr = no periodic edges
+    const int* perEdge; //!< [4][Npad] index of the edge whose normal velocity that flux uses
+    const double* in[kTransportMaxFields];
+    const double* base[kTransportMaxFields];
+    double* out[kTransportMaxFields];
+    int epi;
+    double c0, c1;
+    int limitMode[kTransportMaxFields];
+    double maxv[kTransportMaxFields], minv[kTransportMaxFields];
+};
+
+template <int DG, int NF>
+__global__ void __launch_bounds__(128, 3) transport_stage_kernel(const __grid_constant__ TransportStageArgs a)
+{
+    constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
+    constexpr unsigned FULL = 0xffffffffu;
+    const GridDims& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const int ixRaw = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y;
+    const bool active = ixRaw < g.nx;
+    const int ix = active ? ixRaw : g.nx - 1;
+    const size_t e = size_t(iy) * g.nxs + ix;
+    const size_t Npad = g.Npad;
+    const double dt = a.dt;
+    const bool ice = isIce(a.landmask, e);
+    const uint8_t dm = a.dirmask[e];
+    const size_t eo = e * a.op.estride;
+
+    // ---- shared by the fields: neighbours, velocities ----
+    // side: 0 bottom, 1 right, 2 top, 3 left
+    long nb[4]; // plane index of the element across each side, -1: none (domain edge, land on either side)
+    long edgeId[4];
+    bool per[4] = { false, false, false, false };
+    {
+        const int nix[4] = { ix, ix + 1, ix, ix - 1 }, niy[4] = { iy - 1, iy, iy + 1, iy };
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool inside = nix[s] >= 0 && nix[s] < g.nx && niy[s] >= 0 && niy[s] < g.ny;
+            nb[s] = inside ? long(size_t(niy[s]) * g.nxs + nix[s]) : -1;
+            edgeId[s] = (s == 0 || s == 2) ? long(size_t(s == 2 ? iy + 1 : iy) * g.nx + ix) : long(size_t(iy) * (g.nx + 1) + (s == 1 ? ix + 1 : ix));
+            if (!inside && a.perNbr != nullptr) {
+                const int pn = a.perNbr[size_t(s) * Npad + e];
+                if (pn >= 0) {
+                    nb[s] = pn;
+                    edgeId[s] = a.perEdge[size_t(s) * Npad + e];
+                    per[s] = true;
+                }
+            }
+            if (nb[s] >= 0 && !(ice && isIce(a.landmask, size_t(nb[s]))))
+                nb[s] = -1; // edge_term_X/Y return when either element is land (DGTransport.cpp:395-398)
+        }
+    }
+    double vxg[Q], vyg[Q];
+    if (DG > 1 && ice) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            vxg[q] = vyg[q] = 0.0;
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            const double vxj = a.velx[size_t(j) * Npad + e], vyj = a.vely[size_t(j) * Npad + e];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const double w = PSI(G, j, q);
+                if (w != 0.0) {
+                    vxg[q] = fma(vxj, w, vxg[q]);
+                    vyg[q] = fma(vyj, w, vyg[q]);
+                }
+            }
+        }
+    }
+    // normal velocity in the edge Gauss points of my four sides (also needed on Dirichlet sides)
+    double vge[4][G];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const bool need = (nb[s] >= 0) || (dm & (1 << s));
+        double nv[ED];
+#pragma unroll
+        for (int k = 0; k < ED; ++k)
+            nv[k] = need ? ((s == 0 || s == 2) ? a.nvX[size_t(k) * a.pitchX + edgeId[s]] : a.nvY[size_t(k) * a.pitchY + edgeId[s]]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            double v = 0;
+#pragma unroll
+            for (int k = 0; k < ED; ++k)
+                v += nv[k] * PSIe(G, k, q);
+            vge[s][q] = v;
+        }
+    }
+    // cell-term weights that do not depend on the field (factored path: element map x velocity in the Gauss points)
+    double cwa[Q], cwb[Q];
+    const bool factored = (G == 3) && a.geo != nullptr;
+    if (DG > 1 && ice && factored) {
+        // AdvectionCellTermX/Y (ParametricMap.cpp:13-66) are w (PSIx dyT_1 - PSIy dxT_1) and w (PSIy dxT_0 - PSIx dyT_0):
+        // formed from the 12 element-map values of the factored-operator path (nsdg_momentum_param.cuh, planes 0..11)
+        double m[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            m[k] = __ldg(a.geo + size_t(k) * Npad + e);
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int qx = q % 3, qy = q / 3;
+            const double w = dt * gaussweight2(3, q);
+            cwa[q] = w * (m[9 + qx] * vxg[q] - m[6 + qx] * vyg[q]); // yeta vx - xeta vy
+            cwb[q] = w * (m[0 + qy] * vyg[q] - m[3 + qy] * vxg[q]); // xxi vy - yxi vx
+        }
+    }
+
+    // the warp-edge lanes and periodic seams cannot shuffle: they read the neighbour's coefficients
+    const bool shflLeft = lane > 0 && !per[3], shflRight = lane < 31 && ixRaw + 1 < g.nx && !per[1];
+
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const double* __restrict__ phi = a.in[f];
+        double ph[DG], up[DG];
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            ph[j] = phi[size_t(j) * Npad + e];
+            up[j] = 0.0;
+        }
+        // ---- cell term (DGTransport.cpp:278-303) ----
+        if (DG > 1 && ice) {
+            double pg[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                pg[q] = 0.0;
+#pragma unroll
+            for (int j = 0; j < DG; ++j)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double w = PSI(G, j, q);
+                    if (w != 0.0)
+                        pg[q] = fma(ph[j], w, pg[q]);
+                }
+            if (factored) {
+#pragma unroll
+                for (int j = 0; j < DG; ++j) {
+                    double s = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const double px = PSIx(G, j, q), py = PSIy(G, j, q);
+                        if (px != 0.0)
+                            s = fma(px, cwa[q] * pg[q], s);
+                        if (py != 0.0)
+                            s = fma(py, cwb[q] * pg[q], s);
+                    }
+                    up[j] += s;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < DG; ++j) {
+                    double s = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const double ax = __ldg(a.op.AdvX + (j * Q + q) * a.op.pitch + eo);
+                        const double ay = __ldg(a.op.AdvY + (j * Q + q) * a.op.pitch + eo);
+                        s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
+                    }
+                    up[j] += s;
+                }
+            }
+        }
+        // ---- traces: mine on the four sides, the neighbours' on the facing sides ----
+        double tme[4][ED], tnb[4][ED];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            edgeofcell<DG>([&](int k) { return ph[k]; }, s, tme[s]);
+#pragma unroll
+        for (int k = 0; k < ED; ++k) { // my left neighbour's right trace, my right neighbour's left trace
+            tnb[3][k] = __shfl_up_sync(FULL, tme[1][k], 1);
+            tnb[1][k] = __shfl_down_sync(FULL, tme[3][k], 1);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const bool viaShfl = (s == 3 && shflLeft) || (s == 1 && shflRight);
+            if (nb[s] >= 0 && !viaShfl) {
+                const size_t en = size_t(nb[s]);
+                edgeofcell<DG>([&](int k) { return phi[size_t(k) * Npad + en]; }, (s + 2) & 3, tnb[s]);
+            }
+        }
+        // ---- edge fluxes (DGTransport.cpp:390-433), reference order: left, right, bottom, top; periodic ones after them ----
+        auto edgeFlux = [&](int s) {
+            // c1 = left / bottom element of the edge, c2 = right / top element
+            const bool meFirst = (s == 1 || s == 2);
+            double tmp[G];
+#pragma unroll
+            for (int q = 0; q < G; ++q) {
+                double g1 = 0, g2 = 0;
+#pragma unroll
+                for (int k = 0; k < ED; ++k) {
+                    g1 += (meFirst ? tme[s][k] : tnb[s][k]) * PSIe(G, k, q);
+                    g2 += (meFirst ? tnb[s][k] : tme[s][k]) * PSIe(G, k, q);
+                }
+                tmp[q] = fmax(vge[s][q], 0.) * g1 + fmin(vge[s][q], 0.) * g2;
+            }
+            const double sdt = meFirst ? -dt : dt;
+#pragma unroll
+            for (int j = 0; j < DG; ++j) {
+                double acc = 0;
+#pragma unroll
+                for (int q = 0; q < G; ++q)
+                    acc += (sdt * tmp[q]) * (s == 0 ? PSIew(G, 0, q, j) : s == 1 ? PSIew(G, 1, q, j) : s == 2 ? PSIew(G, 2, q, j) : PSIew(G, 3, q, j));
+                up[j] += acc;
+            }
+        };
+        const int order[4] = { 3, 1, 0, 2 };
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) // pass 0: interior edges, pass 1: periodic edges
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = order[i];
+                if (nb[s] >= 0 && per[s] == (pass == 1))
+                    edgeFlux(s);
+            }
+        // ---- Dirichlet edges: outflow only (DGTransport.cpp:306-351), sides in list order 0,1,2,3 ----
+        if (dm) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (!(dm & (1 << s)))
+                    continue;
+                const double sg = (s == 0 || s == 3) ? -1.0 : 1.0;
+                double tmp[G];
+#pragma unroll
+                for (int q = 0; q < G; ++q) {
+                    double g1 = 0;
+#pragma unroll
+                    for (int k = 0; k < ED; ++k)
+                        g1 += tme[s][k] * PSIe(G, k, q);
+                    tmp[q] = g1 * fmax(sg * vge[s][q], 0.);
+                }
+#pragma unroll
+                for (int j = 0; j < DG; ++j) {
+                    double acc = 0;
+#pragma unroll
+                    for (int q = 0; q < G; ++q)
+                        acc += (-dt * tmp[q]) * (s == 0 ? PSIew(G, 0, q, j) : s == 1 ? PSIew(G, 1, q, j) : s == 2 ? PSIew(G, 2, q, j) : PSIew(G, 3, q, j));
+                    up[j] += acc;
+                }
+            }
+        }
+        // ---- inverse mass (DGTransport.cpp:509-511), Runge-Kutta epilogue, limiter ----
+        double res[DG];
+#pragma unroll
+        for (int i = 0; i < DG; ++i) {
+            double k = 0;
+#pragma unroll
+            for (int j = 0; j < DG; ++j)
+                k += __ldg(a.op.iMass + (i * DG + j) * a.op.pitch + eo) * up[j];
+            if (a.epi == 0)
+                res[i] = ph[i] + k;
+            else {
+                const double b = a.base[f][size_t(i) * Npad + e];
+                res[i] = a.epi == 1 ? ph[i] + 0.5 * (k - (ph[i] - b)) : a.c1 * (ph[i] + k) + a.c0 * b;
+            }
+        }
+        if (a.limitMode[f])
+            limitDG<DG>(res, a.limitMode[f], a.maxv[f], a.minv[f]);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < DG; ++i)
+                a.out[f][size_t(i) * Npad + e] = res[i];
+        }
+    }
 }
 
 } // namespace nsdg

@@ -185,6 +185,34 @@ class CUDADynamicsBase:
     def step(self, dt: float):
         check(self._lib.nsdg_step(self._h, float(dt)))
 
+    def set_boundaries(self, dirichlet=None, periodic=None):
+        """ParametricMesh::dirichlet / ::periodic assigned directly (ParametricMesh.hpp:76-79), as the reference's advection
+        tests do.  dirichlet: None or a list of 4 element-index lists (None entries keep the mask-derived list);
+        periodic: None or a list of segments, each a list of (type, c1, c2, edge)."""
+        keep = []
+        dptr = nptr = None
+        if dirichlet is not None:
+            # one spare entry so that an EMPTY list still has a non-null pointer (NULL means "keep the mask-derived list")
+            arrs = [None if d is None else np.ascontiguousarray(np.append(np.asarray(d, dtype=np.int64), 0)) for d in dirichlet]
+            keep += arrs
+            dp = (c_void_p * 4)(*[None if a is None else a.ctypes.data_as(c_void_p) for a in arrs])
+            nd = (c_size_t * 4)(*[0 if a is None else a.size - 1 for a in arrs])
+            keep += [dp, nd]
+            dptr, nptr = ctypes.cast(dp, c_void_p), ctypes.cast(nd, c_void_p)
+        segs = [np.ascontiguousarray(sg, dtype=np.int64).reshape(-1, 4) for sg in (periodic or [])]
+        flat = np.ascontiguousarray(np.concatenate(segs, axis=0)) if segs else np.zeros((0, 4), dtype=np.int64)
+        sizes = (c_size_t * max(len(segs), 1))(*[sg.shape[0] for sg in segs])
+        check(self._lib.nsdg_set_boundaries(self._h, dptr, nptr, flat.ctypes.data_as(c_void_p) if flat.size else None,
+                                            ctypes.cast(sizes, c_void_p), len(segs)))
+        del keep
+
+    def advect_field(self, name: str, dt: float, rk_order: int = 2, nsteps: int = 1, limit_max=None, limit_min=None):
+        """nsteps x {DGTransport::reinitnormalvelocity; DGTransport::step (rk1 / rk2 / rk3); LimitMax; LimitMin} on one DG
+        field, with the DG velocity currently in the transport object (set_internal("velx" / "vely"))."""
+        mode = (1 if limit_max is not None else 0) | (2 if limit_min is not None else 0)
+        check(self._lib.nsdg_advect_field(self._h, capi.FIELD_IDS[name], float(dt), int(rk_order), int(nsteps), mode,
+                                          float(limit_max or 0.0), float(limit_min or 0.0)))
+
     def set_benchmark_forcing(self, elapsed_seconds: float, domain_x: float = 512e3, domain_y: float = 512e3):
         """Benchmark{Atmosphere,Ocean} evaluated on the device (no forcing crosses PCIe)."""
         check(self._lib.nsdg_set_benchmark_forcing(self._h, float(elapsed_seconds), float(domain_x), float(domain_y)))

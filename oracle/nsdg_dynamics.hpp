@@ -271,6 +271,7 @@ public:
     virtual const Vec* raw(const std::string& name) = 0;
     virtual Vec* rawMutable(const std::string& name) = 0;
     virtual const Mesh& mesh() const = 0;
+    virtual Mesh& meshMutable() = 0;
     virtual void subcycle() = 0;
     virtual void sweep(const std::string& which) = 0;
     virtual void setDeltaT(double) = 0;
@@ -311,6 +312,7 @@ public:
         delete pmap;
     }
     const Mesh& mesh() const override { return m; }
+    Mesh& meshMutable() override { return m; }
 
     //! DynamicsKernel.hpp:44-75, CGDynamicsKernel.cpp:24-51, BrittleCGDynamicsKernel.hpp:72-86
     void initialise(size_t nx, size_t ny, const double* coords, const double* mask, bool sph) override

@@ -160,9 +160,99 @@ template <int DG> double katPeriodic(int it, double* massloss)
     return sqrt(L2ErrorFunctionDG<DG>(m, phi, packman)) / R0;
 }
 
+// ---- the same two tests with the TIME LOOP left to the caller (the CUDA library, through its C ABI): the oracle only
+// builds the mesh, projects the initial data and the velocity (Function2DG) and measures the error at the end ----
+template <int DG> int katStage(int kind, int it, double distort, double* coords, double* phi0, double* velx, double* vely, long* nt, double* dt)
+{
+    Mesh m;
+    size_t NT;
+    Vec phi, vx, vy;
+    if (kind == 0) {
+        boxMesh(m, 12 * (1 << it), 13 * (1 << it), distort);
+        NT = 100 * (dg2deg(DG) + 1) * (dg2deg(DG) + 1) * (1 << it);
+        *dt = Lx / NT;
+        Function2DG<DG>(m, phi, smoothBump);
+        Function2DG<DG>(m, vx, [](double, double y) { return (y - 0.5 * Lx) * 2.0 * M_PI / Lx; });
+        Function2DG<DG>(m, vy, [](double x, double) { return (0.5 * Lx - x) * 2.0 * M_PI / Lx; });
+    } else {
+        ringMesh(m, 32 * (1 << it), 4 * (1 << it));
+        NT = 50 * (dg2deg(DG) + 1) * (dg2deg(DG) + 1) * (1 << it);
+        *dt = R1 / NT;
+        Function2DG<DG>(m, phi, packman);
+        LimitMax<DG>(phi, 1.0); // AdvectionPeriodicBC_test.cpp:169
+        Function2DG<DG>(m, vx, [](double, double y) { return y * 2.0 * M_PI / R1; });
+        Function2DG<DG>(m, vy, [](double x, double) { return -x * 2.0 * M_PI / R1; });
+    }
+    *nt = long(NT);
+    for (size_t i = 0; i < m.nnodes; ++i) {
+        coords[2 * i] = m.vx[i];
+        coords[2 * i + 1] = m.vy[i];
+    }
+    std::copy(phi.begin(), phi.end(), phi0);
+    std::copy(vx.begin(), vx.end(), velx);
+    std::copy(vy.begin(), vy.end(), vely);
+    return 0;
+}
+template <int DG> double katError(int kind, int it, double distort, const double* phiEnd)
+{
+    Mesh m;
+    if (kind == 0)
+        boxMesh(m, 12 * (1 << it), 13 * (1 << it), distort);
+    else
+        ringMesh(m, 32 * (1 << it), 4 * (1 << it));
+    Vec phi(phiEnd, phiEnd + m.nelements * DG);
+    return kind == 0 ? sqrt(L2ErrorFunctionDG<DG>(m, phi, smoothBump)) / Lx : sqrt(L2ErrorFunctionDG<DG>(m, phi, packman)) / R0;
+}
+
 } // namespace
 
 extern "C" {
+
+//! kind 0: Advection_test.cpp's box, kind 1: AdvectionPeriodicBC_test.cpp's ring.  Fills the vertex coordinates
+//! ((nx+1)(ny+1) x 2), the projected initial field and velocity (N x DG each), the number of time steps and dt.
+int nso_kat_stage(int kind, int DG, int it, double distort, double* coords, double* phi0, double* velx, double* vely, long* nt, double* dt)
+{
+    switch (DG) {
+    case 3:
+        return katStage<3>(kind, it, distort, coords, phi0, velx, vely, nt, dt);
+    case 6:
+        return katStage<6>(kind, it, distort, coords, phi0, velx, vely, nt, dt);
+    }
+    return -1;
+}
+//! `nsteps` steps of the staged problem with scheme rk<order> on the oracle's own transport object (no limiter): the
+//! step-by-step checker of the CUDA Runge-Kutta stages
+int nso_kat_steps(int kind, int DG, int it, double distort, int order, int nsteps, double* out)
+{
+    if (DG != 6 || kind != 0)
+        return -1;
+    Mesh m;
+    boxMesh(m, 12 * (1 << it), 13 * (1 << it), distort);
+    Transport<6> tr(m);
+    tr.scheme = order == 1 ? "rk1" : (order == 2 ? "rk2" : "rk3");
+    const double dt = Lx / (100 * 9 * (1 << it));
+    Vec phi;
+    Function2DG<6>(m, phi, smoothBump);
+    Function2DG<6>(m, tr.velx, [](double, double y) { return (y - 0.5 * Lx) * 2.0 * M_PI / Lx; });
+    Function2DG<6>(m, tr.vely, [](double x, double) { return (0.5 * Lx - x) * 2.0 * M_PI / Lx; });
+    for (int i = 0; i < nsteps; ++i) {
+        tr.reinitnormalvelocity();
+        tr.step(dt, phi);
+    }
+    std::copy(phi.begin(), phi.end(), out);
+    return 0;
+}
+//! the tests' error measure (sqrt(L2ErrorFunctionDG) / L) of a final field computed elsewhere
+double nso_kat_error(int kind, int DG, int it, double distort, const double* phi)
+{
+    switch (DG) {
+    case 3:
+        return katError<3>(kind, it, distort, phi);
+    case 6:
+        return katError<6>(kind, it, distort, phi);
+    }
+    return -1;
+}
 
 //! L2 error of Advection_test.cpp's run<DG>(distort) at refinement `it`; -1 on bad DG.
 double nso_kat_advection(int DG, int it, double distort, double* massloss)

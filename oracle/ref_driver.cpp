@@ -371,6 +371,27 @@ int nso_set_raw(void* hv, const char* name, const double* in)
     std::copy(in, in + r.n, r.p);
     return 0;
 }
+#define MESH_OF(h) const_cast<ParametricMesh&>(static_cast<Handle*>(h)->k->mesh())
+//! ParametricMesh::dirichlet[edge] / ::periodic assigned directly, as the reference's advection tests do
+//! (Advection_test.cpp:222-240, AdvectionPeriodicBC_test.cpp:228-249).  dir[e] == nullptr keeps list e.
+int nso_set_boundaries(void* hv, const long* const* dir, const size_t* ndir, const long* per, const size_t* segSizes, size_t nseg)
+{
+    auto& m = MESH_OF(hv);
+    for (int e = 0; e < 4; ++e)
+        if (dir && dir[e]) {
+            m.dirichlet[e].clear();
+            for (size_t i = 0; i < ndir[e]; ++i)
+                m.dirichlet[e].push_back(static_cast<size_t>(dir[e][i]));
+        }
+    m.periodic.clear();
+    m.periodic.resize(nseg);
+    size_t k = 0;
+    for (size_t s = 0; s < nseg; ++s)
+        for (size_t i = 0; i < segSizes[s]; ++i, ++k)
+            m.periodic[s].push_back({ size_t(per[4 * k]), size_t(per[4 * k + 1]), size_t(per[4 * k + 2]), size_t(per[4 * k + 3]) });
+    return 0;
+}
+#undef MESH_OF
 long nso_dirichlet_size(void* hv, int edge)
 {
     return static_cast<long>(static_cast<Handle*>(hv)->k->mesh().dirichlet[edge].size());
