@@ -826,15 +826,11 @@ public:
         launches += 2;
         normalVelocity<DG>(vxd, vyd, nX, nY);
     }
-    template <int DG> void launchStage(const TransportStageArgs& a, int nf)
+    template <int DG> void launchStage(TransportStageArgs& a, int nf)
     {
-        const dim3 grid((g.nx + 127) / 128, g.ny);
-        if (nf == 1)
-            transport_stage_kernel<DG, 1><<<grid, 128, 0, stream>>>(a);
-        else if (nf == 2)
-            transport_stage_kernel<DG, 2><<<grid, 128, 0, stream>>>(a);
-        else
-            transport_stage_kernel<DG, 3><<<grid, 128, 0, stream>>>(a);
+        a.nf = nf;
+        const dim3 grid(unsigned((g.nx + 127) / 128) * nf, g.ny);
+        transport_stage_kernel<DG><<<grid, 128, 0, stream>>>(a);
         launches += 1;
     }
     struct LimitSpec {

@@ -294,9 +294,10 @@ template <int DG> __global__ void limit_kernel(GridDims g, double* __restrict__ 
 //     out = limiter(out)   where asked                                            (LimitMax / LimitMin, dgLimit.hpp:16-84)
 // The fields of one launch share everything that does not depend on them -- the velocity in the Gauss points, the four
 // edge normal velocities, the element-map values (or AdvectionCellTermX/Y) and the inverse mass matrix -- which is most of
-// the traffic: hice and cice (and the BBM damage) advance in one pass, the three stresses in another.
+// the traffic: hice and cice (and the BBM damage) advance in one pass, the three stresses in another.  The sharing is
+// through L2: neighbouring blocks take the same tile of elements for the different fields.
 //
-// One thread per element, one warp = 32 consecutive elements of a row.  The trace a neighbour needs from me is a linear map
+// One thread per element and field, one warp = 32 consecutive elements of a row.  The trace a neighbour needs from me is a linear map
 // of my own coefficients (edgeofcell), so left / right neighbour traces travel by warp shuffle (lanes 0 / 31 and periodic
 // seams load the neighbour's coefficients instead); bottom / top neighbours are read from the adjacent rows (L2 hits: the
 // rows are in flight in neighbouring blocks).  Every interior edge flux is evaluated twice, identically, by its two
@@ -324,6 +325,7 @@ struct TransportStageArgs {
     const double* geo; //!< element-map planes of the factored-operator path (G = 3 only) or nullptr
     const int* perNbr; //!< [4][Npad] element (plane index) across a periodic edge on that side, -1 = none; nullptr = no periodic edges
     const int* perEdge; //!< [4][Npad] index of the edge whose normal velocity that flux uses
+    int nf; //!< fields advanced by this launch (grid.x = tiles * nf)
     const double* in[kTransportMaxFields];
     const double* base[kTransportMaxFields];
     double* out[kTransportMaxFields];
@@ -333,14 +335,21 @@ struct TransportStageArgs {
     double maxv[kTransportMaxFields], minv[kTransportMaxFields];
 };
 
-template <int DG, int NF>
-__global__ void __launch_bounds__(128, 3) transport_stage_kernel(const __grid_constant__ TransportStageArgs a)
+#ifndef NSDG_TRANSPORT_MINB
+#define NSDG_TRANSPORT_MINB 1 //!< minimum resident blocks per SM asked of the compiler (register cap): tuning knob
+#endif
+template <int DG>
+__global__ void __launch_bounds__(128, NSDG_TRANSPORT_MINB) transport_stage_kernel(const __grid_constant__ TransportStageArgs a)
 {
     constexpr int G = gp1d(DG), Q = G * G, ED = edgedofs(DG);
     constexpr unsigned FULL = 0xffffffffu;
     const GridDims& g = a.g;
     const int lane = threadIdx.x & 31;
-    const int ixRaw = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y;
+    // blockIdx.x = tile * nf + field: the blocks that advance the different fields of one tile are scheduled together, so
+    // what they share (velocities, edge velocities, element map, inverse mass) comes from DRAM once and from L2 after
+    // that, while each thread carries the registers of ONE field (interleaving the fields in one thread spills)
+    const int f = blockIdx.x % a.nf;
+    const int ixRaw = (blockIdx.x / a.nf) * blockDim.x + threadIdx.x, iy = blockIdx.y;
     const bool active = ixRaw < g.nx;
     const int ix = active ? ixRaw : g.nx - 1;
     const size_t e = size_t(iy) * g.nxs + ix;
@@ -432,8 +441,7 @@ __global__ void __launch_bounds__(128, 3) transport_stage_kernel(const __grid_co
     // the warp-edge lanes and periodic seams cannot shuffle: they read the neighbour's coefficients
     const bool shflLeft = lane > 0 && !per[3], shflRight = lane < 31 && ixRaw + 1 < g.nx && !per[1];
 
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
+    {
         const double* __restrict__ phi = a.in[f];
         double ph[DG], up[DG];
 #pragma unroll

@@ -1,9 +1,9 @@
 /*!
  * @file CUDADynamics.cpp
  *
- * Implementation of Nextsim::CUDAMEVPDynamics / Nextsim::CUDABBMDynamics above the C ABI.
- * Control flow follows core/src/modules/DynamicsModule/MEVPDynamics.cpp:37-101 and
- * BBMDynamics.cpp:32-132; every kernel.* call of the reference is one nsdg_* call here.
+ * Implementation of Nextsim::CUDAMEVPDynamics / CUDABBMDynamics / CUDAFreeDriftDynamics above the C ABI.
+ * Control flow follows core/src/modules/DynamicsModule/MEVPDynamics.cpp:37-101, BBMDynamics.cpp:32-132 and
+ * include/FreeDriftDynamics.hpp:37-81; every kernel.* call of the reference is one nsdg_* call here.
  *
  * Goes to core/src/modules/DynamicsModule/ in the nextsimdg tree.
  */
@@ -209,6 +209,55 @@ ModelState CUDABBMDynamics::getStateRecursive(const OutputSpec& os) const
         });
     }
     return state;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+CUDAFreeDriftDynamics::CUDAFreeDriftDynamics()
+    : CUDADynamicsBase(NSDG_FREEDRIFT, false)
+{
+}
+
+void CUDAFreeDriftDynamics::setData(const ModelState::DataMap& ms)
+{
+    IDynamics::setData(ms);
+
+    bool isSpherical = checkSpherical(ms);
+
+    ModelArray coords = ms.at(coordsName);
+    if (isSpherical) {
+        coords *= radians;
+    }
+    // kernel.initialise(coords, false, mask): the reference passes isSpherical = false whatever the coordinates are
+    // (FreeDriftDynamics.hpp:69), after scaling longitude / latitude to radians
+    const ModelArray& mask = ms.at(maskName);
+    check(nsdg_set_mesh(handle, static_cast<int>(ModelArray::size(ModelArray::Dimension::X)),
+        static_cast<int>(ModelArray::size(ModelArray::Dimension::Y)), coords.getData(), mask.getData(), 0));
+
+    // Set the data in the kernel arrays.
+    for (const auto& fieldName : namedFields) {
+        const ModelArray& data = ms.at(fieldName);
+        check(nsdg_set_field(
+            handle, fieldIds.at(fieldName), data.getData(), static_cast<int>(data.nComponents())));
+    }
+}
+
+void CUDAFreeDriftDynamics::update(const TimestepTime& tst)
+{
+    std::cout << tst.start << std::endl;
+
+    // only the updated ice thickness and concentration and the ocean velocity go in; hice, cice, u, v come out: no wind,
+    // no sea-surface height, no ice-ocean stress (FreeDriftDynamics.hpp:39-58)
+    nsdg_update_io io {};
+    io.hice_in = hice.data().getData();
+    io.cice_in = cice.data().getData();
+    io.uocean = uocean.data().getData();
+    io.vocean = vocean.data().getData();
+    io.hice_out = const_cast<double*>(hice.data().getData());
+    io.cice_out = const_cast<double*>(cice.data().getData());
+    io.u_out = const_cast<double*>(uice.getData());
+    io.v_out = const_cast<double*>(vice.getData());
+    check(nsdg_update(handle, &io, tst.step.seconds()));
 }
 
 } /* namespace Nextsim */

@@ -1,14 +1,16 @@
 /*!
  * @file CUDADynamics.hpp
  *
- * Nextsim::CUDAMEVPDynamics / Nextsim::CUDABBMDynamics -- drop-in IDynamics modules whose kernel
- * object lives on a B200 behind the C ABI of libnsdg_cuda.so (include/nsdg.h).
+ * Nextsim::CUDAMEVPDynamics / Nextsim::CUDABBMDynamics / Nextsim::CUDAFreeDriftDynamics -- drop-in IDynamics modules
+ * whose kernel object lives on a B200 behind the C ABI of libnsdg_cuda.so (include/nsdg.h).
  *
  * They replace, method for method,
- *   Nextsim::MEVPDynamics  core/src/modules/DynamicsModule/MEVPDynamics.cpp:23-101
- *   Nextsim::BBMDynamics   core/src/modules/DynamicsModule/BBMDynamics.cpp:19-132
+ *   Nextsim::MEVPDynamics       core/src/modules/DynamicsModule/MEVPDynamics.cpp:23-101
+ *   Nextsim::BBMDynamics        core/src/modules/DynamicsModule/BBMDynamics.cpp:19-132
+ *   Nextsim::FreeDriftDynamics  core/src/modules/DynamicsModule/include/FreeDriftDynamics.hpp:26-83
  * and are selected like them from the .cfg:   [Modules]  DynamicsModule = Nextsim::CUDAMEVPDynamics
- * (registration: INTEGRATION.md).  Host code only marshals ModelArray buffers; there is no CPU
+ * (registration: INTEGRATION.md, integration/module.cfg.patch; the module builder includes include/<file_prefix>.hpp,
+ * hence the one-line headers CUDAMEVPDynamics.hpp, CUDABBMDynamics.hpp, CUDAFreeDriftDynamics.hpp next to this file).  Host code only marshals ModelArray buffers; there is no CPU
  * fallback -- construction throws std::runtime_error if no CUDA device is usable.
  *
  * Goes to core/src/modules/DynamicsModule/include/ in the nextsimdg tree.
@@ -69,6 +71,15 @@ public:
     void setData(const ModelState::DataMap& ms) override;
     ModelState getState() const override;
     ModelState getStateRecursive(const OutputSpec& os) const override;
+};
+
+//! Drop-in for Nextsim::FreeDriftDynamics (FreeDriftDynamics.hpp:26-83): the ice follows the ocean, hice and cice are advected
+class CUDAFreeDriftDynamics : public CUDADynamicsBase {
+public:
+    CUDAFreeDriftDynamics();
+    std::string getName() const override { return "CUDAFreeDriftDynamics"; }
+    void setData(const ModelState::DataMap& ms) override;
+    void update(const TimestepTime& tst) override;
 };
 
 } /* namespace Nextsim */

@@ -118,6 +118,157 @@ class Partition:
         return out
 
 
+# -- the reference's partition metadata file ------------------------------------------------------------------------------
+def parse_cdl(text: str) -> dict:
+    """Minimal reader of the CDL text form (`ncdump` output) of the reference's partition files (run/partition.cdl,
+    core/test/partition_metadata_{2,3}.cdl): {"dimensions": {name: size}, "groups": {group: {variable: [int, ...]}}}.
+    The model itself reads the netCDF binary (`ncgen` of the same text) in ModelMetadata::getPartitionMetadata
+    (core/src/ModelMetadata.cpp:42-62); netCDF is absent from this image, the text carries the same content."""
+    import re
+
+    text = re.sub(r"//[^\n]*", "", text)
+    dims, groups = {}, {}
+    m = re.search(r"dimensions:(.*?)(?=group:|variables:|data:|\})", text, re.S)
+    if m:
+        for name, val in re.findall(r"(\w+)\s*=\s*(\w+)\s*;", m.group(1)):
+            dims[name] = 0 if val == "UNLIMITED" else int(val)
+    for gm in re.finditer(r"group:\s*(\w+)\s*\{(.*?)\}", text, re.S):
+        body = gm.group(2)
+        data = body.split("data:", 1)[1] if "data:" in body else ""
+        groups[gm.group(1)] = {name: [int(v) for v in vals.replace(",", " ").split()]
+                               for name, vals in re.findall(r"(\w+)\s*=\s*([-\d,\s]+);", data)}
+    return {"dimensions": dims, "groups": groups}
+
+
+@dataclass
+class PartitionFile:
+    """Content of a partition metadata file: global extent, one bounding box per rank, and the connectivity group as
+    written (per rank and file side a list of (neighbour rank, halo length); core/test/partition_metadata_3.cdl:28-66)."""
+
+    global_nx: int
+    global_ny: int
+    boxes: list  # (x0, y0, extent_x, extent_y) per rank
+    connectivity: dict  # {"top" | "bottom" | "left" | "right": [[(rank, halo), ...] per rank]} or {}
+
+    @classmethod
+    def read(cls, path: str) -> "PartitionFile":
+        return cls.from_cdl(open(path).read())
+
+    @classmethod
+    def from_cdl(cls, text: str) -> "PartitionFile":
+        d = parse_cdl(text)
+        bb = d["groups"]["bounding_boxes"]
+        nb = d["dimensions"]["P"]
+        boxes = [(bb["domain_x"][r], bb["domain_y"][r], bb["domain_extent_x"][r], bb["domain_extent_y"][r]) for r in range(nb)]
+        conn = {}
+        cg = d["groups"].get("connectivity")
+        if cg:
+            for side in ("top", "bottom", "left", "right"):
+                counts = cg.get(f"{side}_neighbors", [0] * nb)
+                ids, halos = cg.get(f"{side}_neighbor_ids", []), cg.get(f"{side}_neighbor_halos", [])
+                per_rank, k = [], 0
+                for r in range(nb):
+                    per_rank.append([(ids[k + i], halos[k + i]) for i in range(counts[r])])
+                    k += counts[r]
+                conn[side] = per_rank
+        return cls(d["dimensions"]["NX"], d["dimensions"]["NY"], boxes, conn)
+
+    def neighbours_geometric(self, rank: int) -> dict:
+        """{side (this module's BOTTOM/RIGHT/TOP/LEFT = -y/+x/+y/-x): [(neighbour rank, shared edge length), ...]}"""
+        x0, y0, ex, ey = self.boxes[rank]
+        out = {BOTTOM: [], RIGHT: [], TOP: [], LEFT: []}
+        for q, (a0, b0, ea, eb) in enumerate(self.boxes):
+            if q == rank:
+                continue
+            ox = min(x0 + ex, a0 + ea) - max(x0, a0)  # overlap along x
+            oy = min(y0 + ey, b0 + eb) - max(y0, b0)
+            if b0 + eb == y0 and ox > 0:
+                out[BOTTOM].append((q, ox))
+            if b0 == y0 + ey and ox > 0:
+                out[TOP].append((q, ox))
+            if a0 + ea == x0 and oy > 0:
+                out[LEFT].append((q, oy))
+            if a0 == x0 + ex and oy > 0:
+                out[RIGHT].append((q, oy))
+        return out
+
+    def check_connectivity(self):
+        """The connectivity group must name exactly the boxes that touch geometrically, with the shared edge length as
+        the halo size.  The files call the -x / +x sides top / bottom and -y / +y left / right (x is their row index:
+        partition_metadata_2.cdl has box 1 at domain_x = 4 as the BOTTOM neighbour of box 0)."""
+        if not self.connectivity:
+            return
+        names = {LEFT: "top", RIGHT: "bottom", BOTTOM: "left", TOP: "right"}
+        for r in range(len(self.boxes)):
+            geo = self.neighbours_geometric(r)
+            for side, fname in names.items():
+                if sorted(geo[side]) != sorted(self.connectivity[fname][r]):
+                    raise ValueError(f"partition file: {fname} neighbours of box {r} are {self.connectivity[fname][r]}, the boxes give {geo[side]}")
+
+    def partition(self, rank: int) -> "Partition":
+        """The box of `rank` as a Partition the device library can run: every side must face at most ONE neighbour that
+        covers the whole side (nsdg_config.neighbour[4]); the regular px x py decompositions of this module and of
+        bench.py are of that kind, the general files of the reference (e.g. partition_metadata_3.cdl) need not be."""
+        self.check_connectivity()
+        x0, y0, ex, ey = self.boxes[rank]
+        geo = self.neighbours_geometric(rank)
+        nb = [-1, -1, -1, -1]
+        for side in (BOTTOM, RIGHT, TOP, LEFT):
+            want = ex if side in (BOTTOM, TOP) else ey
+            on_edge = {BOTTOM: y0 == 0, TOP: y0 + ey == self.global_ny, LEFT: x0 == 0, RIGHT: x0 + ex == self.global_nx}[side]
+            if not geo[side]:
+                if not on_edge:
+                    raise ValueError(f"box {rank}: side {side} is neither on the domain edge nor covered by a neighbour")
+                continue
+            if len(geo[side]) != 1 or geo[side][0][1] != want:
+                raise ValueError(f"box {rank}: side {side} faces {len(geo[side])} neighbours / a partial overlap; libnsdg_cuda "
+                                 "exchanges halos with one neighbour per side (regular box grids)")
+            q = geo[side][0][0]
+            # the neighbour must see this box the same way (equal extents along the shared side)
+            a0, b0, ea, eb = self.boxes[q]
+            if (side in (BOTTOM, TOP) and (a0, ea) != (x0, ex)) or (side in (LEFT, RIGHT) and (b0, eb) != (y0, ey)):
+                raise ValueError(f"box {rank}: neighbour {q} across side {side} has a different extent along the shared side")
+            nb[side] = q
+        p = object.__new__(Partition)
+        p.rank, p.nranks, p.global_nx, p.global_ny = rank, len(self.boxes), self.global_nx, self.global_ny
+        p.px = p.py = 0  # not a regular grid description
+        p.ix = p.iy = -1
+        p.nx, p.ny, p.x0, p.y0 = ex, ey, x0, y0
+        p.neighbour = nb
+        p.ring = [1 if r >= 0 else 0 for r in nb]
+        p.lx0, p.ly0 = p.x0 - p.ring[LEFT], p.y0 - p.ring[BOTTOM]
+        p.lnx = p.nx + p.ring[LEFT] + p.ring[RIGHT]
+        p.lny = p.ny + p.ring[BOTTOM] + p.ring[TOP]
+        return p
+
+
+def write_partition_cdl(parts, name: str = "partition") -> str:
+    """The CDL text of a list of Partitions in the reference's format (bounding_boxes + connectivity groups, with the
+    files' side names: top / bottom = -x / +x, left / right = -y / +y)."""
+    nb = len(parts)
+    fside = {"top": LEFT, "bottom": RIGHT, "left": BOTTOM, "right": TOP}
+    cnt = {k: [1 if p.neighbour[s] >= 0 else 0 for p in parts] for k, s in fside.items()}
+    ids = {k: [p.neighbour[s] for p in parts if p.neighbour[s] >= 0] for k, s in fside.items()}
+    halo = {k: [(p.ny if s in (LEFT, RIGHT) else p.nx) for p in parts if p.neighbour[s] >= 0] for k, s in fside.items()}
+    dimn = {"top": "T", "bottom": "B", "left": "L", "right": "R"}
+    join = lambda v: ", ".join(str(x) for x in v)  # noqa: E731
+    out = [f"netcdf {name} {{", "dimensions:", f"\tNX = {parts[0].global_nx} ;", f"\tNY = {parts[0].global_ny} ;", f"\tP = {nb} ;"]
+    out += [f"\t{dimn[k]} = {max(len(ids[k]), 1)} ;" for k in fside]
+    out += ["", "group: bounding_boxes {", "  variables:", "\tint domain_x(P) ;", "\tint domain_y(P) ;", "\tint domain_extent_x(P) ;",
+            "\tint domain_extent_y(P) ;", "  data:", "", f"   domain_x = {join(p.x0 for p in parts)} ;", "",
+            f"   domain_y = {join(p.y0 for p in parts)} ;", "", f"   domain_extent_x = {join(p.nx for p in parts)} ;", "",
+            f"   domain_extent_y = {join(p.ny for p in parts)} ;", "  } // group bounding_boxes", "", "group: connectivity {", "  variables:"]
+    for k in fside:
+        out += [f"\tint {k}_neighbors(P) ;", f"\tint {k}_neighbor_ids({dimn[k]}) ;", f"\tint {k}_neighbor_halos({dimn[k]}) ;"]
+    out += ["  data:", ""]
+    for k in fside:
+        out += [f"   {k}_neighbors = {join(cnt[k])} ;", ""]
+        if ids[k]:
+            out += [f"   {k}_neighbor_ids = {join(ids[k])} ;", "", f"   {k}_neighbor_halos = {join(halo[k])} ;", ""]
+    out += ["  } // group connectivity", "}", ""]
+    return "\n".join(out)
+
+
 def connect_halos(dyn, part: Partition, all_gather):
     """Exchange the arena IPC handles and connect every neighbour side.
 

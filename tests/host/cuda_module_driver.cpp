@@ -1,8 +1,8 @@
 /*
- * Drives Nextsim::CUDAMEVPDynamics / CUDABBMDynamics (nextsimdg_b200/host/CUDADynamics.cpp) exactly as PrognosticData
+ * Drives Nextsim::CUDAMEVPDynamics / CUDABBMDynamics / CUDAFreeDriftDynamics (nextsimdg_b200/host/CUDADynamics.cpp) exactly as PrognosticData
  * does (core/src/PrognosticData.cpp:56-100): configure, setData(ms), fill the shared arrays, update(tst) -- against the
  * MOCK nextsim headers, linked with libnsdg_cuda.so.  Prints one line of results for tests/test_host_adapter.py.
- *   usage: cuda_module_driver mevp|bbm n nupdates
+ *   usage: cuda_module_driver mevp|bbm|freedrift n nupdates
  */
 #include "include/CUDADynamics.hpp"
 #include "include/gridNames.hpp"
@@ -67,6 +67,8 @@ int main(int argc, char** argv)
     std::unique_ptr<IDynamics> dyn;
     if (rheo == "bbm")
         dyn.reset(new CUDABBMDynamics());
+    else if (rheo == "freedrift")
+        dyn.reset(new CUDAFreeDriftDynamics());
     else {
         auto* m = new CUDAMEVPDynamics();
         m->configure();

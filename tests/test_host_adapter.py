@@ -1,4 +1,4 @@
-"""The C++ IDynamics modules (nextsimdg_b200/host/CUDADynamics.{hpp,cpp}) against MOCK nextsim headers:
+"""The C++ IDynamics modules (nextsimdg_b200/host/CUDADynamics.{hpp,cpp}) against MOCK nextsim headers (tests/host/mock):
 CPU: they compile (the real headers need Eigen/Boost/netCDF, absent here);
 GPU: a PrognosticData-style driver links libnsdg_cuda.so, runs setData + update and must reproduce the Python mirror."""
 import os
@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "nextsimdg_b200", "host")
-INC = ["-I", os.path.join(HOST, "mock", "include"), "-I", os.path.join(ROOT, "include")]
+INC = ["-I", os.path.join(ROOT, "tests", "host", "mock", "include"), "-I", os.path.join(ROOT, "include")]
 FLAGS = ["-std=c++17", "-DDGCOMP=6", "-DCGDEGREE=2", "-Wall"]
 
 
@@ -26,23 +26,62 @@ def test_cpp_modules_compile_against_the_reference_headers(tmp_path):
     ref = os.environ.get("NSDG_REFERENCE_ROOT", "/root/reference")
     if not os.path.isdir(os.path.join(ref, "core", "src", "modules", "include")):
         pytest.skip("reference tree not present")
-    inc = tmp_path / "include"
-    inc.mkdir()
-    (inc / "CUDADynamics.hpp").write_text(open(os.path.join(HOST, "CUDADynamics.hpp")).read())
     cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unknown-pragmas", "-DDGCOMP=6", "-DCGDEGREE=2", "-DDGSTRESSCOMP=8",
-           "-I", os.path.join(ROOT, "oracle", "mini_eigen"), "-I", os.path.join(ROOT, "oracle", "mini_boost"),
-           "-I", os.path.join(ROOT, "include"), "-I", str(tmp_path),
-           "-I", os.path.join(ref, "core", "src"), "-I", os.path.join(ref, "core", "src", "modules"),
-           "-I", os.path.join(ref, "physics", "src", "modules"), "-I", os.path.join(ref, "core", "src", "discontinuousgalerkin"),
-           "-I", os.path.join(ref, "dynamics", "src"), os.path.join(HOST, "CUDADynamics.cpp")]
+           *_reference_includes(ref, tmp_path), os.path.join(HOST, "CUDADynamics.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
 
 
+def _reference_includes(ref, tmp_path):
+    """include paths of the real nextsimdg headers + the adapter's headers laid out as in the nextsimdg tree (tmp/include/)"""
+    inc = tmp_path / "include"
+    inc.mkdir(exist_ok=True)
+    for name in ("CUDADynamics.hpp", "CUDAMEVPDynamics.hpp", "CUDABBMDynamics.hpp", "CUDAFreeDriftDynamics.hpp"):
+        (inc / name).write_text(open(os.path.join(HOST, name)).read())
+    return ["-I", os.path.join(ROOT, "oracle", "mini_eigen"), "-I", os.path.join(ROOT, "oracle", "mini_boost"),
+            "-I", os.path.join(ROOT, "include"), "-I", str(tmp_path),
+            "-I", os.path.join(ref, "core", "src"), "-I", os.path.join(ref, "core", "src", "modules"),
+            "-I", os.path.join(ref, "core", "src", "modules", "DynamicsModule"),
+            "-I", os.path.join(ref, "physics", "src", "modules"), "-I", os.path.join(ref, "core", "src", "discontinuousgalerkin"),
+            "-I", os.path.join(ref, "dynamics", "src")]
+
+
+def test_module_builder_registers_the_cuda_modules(tmp_path):
+    """The reference's OWN registration mechanism, run here: integration/module.cfg.patch is applied to a copy of
+    core/src/modules/DynamicsModule/module.cfg (module.cfg:16-27), the reference's scripts/module_builder.py:57-80 generates
+    the Module<IDynamics> table from it, and the generated translation unit -- which includes include/CUDAMEVPDynamics.hpp,
+    include/CUDABBMDynamics.hpp and include/CUDAFreeDriftDynamics.hpp next to the reference's own module headers -- is
+    type-checked against the real nextsimdg headers."""
+    import shutil
+    import sys
+
+    ref = os.environ.get("NSDG_REFERENCE_ROOT", "/root/reference")
+    builder = os.path.join(ref, "scripts", "module_builder.py")
+    if not os.path.exists(builder):
+        pytest.skip("reference tree not present")
+    work = tmp_path / "DynamicsModule"
+    work.mkdir()
+    shutil.copy(os.path.join(ref, "core", "src", "modules", "DynamicsModule", "module.cfg"), work / "module.cfg")
+    r = subprocess.run(["patch", "-p5", "-i", os.path.join(ROOT, "integration", "module.cfg.patch")], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, builder], cwd=work, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    gen = (work / "module.cpp").read_text()
+    for cls in ("CUDAMEVPDynamics", "CUDABBMDynamics", "CUDAFreeDriftDynamics"):
+        assert f'#include "include/{cls}.hpp"' in gen
+        assert f"newImpl<Nextsim::IDynamics, Nextsim::{cls}>" in gen
+        assert f'const std::string {cls.upper()} = "Nextsim::{cls}";' in gen
+    assert "return DYNAMICS::DUMMYDYNAMICS;" in gen.replace("IDYNAMICS", "DYNAMICS") or "DUMMYDYNAMICS" in gen  # the default is unchanged
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wno-unknown-pragmas", "-w", "-DDGCOMP=6", "-DCGDEGREE=2", "-DDGSTRESSCOMP=8",
+           *_reference_includes(ref, tmp_path), str(work / "module.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+@pytest.mark.parametrize("rheo", ["mevp", "bbm", "freedrift"])
 def test_cpp_module_reproduces_python_mirror(rheo, cuda_lib, tmp_path):
-    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, capi, synthetic
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAFreeDriftDynamics, CUDAMEVPDynamics, capi, synthetic
 
     exe = str(tmp_path / "driver")
     libdir = os.path.dirname(capi.library_path())
@@ -54,11 +93,11 @@ def test_cpp_module_reproduces_python_mirror(rheo, cuda_lib, tmp_path):
     out = subprocess.run([exe, rheo, str(n), str(nupd)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr + out.stdout
     line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0].split()
-    assert line[1] == ("CUDABBMDynamics" if rheo == "bbm" else "CUDAMEVPDynamics")
+    assert line[1] == {"bbm": "CUDABBMDynamics", "mevp": "CUDAMEVPDynamics", "freedrift": "CUDAFreeDriftDynamics"}[rheo]
     got = np.array([float(x) for x in line[2:]])
     ms = synthetic.benchmark_box(n)
     ms.pop("damage")
-    d = (CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics)()
+    d = {"bbm": CUDABBMDynamics, "mevp": CUDAMEVPDynamics, "freedrift": CUDAFreeDriftDynamics}[rheo]()
     d.setData(ms)
     d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
     if rheo == "bbm":
@@ -67,4 +106,5 @@ def test_cpp_module_reproduces_python_mirror(rheo, cuda_lib, tmp_path):
         d.shared.update(synthetic.benchmark_forcing(n, k * dt))
         d.update(dt)
     want = np.array([np.abs(d.uice).sum(), np.abs(d.vice).sum(), d.shared["hice"].sum(), np.abs(d.taux).sum()])
+    assert want[0] > 0
     assert np.allclose(got, want, rtol=1e-9), (got, want)

@@ -102,3 +102,79 @@ def test_ipc_handle_routing_over_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+# ---- the reference's partition metadata files ----
+REF = os.environ.get("NSDG_REFERENCE_ROOT", "/root/reference")
+# run/partition.cdl and core/test/partition_metadata_{2,3}.cdl, restated so that the test also runs where the reference tree is absent
+CDL_1 = """netcdf partition { dimensions: P = 1 ; L = 1 ; NX = 30 ; NY = 30 ;
+group: bounding_boxes { variables: int domain_x(P) ; data:
+ domain_x = 0 ; domain_y = 0 ; domain_extent_x = 30 ; domain_extent_y = 30 ; } }"""
+
+
+def _ref_text(rel, fallback=None):
+    path = os.path.join(REF, rel)
+    if os.path.exists(path):
+        return open(path).read()
+    if fallback is None:
+        pytest.skip("reference tree not present")
+    return fallback
+
+
+def test_reads_the_reference_single_box_partition_file():
+    from nextsimdg_b200.partition import PartitionFile
+
+    pf = PartitionFile.from_cdl(_ref_text("run/partition.cdl", CDL_1))
+    assert (pf.global_nx, pf.global_ny, pf.boxes) == (30, 30, [(0, 0, 30, 30)])
+    p = pf.partition(0)
+    assert (p.nx, p.ny, p.x0, p.y0, p.neighbour, p.lnx, p.lny) == (30, 30, 0, 0, [-1, -1, -1, -1], 30, 30)
+
+
+def test_reads_the_reference_two_box_partition_file():
+    """core/test/partition_metadata_2.cdl: boxes at domain_x = 0 and 4 of a 10 x 9 grid; the file's bottom / top are +x / -x."""
+    from nextsimdg_b200.partition import PartitionFile
+
+    pf = PartitionFile.from_cdl(_ref_text("core/test/partition_metadata_2.cdl"))
+    assert (pf.global_nx, pf.global_ny) == (10, 9) and pf.boxes == [(0, 0, 4, 9), (4, 0, 6, 9)]
+    assert pf.connectivity["bottom"] == [[(1, 9)], []] and pf.connectivity["top"] == [[], [(0, 9)]]
+    pf.check_connectivity()
+    p0, p1 = pf.partition(0), pf.partition(1)
+    assert p0.neighbour == [-1, 1, -1, -1] and p1.neighbour == [-1, -1, -1, 0]
+    assert (p0.lnx, p0.lny, p1.lx0, p1.lnx) == (5, 9, 3, 7)
+    cfg_fields = {}
+
+    class Cfg:
+        neighbour = [0, 0, 0, 0]
+
+    c = Cfg()
+    p1.fill_config(c)
+    assert (c.global_nx, c.global_ny, c.box_x0, c.box_y0, c.rank, c.nranks, c.neighbour) == (10, 9, 4, 0, 1, 2, [-1, -1, -1, 0])
+    del cfg_fields
+
+
+def test_reads_the_reference_three_box_partition_file():
+    """core/test/partition_metadata_3.cdl:28-66: box 2 faces TWO boxes across one side -- parsed and cross-checked exactly,
+    but refused as a device partition (one neighbour per side)."""
+    from nextsimdg_b200.partition import LEFT, PartitionFile
+
+    pf = PartitionFile.from_cdl(_ref_text("core/test/partition_metadata_3.cdl"))
+    assert (pf.global_nx, pf.global_ny) == (5, 7)
+    assert pf.boxes == [(0, 0, 3, 3), (0, 3, 3, 4), (3, 0, 2, 7)]
+    assert pf.connectivity["top"][2] == [(0, 3), (1, 4)] and pf.connectivity["right"][0] == [(1, 3)]
+    pf.check_connectivity()
+    assert sorted(pf.neighbours_geometric(2)[LEFT]) == [(0, 3), (1, 4)]
+    with pytest.raises(ValueError):
+        pf.partition(2)
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_partition_file_round_trip_of_the_regular_box_grids(nranks):
+    from nextsimdg_b200.partition import PartitionFile, write_partition_cdl
+
+    parts = [Partition.strong(r, nranks, 64, 32) for r in range(nranks)]
+    pf = PartitionFile.from_cdl(write_partition_cdl(parts))
+    pf.check_connectivity()
+    for r, want in enumerate(parts):
+        got = pf.partition(r)
+        for k in ("nx", "ny", "x0", "y0", "neighbour", "ring", "lx0", "ly0", "lnx", "lny", "global_nx", "global_ny", "nranks"):
+            assert getattr(got, k) == getattr(want, k), (r, k)
