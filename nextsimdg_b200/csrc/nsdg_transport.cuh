@@ -336,7 +336,10 @@ struct TransportStageArgs {
 };
 
 #ifndef NSDG_TRANSPORT_MINB
-#define NSDG_TRANSPORT_MINB 1 //!< minimum resident blocks per SM asked of the compiler (register cap): tuning knob
+#define NSDG_TRANSPORT_MINB 4 //!< resident blocks per SM asked of the compiler (128 registers): the kernel is latency bound, occupancy pays
+#endif
+#ifndef NSDG_TRANSPORT_SHFL
+#define NSDG_TRANSPORT_SHFL 1 //!< left / right neighbour traces by warp shuffle (0: load the neighbour's coefficients)
 #endif
 template <int DG>
 __global__ void __launch_bounds__(128, NSDG_TRANSPORT_MINB) transport_stage_kernel(const __grid_constant__ TransportStageArgs a)
@@ -356,241 +359,217 @@ __global__ void __launch_bounds__(128, NSDG_TRANSPORT_MINB) transport_stage_kern
     const size_t Npad = g.Npad;
     const double dt = a.dt;
     const bool ice = isIce(a.landmask, e);
-    const uint8_t dm = a.dirmask[e];
-    const size_t eo = e * a.op.estride;
-
-    // ---- shared by the fields: neighbours, velocities ----
-    // side: 0 bottom, 1 right, 2 top, 3 left
-    long nb[4]; // plane index of the element across each side, -1: none (domain edge, land on either side)
-    long edgeId[4];
-    bool per[4] = { false, false, false, false };
-    {
-        const int nix[4] = { ix, ix + 1, ix, ix - 1 }, niy[4] = { iy - 1, iy, iy + 1, iy };
+    const double* __restrict__ phi = a.in[f];
+    const double* __restrict__ velx = a.velx;
+    const double* __restrict__ vely = a.vely;
+    const double* __restrict__ nvX = a.nvX;
+    const double* __restrict__ nvY = a.nvY;
+    double up[DG];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const bool inside = nix[s] >= 0 && nix[s] < g.nx && niy[s] >= 0 && niy[s] < g.ny;
-            nb[s] = inside ? long(size_t(niy[s]) * g.nxs + nix[s]) : -1;
-            edgeId[s] = (s == 0 || s == 2) ? long(size_t(s == 2 ? iy + 1 : iy) * g.nx + ix) : long(size_t(iy) * (g.nx + 1) + (s == 1 ? ix + 1 : ix));
-            if (!inside && a.perNbr != nullptr) {
-                const int pn = a.perNbr[size_t(s) * Npad + e];
-                if (pn >= 0) {
-                    nb[s] = pn;
-                    edgeId[s] = a.perEdge[size_t(s) * Npad + e];
-                    per[s] = true;
-                }
-            }
-            if (nb[s] >= 0 && !(ice && isIce(a.landmask, size_t(nb[s]))))
-                nb[s] = -1; // edge_term_X/Y return when either element is land (DGTransport.cpp:395-398)
-        }
-    }
-    double vxg[Q], vyg[Q];
+    for (int j = 0; j < DG; ++j)
+        up[j] = 0.0;
+    double ph[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        ph[j] = phi[size_t(j) * Npad + e];
+
+    const size_t eo = e * a.op.estride;
+    // ---- cell term (DGTransport.cpp:278-303) ----
     if (DG > 1 && ice) {
+        double vxg[Q], vyg[Q], pg[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
-            vxg[q] = vyg[q] = 0.0;
+            vxg[q] = vyg[q] = pg[q] = 0.0;
 #pragma unroll
         for (int j = 0; j < DG; ++j) {
-            const double vxj = a.velx[size_t(j) * Npad + e], vyj = a.vely[size_t(j) * Npad + e];
+            const double vxj = velx[size_t(j) * Npad + e], vyj = vely[size_t(j) * Npad + e];
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const double w = PSI(G, j, q);
                 if (w != 0.0) {
                     vxg[q] = fma(vxj, w, vxg[q]);
                     vyg[q] = fma(vyj, w, vyg[q]);
+                    pg[q] = fma(ph[j], w, pg[q]);
                 }
             }
         }
-    }
-    // normal velocity in the edge Gauss points of my four sides (also needed on Dirichlet sides)
-    double vge[4][G];
+        if (G == 3 && a.geo != nullptr) {
+            // AdvectionCellTermX/Y (ParametricMap.cpp:13-66) are w (PSIx dyT_1 - PSIy dxT_1) and w (PSIy dxT_0 - PSIx dyT_0):
+            // formed from the 12 element-map values of the factored-operator path (nsdg_momentum_param.cuh, planes 0..11)
+            // instead of streaming 2 x DG x 9 doubles per element
+            double m[12];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const bool need = (nb[s] >= 0) || (dm & (1 << s));
-        double nv[ED];
+            for (int k = 0; k < 12; ++k)
+                m[k] = __ldg(a.geo + size_t(k) * Npad + e);
+            double aq[Q], bq[Q];
 #pragma unroll
-        for (int k = 0; k < ED; ++k)
-            nv[k] = need ? ((s == 0 || s == 2) ? a.nvX[size_t(k) * a.pitchX + edgeId[s]] : a.nvY[size_t(k) * a.pitchY + edgeId[s]]) : 0.0;
-#pragma unroll
-        for (int q = 0; q < G; ++q) {
-            double v = 0;
-#pragma unroll
-            for (int k = 0; k < ED; ++k)
-                v += nv[k] * PSIe(G, k, q);
-            vge[s][q] = v;
-        }
-    }
-    // cell-term weights that do not depend on the field (factored path: element map x velocity in the Gauss points)
-    double cwa[Q], cwb[Q];
-    const bool factored = (G == 3) && a.geo != nullptr;
-    if (DG > 1 && ice && factored) {
-        // AdvectionCellTermX/Y (ParametricMap.cpp:13-66) are w (PSIx dyT_1 - PSIy dxT_1) and w (PSIy dxT_0 - PSIx dyT_0):
-        // formed from the 12 element-map values of the factored-operator path (nsdg_momentum_param.cuh, planes 0..11)
-        double m[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k)
-            m[k] = __ldg(a.geo + size_t(k) * Npad + e);
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int qx = q % 3, qy = q / 3;
-            const double w = dt * gaussweight2(3, q);
-            cwa[q] = w * (m[9 + qx] * vxg[q] - m[6 + qx] * vyg[q]); // yeta vx - xeta vy
-            cwb[q] = w * (m[0 + qy] * vyg[q] - m[3 + qy] * vxg[q]); // xxi vy - yxi vx
-        }
-    }
-
-    // the warp-edge lanes and periodic seams cannot shuffle: they read the neighbour's coefficients
-    const bool shflLeft = lane > 0 && !per[3], shflRight = lane < 31 && ixRaw + 1 < g.nx && !per[1];
-
-    {
-        const double* __restrict__ phi = a.in[f];
-        double ph[DG], up[DG];
-#pragma unroll
-        for (int j = 0; j < DG; ++j) {
-            ph[j] = phi[size_t(j) * Npad + e];
-            up[j] = 0.0;
-        }
-        // ---- cell term (DGTransport.cpp:278-303) ----
-        if (DG > 1 && ice) {
-            double pg[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q)
-                pg[q] = 0.0;
-#pragma unroll
-            for (int j = 0; j < DG; ++j)
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const double w = PSI(G, j, q);
-                    if (w != 0.0)
-                        pg[q] = fma(ph[j], w, pg[q]);
-                }
-            if (factored) {
-#pragma unroll
-                for (int j = 0; j < DG; ++j) {
-                    double s = 0;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        const double px = PSIx(G, j, q), py = PSIy(G, j, q);
-                        if (px != 0.0)
-                            s = fma(px, cwa[q] * pg[q], s);
-                        if (py != 0.0)
-                            s = fma(py, cwb[q] * pg[q], s);
-                    }
-                    up[j] += s;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < DG; ++j) {
-                    double s = 0;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        const double ax = __ldg(a.op.AdvX + (j * Q + q) * a.op.pitch + eo);
-                        const double ay = __ldg(a.op.AdvY + (j * Q + q) * a.op.pitch + eo);
-                        s += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
-                    }
-                    up[j] += s;
-                }
+            for (int q = 0; q < Q; ++q) {
+                const int qx = q % 3, qy = q / 3;
+                const double wp = (dt * gaussweight2(3, q)) * pg[q];
+                aq[q] = wp * (m[9 + qx] * vxg[q] - m[6 + qx] * vyg[q]); // yeta vx - xeta vy
+                bq[q] = wp * (m[0 + qy] * vyg[q] - m[3 + qy] * vxg[q]); // xxi vy - yxi vx
             }
-        }
-        // ---- traces: mine on the four sides, the neighbours' on the facing sides ----
-        double tme[4][ED], tnb[4][ED];
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-            edgeofcell<DG>([&](int k) { return ph[k]; }, s, tme[s]);
-#pragma unroll
-        for (int k = 0; k < ED; ++k) { // my left neighbour's right trace, my right neighbour's left trace
-            tnb[3][k] = __shfl_up_sync(FULL, tme[1][k], 1);
-            tnb[1][k] = __shfl_down_sync(FULL, tme[3][k], 1);
-        }
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const bool viaShfl = (s == 3 && shflLeft) || (s == 1 && shflRight);
-            if (nb[s] >= 0 && !viaShfl) {
-                const size_t en = size_t(nb[s]);
-                edgeofcell<DG>([&](int k) { return phi[size_t(k) * Npad + en]; }, (s + 2) & 3, tnb[s]);
-            }
-        }
-        // ---- edge fluxes (DGTransport.cpp:390-433), reference order: left, right, bottom, top; periodic ones after them ----
-        auto edgeFlux = [&](int s) {
-            // c1 = left / bottom element of the edge, c2 = right / top element
-            const bool meFirst = (s == 1 || s == 2);
-            double tmp[G];
-#pragma unroll
-            for (int q = 0; q < G; ++q) {
-                double g1 = 0, g2 = 0;
-#pragma unroll
-                for (int k = 0; k < ED; ++k) {
-                    g1 += (meFirst ? tme[s][k] : tnb[s][k]) * PSIe(G, k, q);
-                    g2 += (meFirst ? tnb[s][k] : tme[s][k]) * PSIe(G, k, q);
-                }
-                tmp[q] = fmax(vge[s][q], 0.) * g1 + fmin(vge[s][q], 0.) * g2;
-            }
-            const double sdt = meFirst ? -dt : dt;
 #pragma unroll
             for (int j = 0; j < DG; ++j) {
                 double acc = 0;
 #pragma unroll
-                for (int q = 0; q < G; ++q)
-                    acc += (sdt * tmp[q]) * (s == 0 ? PSIew(G, 0, q, j) : s == 1 ? PSIew(G, 1, q, j) : s == 2 ? PSIew(G, 2, q, j) : PSIew(G, 3, q, j));
+                for (int q = 0; q < Q; ++q) {
+                    const double px = PSIx(G, j, q), py = PSIy(G, j, q);
+                    if (px != 0.0)
+                        acc = fma(px, aq[q], acc);
+                    if (py != 0.0)
+                        acc = fma(py, bq[q], acc);
+                }
                 up[j] += acc;
             }
-        };
-        const int order[4] = { 3, 1, 0, 2 };
+        } else {
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) // pass 0: interior edges, pass 1: periodic edges
+            for (int j = 0; j < DG; ++j) {
+                double acc = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int s = order[i];
-                if (nb[s] >= 0 && per[s] == (pass == 1))
-                    edgeFlux(s);
+                for (int q = 0; q < Q; ++q) {
+                    const double ax = __ldg(a.op.AdvX + (j * Q + q) * a.op.pitch + eo);
+                    const double ay = __ldg(a.op.AdvY + (j * Q + q) * a.op.pitch + eo);
+                    acc += (dt * (ax * vxg[q] + ay * vyg[q])) * pg[q];
+                }
+                up[j] += acc;
             }
-        // ---- Dirichlet edges: outflow only (DGTransport.cpp:306-351), sides in list order 0,1,2,3 ----
-        if (dm) {
+        }
+    }
+    // ---- edges (DGTransport.cpp:390-433, :466-481).  side: 0 bottom, 1 right, 2 top, 3 left; reference order of the
+    //      accumulation: left, right, bottom, top, then the periodic ones.  `shfl`: the neighbour's trace arrives from the
+    //      adjacent lane (all lanes take part in the shuffle, whether or not they have such an edge) ----
+    auto edgeFlux = [&](int side, bool wantPeriodic) {
+        const int nix = ix + (side == 1 ? 1 : (side == 3 ? -1 : 0));
+        const int niy = iy + (side == 2 ? 1 : (side == 0 ? -1 : 0));
+        const bool inside = nix >= 0 && nix < g.nx && niy >= 0 && niy < g.ny;
+        long en = inside ? long(size_t(niy) * g.nxs + nix) : -1;
+        long ie = (side == 0 || side == 2) ? long(size_t(side == 2 ? iy + 1 : iy) * g.nx + ix) : long(size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix));
+        bool periodic = false;
+        if (!inside && a.perNbr != nullptr) {
+            const int pn = a.perNbr[size_t(side) * Npad + e];
+            if (pn >= 0) {
+                en = pn;
+                ie = a.perEdge[size_t(side) * Npad + e];
+                periodic = true;
+            }
+        }
+        double tme[ED], tnb[ED];
+        edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
+        bool viaShfl = false;
+#if NSDG_TRANSPORT_SHFL
+        if (!wantPeriodic && (side == 1 || side == 3)) { // uniform across the warp: every lane shuffles
+            double mine[ED];
+            edgeofcell<DG>([&](int k) { return ph[k]; }, (side + 2) & 3, mine); // what the neighbour on `side` wants from me is my trace on the opposite side
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (!(dm & (1 << s)))
-                    continue;
-                const double sg = (s == 0 || s == 3) ? -1.0 : 1.0;
-                double tmp[G];
+            for (int k = 0; k < ED; ++k)
+                tnb[k] = side == 3 ? __shfl_up_sync(FULL, mine[k], 1) : __shfl_down_sync(FULL, mine[k], 1);
+            viaShfl = side == 3 ? (lane > 0) : (lane < 31 && ixRaw + 1 < g.nx);
+        }
+#endif
+        if (en < 0 || periodic != wantPeriodic || !ice || !isIce(a.landmask, size_t(en)))
+            return; // edge_term_X/Y return when either element is land (DGTransport.cpp:395-398)
+        // c1 = left/bottom element, c2 = right/top element of the edge
+        const bool meFirst = (side == 1 || side == 2);
+        double nv[ED];
 #pragma unroll
+        for (int k = 0; k < ED; ++k)
+            nv[k] = (side == 0 || side == 2) ? nvX[size_t(k) * a.pitchX + ie] : nvY[size_t(k) * a.pitchY + ie];
+        if (!viaShfl)
+            edgeofcell<DG>([&](int k) { return phi[size_t(k) * Npad + size_t(en)]; }, (side + 2) & 3, tnb);
+        double tmp[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) {
+            double vg = 0, g1 = 0, g2 = 0;
+#pragma unroll
+            for (int k = 0; k < ED; ++k) {
+                vg += nv[k] * PSIe(G, k, q);
+                g1 += (meFirst ? tme[k] : tnb[k]) * PSIe(G, k, q);
+                g2 += (meFirst ? tnb[k] : tme[k]) * PSIe(G, k, q);
+            }
+            tmp[q] = fmax(vg, 0.) * g1 + fmin(vg, 0.) * g2;
+        }
+        const double sdt = meFirst ? -dt : dt;
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            double acc = 0;
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                acc += (sdt * tmp[q]) * PSIew(G, side, q, j);
+            up[j] += acc;
+        }
+    };
+    edgeFlux(3, false);
+    edgeFlux(1, false);
+    edgeFlux(0, false);
+    edgeFlux(2, false);
+    if (a.perNbr != nullptr) {
+        edgeFlux(3, true);
+        edgeFlux(1, true);
+        edgeFlux(0, true);
+        edgeFlux(2, true);
+    }
+    // ---- Dirichlet edges: outflow only (DGTransport.cpp:306-351), sides in list order 0,1,2,3 ----
+    const uint8_t dm = a.dirmask[e];
+    if (dm)
+        for (int side = 0; side < 4; ++side) {
+            if (!(dm & (1 << side)))
+                continue;
+            double nv[ED];
+            if (side == 0 || side == 2) {
+                const size_t ie = size_t(side == 2 ? iy + 1 : iy) * g.nx + ix;
+                for (int k = 0; k < ED; ++k)
+                    nv[k] = nvX[size_t(k) * a.pitchX + ie];
+            } else {
+                const size_t ie = size_t(iy) * (g.nx + 1) + (side == 1 ? ix + 1 : ix);
+                for (int k = 0; k < ED; ++k)
+                    nv[k] = nvY[size_t(k) * a.pitchY + ie];
+            }
+            double tme[ED];
+            edgeofcell<DG>([&](int k) { return ph[k]; }, side, tme);
+            const double sg = (side == 0 || side == 3) ? -1.0 : 1.0;
+            double tmp[G];
+            for (int q = 0; q < G; ++q) {
+                double vg = 0, g1 = 0;
+                for (int k = 0; k < ED; ++k) {
+                    vg += nv[k] * PSIe(G, k, q);
+                    g1 += tme[k] * PSIe(G, k, q);
+                }
+                tmp[q] = g1 * fmax(sg * vg, 0.);
+            }
+            for (int j = 0; j < DG; ++j) {
+                double acc = 0;
                 for (int q = 0; q < G; ++q) {
-                    double g1 = 0;
-#pragma unroll
-                    for (int k = 0; k < ED; ++k)
-                        g1 += tme[s][k] * PSIe(G, k, q);
-                    tmp[q] = g1 * fmax(sg * vge[s][q], 0.);
+                    const double w = side == 0 ? PSIew(G, 0, q, j)
+                        : side == 1            ? PSIew(G, 1, q, j)
+                        : side == 2            ? PSIew(G, 2, q, j)
+                                               : PSIew(G, 3, q, j);
+                    acc += (-dt * tmp[q]) * w;
                 }
-#pragma unroll
-                for (int j = 0; j < DG; ++j) {
-                    double acc = 0;
-#pragma unroll
-                    for (int q = 0; q < G; ++q)
-                        acc += (-dt * tmp[q]) * (s == 0 ? PSIew(G, 0, q, j) : s == 1 ? PSIew(G, 1, q, j) : s == 2 ? PSIew(G, 2, q, j) : PSIew(G, 3, q, j));
-                    up[j] += acc;
-                }
+                up[j] += acc;
             }
         }
-        // ---- inverse mass (DGTransport.cpp:509-511), Runge-Kutta epilogue, limiter ----
-        double res[DG];
+    // ---- inverse mass (DGTransport.cpp:509-511), Runge-Kutta epilogue, limiter ----
+    double res[DG];
 #pragma unroll
-        for (int i = 0; i < DG; ++i) {
-            double k = 0;
+    for (int i = 0; i < DG; ++i) {
+        double k = 0;
 #pragma unroll
-            for (int j = 0; j < DG; ++j)
-                k += __ldg(a.op.iMass + (i * DG + j) * a.op.pitch + eo) * up[j];
-            if (a.epi == 0)
-                res[i] = ph[i] + k;
-            else {
-                const double b = a.base[f][size_t(i) * Npad + e];
-                res[i] = a.epi == 1 ? ph[i] + 0.5 * (k - (ph[i] - b)) : a.c1 * (ph[i] + k) + a.c0 * b;
-            }
+        for (int j = 0; j < DG; ++j)
+            k += __ldg(a.op.iMass + (i * DG + j) * a.op.pitch + eo) * up[j];
+        if (a.epi == 0)
+            res[i] = ph[i] + k;
+        else {
+            const double b = a.base[f][size_t(i) * Npad + e];
+            res[i] = a.epi == 1 ? ph[i] + 0.5 * (k - (ph[i] - b)) : a.c1 * (ph[i] + k) + a.c0 * b;
         }
-        if (a.limitMode[f])
-            limitDG<DG>(res, a.limitMode[f], a.maxv[f], a.minv[f]);
-        if (active) {
+    }
+    if (a.limitMode[f])
+        limitDG<DG>(res, a.limitMode[f], a.maxv[f], a.minv[f]);
+    if (active) {
 #pragma unroll
-            for (int i = 0; i < DG; ++i)
-                a.out[f][size_t(i) * Npad + e] = res[i];
-        }
+        for (int i = 0; i < DG; ++i)
+            a.out[f][size_t(i) * Npad + e] = res[i];
     }
 }
 
