@@ -124,9 +124,8 @@ public:
     DevBuf<unsigned char> arena; //!< my receive arena: [side][parity] payload slots + flags
     HaloArenaLayout arenaLayout {};
     unsigned char* peerArena[kHaloSides] = { nullptr, nullptr, nullptr, nullptr }; //!< IPC-mapped neighbour arenas
-    unsigned sideEpoch[kHaloSides] = { 0, 0, 0, 0 };
     DevBuf<int> haloError;
-    DevBuf<unsigned> haloDone;
+    DevBuf<HaloDevState> haloState; //!< exchange epochs and block counters, advanced on the device
     bool haloActive = false;
     // staging
     DevBuf<double> staging;
@@ -471,9 +470,7 @@ public:
             arenaLayout.slotDoubles = alignUp(size_t(6) * std::max(g.cgnx, g.cgny) + 64, 64);
             arena.alloc(arenaLayout.totalBytes());
             haloError.alloc(1);
-            haloDone.alloc(kHaloSides);
-            for (auto& e : sideEpoch)
-                e = 0;
+            haloState.alloc(1); // zeroed: epochs restart with a new arena
         }
         meshSet = true;
     }
@@ -743,43 +740,33 @@ public:
         if (!haloActive)
             return;
         const int phases[2] = { (1 << NSDG_LEFT) | (1 << NSDG_RIGHT), (1 << NSDG_BOTTOM) | (1 << NSDG_TOP) };
-        const int opposite[4] = { NSDG_TOP, NSDG_LEFT, NSDG_BOTTOM, NSDG_RIGHT };
         for (int ph = 0; ph < 2; ++ph) {
             bool any = false;
             for (int s = 0; s < kHaloSides; ++s)
                 any = any || ((phases[ph] & (1 << s)) && hasNeighbour(s));
             if (!any)
                 continue;
-            HaloPushArgs pa {};
-            HaloUnpackArgs ua {};
-            for (int f = 0; f < nFields && f < 8; ++f) {
-                pa.fields[f] = pitch ? nullptr : fields[f];
-                ua.fields[f] = pitch ? nullptr : fields[f];
-            }
-            pa.fields[0] = ua.fields[0] = fields[0];
-            pa.fieldPitch = ua.fieldPitch = pitch;
-            pa.sideMask = ua.sideMask = phases[ph];
-            ua.errorFlag = haloError;
+            HaloExchangeArgs xa {};
+            for (int f = 0; f < nFields && f < 8; ++f)
+                xa.fields[f] = pitch ? nullptr : fields[f];
+            xa.fields[0] = fields[0];
+            xa.fieldPitch = pitch;
+            xa.sideMask = phases[ph];
+            xa.errorFlag = haloError;
+            xa.state = haloState;
+            xa.myArena = reinterpret_cast<double*>(arena.p);
+            xa.layout = arenaLayout;
             for (int s = 0; s < kHaloSides; ++s) {
                 if (!(phases[ph] & (1 << s)) || !hasNeighbour(s))
                     continue;
-                const unsigned epoch = ++sideEpoch[s];
-                const int parity = int(epoch & 1u);
-                pa.send[s] = nodes ? nodeLines(s, true, nFields, deg) : elemLines(s, true, nFields);
-                ua.recv[s] = nodes ? nodeLines(s, false, nFields, deg) : elemLines(s, false, nFields);
-                // my message lands in the neighbour's slot for ITS side facing me
-                const int os = opposite[s];
-                pa.peerSlot[s] = reinterpret_cast<double*>(peerArena[s]) + arenaLayout.slotOffset(os, parity);
-                pa.peerFlag[s] = reinterpret_cast<unsigned*>(peerArena[s] + arenaLayout.flagsOffsetBytes()) + os;
-                pa.epoch[s] = epoch;
-                ua.mySlot[s] = reinterpret_cast<const double*>(arena.p) + arenaLayout.slotOffset(s, parity);
-                ua.myFlag[s] = reinterpret_cast<const unsigned*>(arena.p + arenaLayout.flagsOffsetBytes()) + s;
-                ua.epoch[s] = epoch;
+                xa.send[s] = nodes ? nodeLines(s, true, nFields, deg) : elemLines(s, true, nFields);
+                xa.recv[s] = nodes ? nodeLines(s, false, nFields, deg) : elemLines(s, false, nFields);
+                xa.peerArena[s] = reinterpret_cast<double*>(peerArena[s]);
             }
-            pa.done = haloDone;
-            halo_push_kernel<<<dim3(kHaloBlocksPerSide, kHaloSides), 256, 0, stream>>>(pa);
-            halo_unpack_kernel<<<dim3(kHaloBlocksPerSide, kHaloSides), 256, 0, stream>>>(ua);
-            launches += 2;
+            // the exchange epoch is device state advanced by the kernel: the arguments are the same for every exchange of
+            // these fields, so the launch can be captured in the subcycle graph
+            halo_exchange_kernel<<<dim3(2 * kHaloBlocksPerSide, kHaloSides), 256, 0, stream>>>(xa);
+            launches += 1;
         }
     }
     void exchangeNodes(double* a, double* b)
@@ -799,7 +786,7 @@ public:
         exchange(f, ncomp, g.Npad, false);
     }
     //! Called after the final stream synchronisation of every entry point that exchanges halos: a box whose neighbour
-    //! never delivered (halo_unpack_kernel's wall-clock timeout) has NOT unpacked, so its ring holds stale data and the
+    //! never delivered (the wall-clock timeout of halo_exchange_kernel) has NOT unpacked, so its ring holds stale data and the
     //! call must fail instead of returning success.  The flag is cleared once reported.
     void checkHaloError()
     {
@@ -830,7 +817,13 @@ public:
     {
         a.nf = nf;
         const dim3 grid(unsigned((g.nx + 127) / 128) * nf, g.ny);
-        transport_stage_kernel<DG><<<grid, 128, 0, stream>>>(a);
+        if (uniform && !std::getenv("NSDG_NO_UNIFORM_TRANSPORT")) {
+            a.dxU = hvx[1] - hvx[0];
+            a.dyU = hvy[g.nx + 1] - hvy[0];
+            a.iAreaU = 1.0 / (a.dxU * a.dyU);
+            transport_stage_kernel<DG, true><<<grid, 128, 0, stream>>>(a);
+        } else
+            transport_stage_kernel<DG, false><<<grid, 128, 0, stream>>>(a);
         launches += 1;
     }
     struct LimitSpec {
@@ -1278,6 +1271,7 @@ public:
 
     void runSubcycles(int n, double deltaT)
     {
+        const long launchesBefore = launches;
         ensureConstOps();
         const SubcycleArgs a = makeArgs(deltaT);
         const UniformArgs ua = makeUniformArgs(deltaT);
@@ -1354,8 +1348,8 @@ public:
             launches += 4L * n;
             return;
         }
-        // the exchange epochs are kernel arguments, so a partitioned box replays plain launches
-        if (cfg.use_cuda_graph && n > 1 && !haloActive) {
+        // partitioned boxes too: the exchange epochs are device state, the launch arguments never change
+        if (cfg.use_cuda_graph && n > 1) {
             if (!graphExec || graphN != n || graphDeltaT != deltaT) {
                 if (graphExec) {
                     cudaGraphExecDestroy(graphExec);
@@ -1375,7 +1369,10 @@ public:
             body();
         }
         NSDG_CUDA_CHECK(cudaGetLastError());
-        launches += 2L * n;
+        // kernels per subcycle: strip + lines + one exchange kernel per active phase (a graph replay runs them without
+        // passing through exchange(), which counts only at capture time)
+        const int phasesActive = haloActive ? (hasNeighbour(NSDG_LEFT) || hasNeighbour(NSDG_RIGHT) ? 1 : 0) + (hasNeighbour(NSDG_BOTTOM) || hasNeighbour(NSDG_TOP) ? 1 : 0) : 0;
+        launches = launchesBefore + long(n) * (2 + phasesActive);
     }
 
     void subcycles(int n, float* ms) override

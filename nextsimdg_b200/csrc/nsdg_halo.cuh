@@ -8,12 +8,15 @@
  *     neighbour, 3 from the right/top one: the right/top box owns the shared boundary line);
  *   - every transport RK stage: the ring column/row of the advected DG field.
  * Mechanism: each box exposes one "arena" (per side: two parity slots of payload + one flag) through a CUDA
- * IPC handle.  The sender's kernel packs its lines straight into the RECEIVER's arena with plain stores
- * through the peer mapping, then releases a system-scope flag carrying the exchange epoch; the receiver's
- * kernel acquires the flag and unpacks.  Two parity slots make the scheme race-free without
- * acknowledgements: slot (epoch % 2) is rewritten only after the receiver has unpacked epoch - 2, which it
- * must have done before it could send the epoch - 1 message the sender waited for.  x-direction first, then y
- * over the full local width, so corner values arrive by two hops.
+ * IPC handle.  ONE kernel per phase (halo_exchange_kernel): its push blocks pack the box's lines straight into the
+ * RECEIVER's arena with plain stores through the peer mapping, then release a system-scope flag carrying the
+ * exchange epoch; its unpack blocks acquire the box's own flag and scatter what the neighbour delivered (the lines
+ * sent and the lines received are disjoint).  The epoch lives in DEVICE memory and is advanced by the kernel
+ * itself, so the launch arguments never change and the whole subcycle loop of a partitioned box replays as one
+ * CUDA graph.  Two parity slots make the scheme race-free without acknowledgements: slot (epoch % 2) is rewritten
+ * only by the kernel of epoch + 2, which starts after this box has waited for the neighbour's epoch + 1 message,
+ * which the neighbour sent from a kernel that started after its unpack of this epoch had finished.  x-direction
+ * first, then y over the full local width, so corner values arrive by two hops.
  */
 #pragma once
 #include "nsdg_state.cuh"
@@ -61,95 +64,108 @@ struct HaloLineDesc {
     long stride; //!< distance between consecutive entries of a line
 };
 
-struct HaloPushArgs {
-    double* fields[8];
-    size_t fieldPitch; //!< DG planes: distance between planes when fields[1..] are not given (0 = use fields[])
-    HaloLineDesc send[kHaloSides];
-    double* peerSlot[kHaloSides]; //!< mapped pointer to the neighbour's slot for THIS exchange's parity (nullptr: no neighbour)
-    unsigned* peerFlag[kHaloSides];
-    unsigned epoch[kHaloSides];
-    int sideMask; //!< which sides take part in this phase (x: left|right, y: bottom|top)
-    unsigned* done; //!< [kHaloSides] block-completion counters in MY memory (zero between launches)
-};
-
 constexpr int kHaloBlocksPerSide = 24;
 
-//! grid = (blocks per side, 4 sides).  Packs the lines into the neighbour's arena; the last block of a side
-//! to finish publishes the epoch.
-__global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ HaloPushArgs a)
-{
-    const int side = blockIdx.y;
-    if (!(a.sideMask & (1 << side)) || a.peerSlot[side] == nullptr)
-        return;
-    const HaloLineDesc& d = a.send[side];
-    const long perField = long(d.nLines) * d.lineLen;
-    const long total = perField * d.nFields;
-    double* dst = a.peerSlot[side];
-    for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-        const int f = int(i / perField);
-        const long r = i % perField;
-        const int line = int(r / d.lineLen);
-        const long k = r % d.lineLen;
-        const double* src = a.fieldPitch ? a.fields[0] + size_t(f) * a.fieldPitch : a.fields[f];
-        dst[i] = src[d.firstLine[line] + k * d.stride];
-    }
-    __threadfence_system(); // my peer stores are visible system-wide before I report completion
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(a.done + side, 1u);
-        if (prev == gridDim.x - 1) { // every block of this side has fenced its stores
-            a.done[side] = 0;
-            __threadfence_system();
-            stReleaseSys(a.peerFlag[side], a.epoch[side]);
-        }
-    }
-}
-
-struct HaloUnpackArgs {
-    double* fields[8];
-    size_t fieldPitch;
-    HaloLineDesc recv[kHaloSides];
-    const double* mySlot[kHaloSides]; //!< my own arena slot of this parity (nullptr: no neighbour)
-    const unsigned* myFlag[kHaloSides];
-    unsigned epoch[kHaloSides];
-    int sideMask;
-    int* errorFlag; //!< set to 1 if a neighbour never showed up (spin timeout)
+//! device-resident exchange state of a box (zero-initialised)
+struct HaloDevState {
+    unsigned epoch[kHaloSides]; //!< exchanges completed per side
+    unsigned pushed[kHaloSides]; //!< push blocks of the running kernel that have fenced their stores
+    unsigned finished[kHaloSides]; //!< blocks (push and unpack) of the running kernel that are done
 };
 
-//! grid = (blocks per side, 4 sides).  Waits until the neighbour's message of this epoch has landed, then scatters it.
-__global__ void __launch_bounds__(256) halo_unpack_kernel(const __grid_constant__ HaloUnpackArgs a)
+struct HaloExchangeArgs {
+    double* fields[8];
+    size_t fieldPitch; //!< DG planes: distance between planes when fields[1..] are not given (0 = use fields[])
+    HaloLineDesc send[kHaloSides], recv[kHaloSides];
+    double* peerArena[kHaloSides]; //!< mapped base of the neighbour's arena (nullptr: no neighbour)
+    double* myArena;
+    HaloArenaLayout layout;
+    int sideMask; //!< which sides take part in this phase (x: left|right, y: bottom|top)
+    HaloDevState* state;
+    int* errorFlag; //!< set to 1 if a neighbour never showed up (wall-clock timeout)
+};
+
+//! grid = (2 * kHaloBlocksPerSide, 4 sides): blocks [0, B) push to the neighbour across the side, blocks [B, 2B) wait for
+//! and unpack what that neighbour pushed.  All blocks are resident at once (192 blocks of 256 threads), so the waiting
+//! unpack blocks cannot starve the push blocks.
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const __grid_constant__ HaloExchangeArgs a)
 {
     const int side = blockIdx.y;
-    if (!(a.sideMask & (1 << side)) || a.mySlot[side] == nullptr)
+    if (!(a.sideMask & (1 << side)) || a.peerArena[side] == nullptr)
         return;
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        ok = 1;
-        const unsigned long long t0 = globalTimerNs();
-        // flags only ever grow: >= tolerates a neighbour that is already one phase ahead
-        while (int(ldAcquireSys(a.myFlag[side]) - a.epoch[side]) < 0) {
-            if (globalTimerNs() - t0 > kHaloTimeoutNs) { // wall clock, independent of the SM clock: the neighbour died; do not hang the GPU
-                ok = 0;
-                *a.errorFlag = 1;
-                break;
+    const int opposite = (side + 2) & 3;
+    const unsigned epoch = a.state->epoch[side] + 1u; // not advanced before every block of this kernel has read it (see below)
+    const int parity = int(epoch & 1u);
+    const bool push = blockIdx.x < kHaloBlocksPerSide;
+    const int b = push ? blockIdx.x : blockIdx.x - kHaloBlocksPerSide;
+    if (push) {
+        const HaloLineDesc& d = a.send[side];
+        const long perField = long(d.nLines) * d.lineLen;
+        const long total = perField * d.nFields;
+        // my message lands in the neighbour's slot for ITS side facing me
+        double* dst = a.peerArena[side] + a.layout.slotOffset(opposite, parity);
+        for (long i = long(b) * blockDim.x + threadIdx.x; i < total; i += long(kHaloBlocksPerSide) * blockDim.x) {
+            const int f = int(i / perField);
+            const long r = i % perField;
+            const int line = int(r / d.lineLen);
+            const long k = r % d.lineLen;
+            const double* src = a.fieldPitch ? a.fields[0] + size_t(f) * a.fieldPitch : a.fields[f];
+            dst[i] = src[d.firstLine[line] + k * d.stride];
+        }
+        __threadfence_system(); // my peer stores are visible system-wide before I report completion
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(a.state->pushed + side, 1u);
+            if (prev == kHaloBlocksPerSide - 1) { // every push block of this side has fenced its stores
+                __threadfence_system();
+                unsigned* peerFlag = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(a.peerArena[side]) + a.layout.flagsOffsetBytes()) + opposite;
+                stReleaseSys(peerFlag, epoch);
             }
-            __nanosleep(200);
+        }
+    } else {
+        __shared__ int ok;
+        if (threadIdx.x == 0) {
+            ok = 1;
+            const unsigned* myFlag = reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(a.myArena) + a.layout.flagsOffsetBytes()) + side;
+            const unsigned long long t0 = globalTimerNs();
+            // flags only ever grow: >= tolerates a neighbour that is already one phase ahead
+            while (int(ldAcquireSys(myFlag) - epoch) < 0) {
+                if (globalTimerNs() - t0 > kHaloTimeoutNs) { // wall clock: the neighbour died; do not hang the GPU
+                    ok = 0;
+                    *a.errorFlag = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (ok) {
+            const HaloLineDesc& d = a.recv[side];
+            const long perField = long(d.nLines) * d.lineLen;
+            const long total = perField * d.nFields;
+            const double* src = a.myArena + a.layout.slotOffset(side, parity);
+            for (long i = long(b) * blockDim.x + threadIdx.x; i < total; i += long(kHaloBlocksPerSide) * blockDim.x) {
+                const int f = int(i / perField);
+                const long r = i % perField;
+                const int line = int(r / d.lineLen);
+                const long k = r % d.lineLen;
+                double* dstf = a.fieldPitch ? a.fields[0] + size_t(f) * a.fieldPitch : a.fields[f];
+                dstf[d.firstLine[line] + k * d.stride] = __ldcv(src + i);
+            }
         }
     }
+    // the last block of this side to finish advances the epoch and re-arms the counters for the next kernel.  Every
+    // block read `epoch` at its very start and no block can be the last one before all others have passed that point.
     __syncthreads();
-    if (!ok)
-        return;
-    const HaloLineDesc& d = a.recv[side];
-    const long perField = long(d.nLines) * d.lineLen;
-    const long total = perField * d.nFields;
-    const double* src = a.mySlot[side];
-    for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += long(gridDim.x) * blockDim.x) {
-        const int f = int(i / perField);
-        const long r = i % perField;
-        const int line = int(r / d.lineLen);
-        const long k = r % d.lineLen;
-        double* dstf = a.fieldPitch ? a.fields[0] + size_t(f) * a.fieldPitch : a.fields[f];
-        dstf[d.firstLine[line] + k * d.stride] = __ldcv(src + i);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(a.state->finished + side, 1u);
+        if (prev == 2 * kHaloBlocksPerSide - 1) {
+            a.state->pushed[side] = 0;
+            a.state->finished[side] = 0;
+            a.state->epoch[side] = epoch;
+            __threadfence();
+        }
     }
 }
 
