@@ -86,6 +86,13 @@ typedef struct nsdg_config {
     int box_x0, box_y0; /* first owned element of this box in the global grid */
     int rank, nranks; /* rank of this box, number of boxes */
     int neighbour[4]; /* rank of the box across each side, -1 = domain edge */
+    /* OPT-IN EXTENSION, not reference behaviour (default 0).  The reference hands hice / cice (/ damage) to the dynamics as
+     * one-component HFields every step, so DGModelArray::ma2dg zeroes the higher DG moments the advection has just built
+     * (quirk Q4: DGModelArray.hpp:20-32; the thermodynamics in between works on cell means, IceGrowth.cpp:45-46).  With
+     * keep_dg_moments = 1, nsdg_update takes the caller's arrays as the new CELL MEANS only: component 0 is replaced, the
+     * higher moments resident on the device are kept and re-limited (LimitMax / LimitMin as after the advection,
+     * DynamicsKernel.hpp:160-172) so that the bounds hold for the new mean.  nsdg_set_field is unaffected. */
+    int keep_dg_moments;
 } nsdg_config;
 
 void nsdg_config_default(nsdg_config* cfg);

@@ -29,7 +29,7 @@ class Config(Structure):
         ("use_cuda_graph", c_int), ("force_general", c_int), ("pin_host_buffers", c_int),
         ("alpha", c_double), ("beta", c_double),
         ("global_nx", c_int), ("global_ny", c_int), ("box_x0", c_int), ("box_y0", c_int),
-        ("rank", c_int), ("nranks", c_int), ("neighbour", c_int * 4),
+        ("rank", c_int), ("nranks", c_int), ("neighbour", c_int * 4), ("keep_dg_moments", c_int),
     ]
 
 

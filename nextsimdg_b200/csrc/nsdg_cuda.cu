@@ -564,6 +564,18 @@ public:
             throw std::runtime_error("nsdg_set_field: field cannot be set");
         }
     }
+    //! opt-in extension (nsdg_config::keep_dg_moments): the caller's array replaces the cell MEANS of an advected field; the
+    //! higher moments stay and are limited again for the new mean (same limiters as DynamicsKernel::advectionAndLimits)
+    void setMeanKeepMoments(int field, const double* host)
+    {
+        requireMesh();
+        double* f = field == NSDG_HICE ? hice.p : (field == NSDG_CICE ? cice.p : damage.p);
+        NSDG_CUDA_CHECK(cudaMemcpy2DAsync(f, size_t(g.nxs) * 8, host, size_t(g.nx) * 8, size_t(g.nx) * 8, g.ny, cudaMemcpyHostToDevice, stream));
+        if (field == NSDG_HICE)
+            limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, 2, 0.0, 0.0);
+        else
+            limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, 3, 1.0, field == NSDG_CICE ? 0.0 : 1e-12);
+    }
     void setField(int field, const double* host, int ncomp) override
     {
         setFieldAsync(field, host, ncomp);
@@ -1574,8 +1586,12 @@ public:
             NSDG_CUDA_CHECK(cudaEventCreateWithFlags(&evCopyDone, cudaEventDisableTiming));
         }
         for (int i = 0; i < 3; ++i)
-            if (ins[i])
-                setFieldAsync(inField[i], ins[i], 1);
+            if (ins[i]) {
+                if (cfg.keep_dg_moments && !(inField[i] == NSDG_DAMAGE && cfg.rheology != NSDG_BBM))
+                    setMeanKeepMoments(inField[i], ins[i]);
+                else
+                    setFieldAsync(inField[i], ins[i], 1);
+            }
         if (overlap) {
             // the previous work of the compute stream (this handle's earlier calls) must not be overtaken
             NSDG_CUDA_CHECK(cudaEventRecord(evCopyDone, stream));

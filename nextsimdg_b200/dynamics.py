@@ -36,7 +36,7 @@ class CUDADynamicsBase:
 
     def __init__(self, dgadv: int = 6, cgdegree: int = 2, nsteps: int = 100, device: int = -1,
                  use_cuda_graph: bool = True, force_general: bool = False, pin_host_buffers: bool = False,
-                 partition=None):
+                 partition=None, keep_dg_moments: bool = False):
         self._lib = capi.load_library()
         cfg = capi.Config()
         self._lib.nsdg_config_default(ctypes.byref(cfg))
@@ -48,6 +48,7 @@ class CUDADynamicsBase:
         cfg.use_cuda_graph = int(use_cuda_graph)
         cfg.force_general = int(force_general)
         cfg.pin_host_buffers = int(pin_host_buffers)
+        cfg.keep_dg_moments = int(keep_dg_moments)  # opt-in extension (include/nsdg.h); the reference zeroes the moments (Q4)
         if partition is not None:
             partition.fill_config(cfg)
         self.cfg = cfg

@@ -287,6 +287,44 @@ def test_restart_state_resumes_bitwise(rheo):
 
 
 @pytest.mark.parametrize("rheo", ["mevp", "bbm"])
+def test_keep_dg_moments_extension(rheo):
+    """nsdg_config::keep_dg_moments (SURVEY 8(f) N4, quirk Q4): with an identity 'thermodynamics' (the caller hands back the
+    cell means it received) two module-level updates equal one update followed by a device-resident step, i.e. the higher
+    DG moments built by the advection survive the hand-off; the default (reference behaviour, moments zeroed by ma2dg,
+    DGModelArray.hpp:20-32) gives a different answer."""
+    from nextsimdg_b200 import CUDABBMDynamics, CUDAMEVPDynamics, synthetic
+
+    cls = CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics
+    nx, ny, dt = 36, 28, 900.0
+    ms = synthetic.para_state(nx, ny, distort=0.03, irregular_mask=True)
+    f = synthetic.smooth_forcing(nx, ny)
+    ice = ms["mask"].astype(bool)
+
+    def run(keep, second):
+        d = cls(nsteps=40, keep_dg_moments=keep)
+        d.setData(ms)
+        d.shared = {"hice": np.ascontiguousarray(ms["hice"][..., 0]), "cice": np.ascontiguousarray(ms["cice"][..., 0]),
+                    **{k: v.copy() for k, v in f.items()}}
+        d.update(dt)
+        moments = d.getDGData("hice")[..., 1:].copy()
+        if second == "update":
+            d.update(dt)
+        else:
+            d.step(dt)
+        out = d.getDGData("hice"), d.getDGData("cice"), d.internal("cg_u")
+        d.close()
+        return moments, out
+
+    m_keep, keep = run(True, "update")
+    _, resident = run(True, "step")
+    _, default = run(False, "update")
+    assert np.abs(m_keep[ice]).max() > 1e-6  # the advection did build slopes
+    for a, b in zip(keep, resident):
+        assert rel(a.reshape(-1), b.reshape(-1)) < 1e-12
+    assert rel(keep[0][ice], default[0][ice]) > 1e-8  # and dropping them (the reference's Q4) changes the answer
+
+
+@pytest.mark.parametrize("rheo", ["mevp", "bbm"])
 def test_fresh_handle_does_not_depend_on_device_heap_contents(rheo):
     """Regression: buffers were zeroed by cudaMemset on the legacy stream, which the handle's non-blocking stream does not
     wait for; once cudaMalloc handed back used memory, a new handle could read garbage (or lose data to the late memset)
