@@ -820,9 +820,11 @@ public:
     template <int DG>
     void prepareAdvection(const double* cgU, const double* cgV, TransportOpPtrs op, double* vxd, double* vyd, double* nX, double* nY)
     {
-        cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgU, op, vxd);
-        cg2dg_kernel<CG, DG><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgV, op, vyd);
-        launches += 2;
+        if (uniform && !std::getenv("NSDG_NO_UNIFORM_TRANSPORT"))
+            cg2dg_pair_kernel<CG, DG, true><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgU, cgV, op, vxd, vyd);
+        else
+            cg2dg_pair_kernel<CG, DG, false><<<blocksFor(g.N), 128, 0, stream>>>(g, vx, vy, cgU, cgV, op, vxd, vyd);
+        launches += 1;
         normalVelocity<DG>(vxd, vyd, nX, nY);
     }
     template <int DG> void launchStage(TransportStageArgs& a, int nf)

@@ -70,6 +70,91 @@ __global__ void cg2dg_kernel(GridDims g, const double* __restrict__ vx, const do
     }
 }
 
+//! Both velocity components at once (DGTransport::prepareAdvection, DGTransport.cpp:262-268): the element map and the
+//! inverse mass matrix are formed / read once for the pair.  UNI (congruent axis-aligned rectangles): J w = dx dy w_q and
+//! M^-1 = diag(1 / (dx dy int psi_j^2)), so the element size cancels and neither geometry nor operators are read.
+template <int CG, int DG, bool UNI>
+__global__ void cg2dg_pair_kernel(GridDims g, const double* __restrict__ vx, const double* __restrict__ vy,
+    const double* __restrict__ cgA, const double* __restrict__ cgB, TransportOpPtrs op, double* __restrict__ dgA, double* __restrict__ dgB)
+{
+    constexpr int G = gp1d(DG), Q = G * G, NR = CG + 1, ND = NR * NR;
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
+    double la[ND], lb[ND];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+            la[r * NR + c] = cgA[size_t(CG * iy + r) * g.cgs + CG * ix + c];
+            lb[r * NR + c] = cgB[size_t(CG * iy + r) * g.cgs + CG * ix + c];
+        }
+    double wj[Q];
+    if constexpr (UNI) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+            wj[q] = gaussweight2(G, q);
+    } else {
+        double crn[4][2], dx[2][Q], dy[2][Q], J[Q], lat[Q];
+        elementCorners(vx, vy, g.nx, ix, iy, g.spherical, crn);
+        elementMap<G>(crn, dx, dy, J, lat);
+        for (int q = 0; q < Q; ++q) {
+            wj[q] = J[q] * gaussweight2(G, q);
+            if (g.spherical)
+                wj[q] *= cos(lat[q]);
+        }
+    }
+    double ra[DG], rb[DG];
+#pragma unroll
+    for (int j = 0; j < DG; ++j)
+        ra[j] = rb[j] = 0.0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double sa = 0, sb = 0;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            const double ph = PHI(CG, G, i, q);
+            if (ph != 0.0) {
+                sa = fma(ph, la[i], sa);
+                sb = fma(ph, lb[i], sb);
+            }
+        }
+        sa *= wj[q];
+        sb *= wj[q];
+#pragma unroll
+        for (int j = 0; j < DG; ++j) {
+            const double ps = PSI(G, j, q);
+            if (ps != 0.0) {
+                ra[j] = fma(ps, sa, ra[j]);
+                rb[j] = fma(ps, sb, rb[j]);
+            }
+        }
+    }
+    if constexpr (UNI) {
+        constexpr double minv[8] = { 1., 12., 12., 180., 180., 144., 2160., 2160. }; // 1 / int psi_j^2 on the unit square
+#pragma unroll
+        for (int i = 0; i < DG; ++i) {
+            dgA[size_t(i) * g.Npad + e] = ra[i] * minv[i];
+            dgB[size_t(i) * g.Npad + e] = rb[i] * minv[i];
+        }
+    } else {
+        const size_t eo = e * op.estride;
+        const double sc = g.spherical ? EarthRadius : 1.0; // the stored inverse carries 1 / EarthRadius on the sphere
+        for (int i = 0; i < DG; ++i) {
+            double sa = 0, sb = 0;
+            for (int j = 0; j < DG; ++j) {
+                const double m = op.iMass[(i * DG + j) * op.pitch + eo];
+                sa += m * ra[j];
+                sb += m * rb[j];
+            }
+            dgA[size_t(i) * g.Npad + e] = sa * sc;
+            dgB[size_t(i) * g.Npad + e] = sb * sc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // DG -> CG nodal averaging (per node gather over <= 4 elements, reference order: odd element
 // rows first, quirk Q7; weights 1/4 corner, 1/2 edge, 1 centre; domain-boundary nodes x2).
