@@ -271,6 +271,36 @@ def parity_probe_partitioned(rheo, rank, world, device, dist):
             "cases": cases}
 
 
+def pcie_probe(world, dist, nbytes=4 * 2048 * 2048 * 8):
+    """What the end-to-end arm's tail costs on THIS host: every rank copies the bytes of the four late outputs (u, v, taux,
+    tauy: 4 x N x 8 B) device -> pinned host, and the same amount host -> device, all ranks AT THE SAME TIME.  The per-rank
+    rate (minimum over ranks) against the single-rank rate shows how much of the e2e scaling loss is the host's shared
+    PCIe / memory path rather than anything in the library (plumbing only: torch tensors, no product code)."""
+    import torch
+
+    dev = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    host = torch.empty(nbytes // 8, dtype=torch.float64).pin_memory()
+    out = {"bytes": nbytes, "ranks_copying_concurrently": world}
+    for name, (dst, src) in (("d2h", (host, dev)), ("h2d", (dev, host))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+        if dist is not None:
+            t = torch.tensor([best], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            best = float(t.item())
+        out[f"{name}_gbs_per_rank"] = best
+    return out
+
+
 def measure_arm(args, rheo, mesh, n, steps, warmup, e2e_steps, rank, local_rank, world, dist, label=None, ms_override=None,
                 nsteps=NSTEPS, dt=DT):
     """One workload through the device-resident arm, the kernel-pair roofline and the end-to-end arm."""
@@ -381,6 +411,19 @@ def measure_arm(args, rheo, mesh, n, steps, warmup, e2e_steps, rank, local_rank,
         roofline["note"] = ("achieved uses SURVEY 8(d)'s 1120 B per element-subcycle; the kernel additionally reads 27 per-step Gauss-point "
                             "constants per element instead of recomputing exp/pow every subcycle, so `traffic` is slightly above it")
 
+    # ---- the advection phase (fused transport stages + the projection of the velocity), once per step ----
+    # algorithmic doubles per element and step (rk2): per field and stage phi r + out w (+ phi0 r in the second stage), the DG
+    # velocity (2 x DG) and the edge velocities (2 x 3) once per stage; prepareAdvection: 8 CG node values in, 2 x DG out,
+    # normal velocities 2 x DG in, 6 out.  mEVP advects 2 DG6 fields, BBM 3 DG6 + 3 DG8 fields (two transport objects).
+    def adv_doubles(dg, nf):
+        return nf * (dg + dg + 2 * dg + dg) + 2 * (2 * dg + 6) + (8 + 2 * dg) + (2 * dg + 6)
+    adv_bytes = 8 * (adv_doubles(6, 3) + adv_doubles(8, 3) if rheo == "bbm" else adv_doubles(6, 2))
+    adv_ms_step = adv_ms / steps
+    adv_gbs = adv_bytes * local_elems / (adv_ms_step * 1e-3) / 1e9 if adv_ms_step > 0 else None
+    advection = {"kernel": "transport_stage (x2 per transport object) + cg2dg_pair + normalvel", "ms_per_step": adv_ms_step, "bound": "hbm",
+                 "alg_bytes_per_element_step": adv_bytes, "achieved": adv_gbs, "peak": peak, "unit": "GB/s",
+                 "frac": (adv_gbs / peak) if adv_gbs else None}
+
     # ---- end-to-end arm: host buffers in, host buffers out, every step ----
     for _ in range(min(warmup, 2)):
         dyn.update(dt)
@@ -399,7 +442,7 @@ def measure_arm(args, rheo, mesh, n, steps, warmup, e2e_steps, rank, local_rank,
     ms_per_step = dev_ms / steps
     res = {
         "workload": wl, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
-        "roofline": roofline,
+        "roofline": roofline, "advection_roofline": advection,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nin * field_bytes, "d2h_bytes_per_step": nout * field_bytes,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -442,6 +485,11 @@ def run_gpu(args):
 
     n, rheo, mesh = args.n, args.rheology, MESH
     main = measure_arm(args, rheo, mesh, n, args.steps, args.warmup, args.e2e_steps, rank, local_rank, world, dist)
+
+    try:
+        probe = pcie_probe(world, dist)
+    except Exception as ex:  # never let the diagnostic take the bench line down
+        probe = {"unavailable": str(ex)}
 
     # ---- correctness where speed is measured ----
     if world == 1:
@@ -489,8 +537,9 @@ def run_gpu(args):
                    "l2": "working set (~3 GB) is larger than the 126 MB L2; no flush needed",
                    "parallelism": "single domain" if world == 1 else f"2-D boxes x{world}, NVLink halo exchange"},
         "roofline": main["roofline"],
+        "advection_roofline": main["advection_roofline"],
         "cpu_baseline": cpu,
-        "e2e": main["e2e"],
+        "e2e": {**main["e2e"], "pcie_probe": probe},
         "gpu_launches": main["gpu_launches"],
         "clocks": main["clocks"],
         "parity_check": parity,

@@ -1561,6 +1561,25 @@ public:
         else
             cudaGetLastError(); // already pinned by the caller or not pinnable: copies still work
     }
+    //! a buffer the caller no longer passes (a ModelArray that was reallocated) must not stay page-locked until nsdg_destroy:
+    //! registrations that are not among this call's pointers are dropped
+    void unpinStale(const void* const* current, int n)
+    {
+        if (!cfg.pin_host_buffers)
+            return;
+        for (size_t i = 0; i < registered.size();) {
+            bool live = false;
+            for (int k = 0; k < n; ++k)
+                live = live || current[k] == registered[i].first;
+            if (live)
+                ++i;
+            else {
+                cudaHostUnregister(const_cast<void*>(registered[i].first));
+                cudaGetLastError(); // the memory may already have been freed by its owner
+                registered.erase(registered.begin() + long(i));
+            }
+        }
+    }
 
     //! MEVPDynamics::update / BBMDynamics::update in one call
     void update(const nsdg_update_io* io, double dt) override
@@ -1571,6 +1590,15 @@ public:
         const int inField[] = { NSDG_HICE, NSDG_CICE, NSDG_DAMAGE, NSDG_UWIND, NSDG_VWIND, NSDG_UOCEAN, NSDG_VOCEAN, NSDG_SSH };
         double* outs[] = { io->hice_out, io->cice_out, io->damage_out, io->u_out, io->v_out, io->taux_out, io->tauy_out };
         const int outField[] = { NSDG_HICE, NSDG_CICE, NSDG_DAMAGE, NSDG_U, NSDG_V, NSDG_TAUX, NSDG_TAUY };
+        {
+            const void* current[15];
+            int nc = 0;
+            for (const double* ptr : ins)
+                current[nc++] = ptr;
+            for (double* ptr : outs)
+                current[nc++] = ptr;
+            unpinStale(current, nc);
+        }
         for (const double* ptr : ins)
             pin(ptr, bytes);
         for (double* ptr : outs)
