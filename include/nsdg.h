@@ -90,8 +90,8 @@ typedef struct nsdg_config {
      * one-component HFields every step, so DGModelArray::ma2dg zeroes the higher DG moments the advection has just built
      * (quirk Q4: DGModelArray.hpp:20-32; the thermodynamics in between works on cell means, IceGrowth.cpp:45-46).  With
      * keep_dg_moments = 1, nsdg_update takes the caller's arrays as the new CELL MEANS only: component 0 is replaced, the
-     * higher moments resident on the device are kept and re-limited (LimitMax / LimitMin as after the advection,
-     * DynamicsKernel.hpp:160-172) so that the bounds hold for the new mean.  nsdg_set_field is unaffected. */
+     * higher moments resident on the device are kept; hice and cice are limited again (LimitMax / LimitMin as after the
+     * advection, DynamicsKernel.hpp:160-172) so that their bounds hold for the new mean.  nsdg_set_field is unaffected. */
     int keep_dg_moments;
 } nsdg_config;
 

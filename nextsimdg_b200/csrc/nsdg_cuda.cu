@@ -571,10 +571,14 @@ public:
         requireMesh();
         double* f = field == NSDG_HICE ? hice.p : (field == NSDG_CICE ? cice.p : damage.p);
         NSDG_CUDA_CHECK(cudaMemcpy2DAsync(f, size_t(g.nxs) * 8, host, size_t(g.nx) * 8, size_t(g.nx) * 8, g.ny, cudaMemcpyHostToDevice, stream));
+        // hice, cice: limited again for the new mean (a no-op while the caller hands back the means it received: they left the
+        // advection limited and the subcycles do not touch them).  The damage is NOT: the BBM subcycles rewrite all its
+        // moments without limiting, and the reference limits it only after the next advection (BrittleCGDynamicsKernel.hpp:
+        // 103-106) -- an extra limiter here would change a field the caller did not touch.
         if (field == NSDG_HICE)
             limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, 2, 0.0, 0.0);
-        else
-            limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, 3, 1.0, field == NSDG_CICE ? 0.0 : 1e-12);
+        else if (field == NSDG_CICE)
+            limit_kernel<DGA><<<blocksFor(g.N), 128, 0, stream>>>(g, f, 3, 1.0, 0.0);
     }
     void setField(int field, const double* host, int ncomp) override
     {

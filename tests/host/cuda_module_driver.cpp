@@ -97,7 +97,8 @@ int main(int argc, char** argv)
         su += std::fabs(dyn->getU()[e]);
         sv += std::fabs(dyn->getV()[e]);
         sh_ += sh.hice[e];
-        st += std::fabs(dyn->getTauX()[e]);
+        if (dyn->getTauX().trueSize() == n * n) // FreeDriftDynamics never exports (or sizes) the ice-ocean stress
+            st += std::fabs(dyn->getTauX()[e]);
     }
     std::printf("RESULT %s %.17e %.17e %.17e %.17e\n", dyn->getName().c_str(), su, sv, sh_, st);
     return 0;
