@@ -678,12 +678,42 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
     const long nV = long(a.nsx) * g.cgny;
     if (t >= nH + nV)
         return;
-    int c, r, vline = 0;
-    double sumX = 0.0, sumY = 0.0;
-    if (t < nH) {
-        const int L = int(t / g.cgnx) + 1;
+    // decode the node first, request everything that does not depend on the contributions (node constants, Dirichlet
+    // flag, u, v), THEN gather the raw contributions: three dependent memory phases become one
+    const bool horizontal = t < nH;
+    int c, r, vline = 0, L;
+    if (horizontal) {
+        L = int(t / g.cgnx) + 1;
         c = int(t % g.cgnx);
         r = min(CG * a.R * L, CG * g.ny);
+    } else {
+        const long tv = t - nH;
+        L = int(tv / g.cgny) + 1;
+        vline = L - 1;
+        r = int(tv % g.cgny);
+        c = min(CG * 32 * L, CG * g.nx);
+        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
+            return;
+    }
+    const size_t n = size_t(r) * g.cgs + c;
+    double k[kNodeConsts];
+    bool d;
+    if (horizontal) {
+        const double* src[kNodeConsts] = { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
+#pragma unroll
+        for (int i = 0; i < kNodeConsts; ++i)
+            k[i] = __ldg(src[i] + n);
+        d = __ldg(a.nodemask + n) & 1;
+    } else { // vertical line: compact copies (vcon_kernel)
+        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
+#pragma unroll
+        for (int i = 0; i < kNodeConsts; ++i)
+            k[i] = __ldg(a.vcon + i * pitch + m);
+        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
+    }
+    const double uOld = a.u[n], vOld = a.v[n];
+    double sumX = 0.0, sumY = 0.0;
+    if (horizontal) {
         const int jx = c % CG, exr = c / CG;
         const bool above = r < CG * g.ny;
         if (a.sub.subset) { // frame-complete: every strip that contributes to the node is a frame strip
@@ -711,13 +741,6 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
                 add(side, exr, jx);
         }
     } else {
-        const long tv = t - nH;
-        const int L = int(tv / g.cgny) + 1;
-        vline = L - 1;
-        r = int(tv % g.cgny);
-        c = min(CG * 32 * L, CG * g.nx);
-        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
-            return;
         const int jy = r % CG, eyr = r / CG;
         const bool right = c < CG * g.nx;
         if (a.sub.subset) {
@@ -739,24 +762,8 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
             add(side, eyr, jy);
         }
     }
-    const size_t n = size_t(r) * g.cgs + c;
-    double k[kNodeConsts];
-    bool d;
-    if (t < nH) {
-        const double* src[kNodeConsts] = { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(src[i] + n);
-        d = __ldg(a.nodemask + n) & 1;
-    } else { // vertical line: compact copies (vcon_kernel)
-        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(a.vcon + i * pitch + m);
-        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
-    }
     double un, vn;
-    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
+    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
     a.u[n] = un;
     a.v[n] = vn;
 }
