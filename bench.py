@@ -162,7 +162,10 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample_grid": f"{n}x{n}", "nsteps": NSTEPS, "dt": DT,
-                   "note": "each step is a bounded sample (smaller grid) of the workload; throughput per element-subcycle is size-independent on the CPU"},
+                   "note": ("each step is a bounded sample (smaller grid) of the workload. The per-element-subcycle rate of the reference's kernels "
+                            "does not depend on the grid size: measured on the GPU box's 16 host cores 2.12e7 /s at 512^2, 2.00e7 at 1024^2, "
+                            "2.06e7 at 2048^2 (mEVP; BBM 1.03e7 at 512^2 and 1024^2) -- profiles/r2_cpu_reference_curve.json, "
+                            "scripts/cpu_reference_curve.py; --ref-n 2048 runs the full-size grid (20 s per update)")},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,

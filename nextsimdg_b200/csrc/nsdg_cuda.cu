@@ -1652,9 +1652,29 @@ public:
             std::swap(stream, copyStream);
             firstLate = 2;
         }
-        for (int i = firstLate; i < 7; ++i)
+        // u, v and the ice-ocean stress can only leave after the last subcycle: on a uniform DG2/CG2 mesh one kernel forms the
+        // four cell-mean fields (the general path: iostress + a full DG projection per field), then the four copies follow
+        bool lateDone = false;
+        if constexpr (CG == 2 && DGA == 6) {
+            if (uniform && cfg.rheology != NSDG_FREEDRIFT && io->u_out && io->v_out && io->taux_out && io->tauy_out
+                && !std::getenv("NSDG_NO_FUSED_EXPORT")) {
+                const bool bbmR = cfg.rheology == NSDG_BBM;
+                if (bbmR)
+                    export_dg0_uniform_kernel<CG, NSDG_BBM><<<blocksFor(g.N), 128, 0, stream>>>(g, p, u, v, avgU, avgV, uO, vO, scratchDG);
+                else
+                    export_dg0_uniform_kernel<CG, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(g, p, u, v, u, v, uO, vO, scratchDG);
+                double* late[4] = { io->u_out, io->v_out, io->taux_out, io->tauy_out };
+                for (int k = 0; k < 4; ++k)
+                    downloadPlanes(scratchDG.p + size_t(k) * g.Npad, 1, late[k]);
+                lateDone = true;
+            }
+        }
+        for (int i = firstLate; i < 7; ++i) {
+            if (lateDone && i >= 3)
+                continue;
             if (outs[i] && !(outField[i] == NSDG_DAMAGE && cfg.rheology != NSDG_BBM))
                 getFieldAsync(outField[i], outs[i], 1);
+        }
         if (overlap)
             NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evCopyDone, 0));
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -271,6 +271,62 @@ __global__ void iostress_kernel(GridDims g, PhysParams p, const double* __restri
     }
 }
 
+//! The four outputs that have to wait for the last subcycle -- cell means of u, v (CGDynamicsKernel::getDG0Data,
+//! CGDynamicsKernel.cpp:92-118: CG2DG, component 0) and of the ice-ocean stress (getIceOceanStress + CG2DG) -- in ONE pass
+//! on a uniform rectangular mesh, where component 0 of the L2 projection is the quadrature mean sum_q w_q f(q) (J w and the
+//! (0,0) entry of the inverse mass matrix cancel).  The general path runs iostress_kernel and a full DG projection per
+//! field.  (us, vs): the velocity the stress is taken with (mEVP: u, v; BBM: the running mean, quirk Q14).
+template <int CG, int RHEO>
+__global__ void export_dg0_uniform_kernel(GridDims g, PhysParams p, const double* __restrict__ u, const double* __restrict__ v,
+    const double* __restrict__ us, const double* __restrict__ vs, const double* __restrict__ uO, const double* __restrict__ vO,
+    double* __restrict__ out /* planes: u, v, taux, tauy */)
+{
+    constexpr int G = 3, Q = G * G, NR = CG + 1, ND = NR * NR;
+    const size_t t_ = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t_ >= size_t(g.N))
+        return;
+    const int ix = int(t_ % g.nx), iy = int(t_ / g.nx);
+    const size_t e = size_t(iy) * g.nxs + ix;
+    double f[4][ND];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+            const size_t n = size_t(CG * iy + r) * g.cgs + CG * ix + c;
+            const int i = r * NR + c;
+            f[0][i] = u[n];
+            f[1][i] = v[n];
+            const double a = us[n], b = vs[n], ao = uO[n], bo = vO[n];
+            if constexpr (RHEO == NSDG_MEVP) {
+                const double uR = a - ao, vR = b - bo;
+                const double absocn = sqrt(uR * uR + vR * vR);
+                f[2][i] = p.F_ocean * absocn * uR;
+                f[3][i] = p.F_ocean * absocn * vR;
+            } else {
+                const double uR = ao - a, vR = bo - b;
+                const double cPrime = p.F_ocean * hypot(uR, vR);
+                f[2][i] = cPrime * (uR * p.cosOceanAngle - vR * p.sinOceanAngle);
+                f[3][i] = cPrime * (vR * p.cosOceanAngle + uR * p.sinOceanAngle);
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double mean = 0.0;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            double sq = 0.0;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+                const double ph = PHI(CG, G, i, q);
+                if (ph != 0.0)
+                    sq = fma(ph, f[k][i], sq);
+            }
+            mean = fma(gaussweight2(G, q), sq, mean);
+        }
+        out[size_t(k) * g.Npad + e] = mean;
+    }
+}
+
 //! FreeDriftDynamicsKernel::updateMomentum + applyBoundaries (FreeDriftDynamicsKernel.hpp:43-68)
 __global__ void freedrift_kernel(GridDims g, PhysParams p, const double* __restrict__ uO, const double* __restrict__ vO,
     const double* __restrict__ uA, const double* __restrict__ vA, const uint8_t* __restrict__ nodemask, double* __restrict__ u,
