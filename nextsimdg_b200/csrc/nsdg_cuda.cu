@@ -20,9 +20,7 @@
 #include <memory>
 #include <utility>
 
-#include "nsdg_momentum.cuh"
-#include "nsdg_momentum_uniform.cuh"
-#include "nsdg_momentum_param.cuh"
+#include "nsdg_fast_launch.cuh" // argument structs + launchers of the fast strip kernels (compiled in their own translation units)
 #include "nsdg_halo.cuh"
 #include "nsdg_prepare.cuh"
 
@@ -426,12 +424,8 @@ public:
                 f->alloc(ncg);
             gaussC.alloc(size_t(Q) * Npad);
             if constexpr (CG == 2 && DGA == 6) {
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_ubbm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUbbmSmemBytes)));
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_pbbm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pbbmSmemBytes<false>())));
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_pbbm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pbbmSmemBytes<true>())));
+                prepareKernelsUBBM();
+                prepareKernelsPBBM();
             }
         }
         fastParamMEVP = !uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
@@ -440,12 +434,8 @@ public:
             for (auto* f : { &ncCA, &ncRx, &ncRy, &ncIlm })
                 f->alloc(ncg);
             if constexpr (CG == 2 && DGA == 6) {
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_umevp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kUmevpSmemBytes)));
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_pmevp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pmevpSmemBytes(false))));
-                NSDG_CUDA_CHECK(cudaFuncSetAttribute(
-                    subcycle_strip_pmevp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pmevpSmemBytes(true))));
+                prepareKernelsUMEVP();
+                prepareKernelsPMEVP();
             }
         }
         if (fastMEVP() || fastBBM())
@@ -1213,39 +1203,26 @@ public:
     void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            if (!linesOnly && fastParamBBM) {
-                const unsigned nb = (unsigned(nsx) * nsy + kPbbmWarps - 1) / kPbbmWarps;
-                if (g.spherical)
-                    subcycle_strip_pbbm<true><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<true>(), stream>>>(ba);
-                else
-                    subcycle_strip_pbbm<false><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<false>(), stream>>>(ba);
-            } else if (!linesOnly) {
-                const unsigned nb = (unsigned(nsx) * nsy + kUbbmWarps - 1) / kUbbmWarps;
-                subcycle_strip_ubbm<0><<<nb, 32 * kUbbmWarps, kUbbmSmemBytes, stream>>>(ba);
-            }
+            const unsigned nStrips = unsigned(nsx) * nsy;
+            if (!linesOnly && fastParamBBM)
+                launchStripPBBM(ba, g.spherical != 0, nStrips, stream);
+            else if (!linesOnly)
+                launchStripUBBM(ba, nStrips, stream);
             if (!stripOnly)
-                subcycle_lines_ubbm<<<blocksFor(nLine), 128, 0, stream>>>(ba);
+                launchLinesUBBM(ba, nLine, stream);
         }
     }
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            if (fastParamMEVP) {
-                const unsigned nw = pmevpWarps(g.spherical), nb = (unsigned(nsx) * nsy + nw - 1) / nw;
-                if (g.spherical)
-                    subcycle_strip_pmevp<true><<<nb, 32 * nw, pmevpSmemBytes(true), stream>>>(ua);
-                else
-                    subcycle_strip_pmevp<false><<<nb, 32 * nw, pmevpSmemBytes(false), stream>>>(ua);
-            } else {
-                const unsigned nb = (unsigned(nsx) * nsy + kUmevpWarps - 1) / kUmevpWarps;
-                subcycle_strip_umevp<0><<<nb, 32 * kUmevpWarps, kUmevpSmemBytes, stream>>>(ua);
-            }
+            const unsigned nStrips = unsigned(nsx) * nsy;
+            if (fastParamMEVP)
+                launchStripPMEVP(ua, g.spherical != 0, nStrips, stream);
+            else
+                launchStripUMEVP(ua, nStrips, stream);
         }
     }
-    void launchLinesFast(const UniformArgs& ua, size_t nLine)
-    {
-        subcycle_lines_umevp<<<blocksFor(nLine), 128, 0, stream>>>(ua);
-    }
+    void launchLinesFast(const UniformArgs& ua, size_t nLine) { launchLinesUMEVP(ua, nLine, stream); }
     template <int RHEO> void launchStrip(const SubcycleArgs& a, unsigned nbStrip)
     {
         if (uniform)
@@ -1509,9 +1486,9 @@ public:
             gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(
                 g, p, hice, cice, gaussA, gaussB, fastMEVP() ? 1.0 / p.alpha : 1.0);
             if (fastMEVP()) {
-                nodeconst_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
+                nodeconst_kernel<0><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncCA, ncRx, ncRy, ncIlm);
-                vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+                vcon_kernel<0><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
                     g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 2;
             }
@@ -1521,9 +1498,9 @@ public:
             NSDG_CUDA_CHECK(cudaMemsetAsync(avgV, 0, cgBytes, stream));
             if (fastBBM()) {
                 gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
-                nodeconst_bbm_kernel<<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
+                nodeconst_bbm_kernel<0><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncCA, ncRx, ncRy, ncIlm);
-                vcon_kernel<<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+                vcon_kernel<0><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
                     g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 2;
             } else

@@ -66,7 +66,7 @@ struct SubcycleArgs {
     PhysParams p;
 };
 
-__constant__ MomentumOps c_mops; //!< the single operator set of a uniform rectangular mesh
+static __constant__ MomentumOps c_mops; //!< the single operator set of a uniform rectangular mesh (one copy per translation unit; only nsdg_cuda.cu uses it)
 
 //! node-constant inputs of the momentum equation
 struct NodeIn {

@@ -160,6 +160,7 @@ struct UniformArgs {
  *   cA  = cgA F_ocean / c1,   rx = R_x / c1,   ry = R_y / c1,   ilm = 1 / (lumpedcgmass c1),   and uO, vO
  * (one array and 32 B per element and subcycle less than keeping c1).
  */
+template <int DUMMY = 0>
 __global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
     const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
     const double* __restrict__ gy, const double* __restrict__ u0, const double* __restrict__ v0, const double* __restrict__ lm,
@@ -187,6 +188,7 @@ __global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const 
  */
 constexpr int kNodeConsts = 6;
 constexpr int kVconPlanes = kNodeConsts + 1;
+template <int DUMMY = 0>
 __global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2,
     const double* __restrict__ k3, const double* __restrict__ k4, const double* __restrict__ k5, const uint8_t* __restrict__ nodemask,
     double* __restrict__ vcon)
@@ -669,6 +671,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 }
 
 //! deferred-line nodes for the uniform mEVP path (see subcycle_lines in nsdg_momentum.cuh)
+template <int DUMMY = 0>
 __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constant__ UniformArgs a)
 {
     constexpr int CG = 2, NR = 3;

@@ -46,6 +46,7 @@ struct UniformBBMArgs {
 
 //! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240); the factor
 //! dte = deltaT / (rho_ice cgH) that multiplies every one of them in the update is folded in (six arrays instead of seven)
+template <int DUMMY = 0>
 __global__ void nodeconst_bbm_kernel(GridDims g, PhysParams p, double deltaT, const double* __restrict__ cgH,
     const double* __restrict__ cgA, const double* __restrict__ uA, const double* __restrict__ vA, const double* __restrict__ gx,
     const double* __restrict__ gy, const double* __restrict__ lm, double* __restrict__ cA, double* __restrict__ ax,
@@ -603,6 +604,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 }
 
 //! deferred-line nodes for the uniform BBM path
+template <int DUMMY = 0>
 __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant__ UniformBBMArgs a)
 {
     constexpr int CG = 2, NR = 3;
