@@ -726,46 +726,37 @@ template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
 #ifndef NSDG_PBBM_LOCKSTEP
 #define NSDG_PBBM_LOCKSTEP 0
 #endif
-constexpr int kPbbmWarps = NSDG_PBBM_LOCKSTEP ? 8 : 2;
-template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps; }
+template <bool SPH> constexpr bool kPbbmLockstep = (NSDG_PBBM_LOCKSTEP != 0) && !SPH; // 8 spherical stages exceed the shared memory of an SM
+template <bool SPH> constexpr int kPbbmWarps = kPbbmLockstep<SPH> ? 8 : 2;
+template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps<SPH>; }
 
 template <bool SPH>
-__global__ void __launch_bounds__(32 * kPbbmWarps, NSDG_PBBM_LOCKSTEP ? 1 : (SPH ? 3 : 4)) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
+__global__ void __launch_bounds__(32 * kPbbmWarps<SPH>, kPbbmLockstep<SPH> ? 1 : (SPH ? 3 : 4)) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
 {
+    constexpr bool LOCKSTEP = kPbbmLockstep<SPH>;
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GB = geoPlanes(SPH); // first BBM-specific plane
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-#if NSDG_PBBM_LOCKSTEP
-    // every warp of the block takes part in the row barriers: a warp without a strip walks an empty row range
+    // lockstep: every warp of the block takes part in the row barriers; a warp without a strip walks an empty row range
     const int wRaw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     bool valid = wRaw < a.nsx * a.nsy;
-    const int w = valid ? wRaw : 0;
-#else
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= a.nsx * a.nsy)
+    if (!LOCKSTEP && !valid)
         return;
-#endif
+    const int w = valid ? wRaw : 0;
     PbbmStage<SPH>& st = reinterpret_cast<PbbmStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-#if NSDG_PBBM_LOCKSTEP
     valid = valid && !skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy));
-#else
-    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
+    if (!LOCKSTEP && !valid)
         return;
-#endif
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
     const bool lastLane = active && (lane == 31 || exRaw == g.nx - 1);
     const bool loadsRight = (lane == 31) || (exRaw >= g.nx - 1);
-#if NSDG_PBBM_LOCKSTEP
     const int ey0 = a.R * sy, ey1 = valid ? min(ey0 + a.R, g.ny) : ey0;
-#else
-    const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
-#endif
     const size_t Npad = g.Npad;
     const int col0 = CG * ex;
     auto geo = [&](int k) { return st.GEO[k][lane]; };
@@ -860,14 +851,12 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, NSDG_PBBM_LOCKSTEP ? 1 : (SPH
         vl[2] = rv;
     }
 
-#if NSDG_PBBM_LOCKSTEP
-    for (int ey = ey0; ey < ey0 + a.R; ++ey) {
-        __syncthreads(); // the warps of the block walk the row body together (instruction-cache sharing)
-        if (ey >= ey1)
-            continue;
-#else
-    for (int ey = ey0; ey < ey1; ++ey) {
-#endif
+    for (int ey = ey0; ey < (LOCKSTEP ? ey0 + a.R : ey1); ++ey) {
+        if constexpr (LOCKSTEP) {
+            __syncthreads(); // the warps of the block walk the row body together (instruction-cache sharing)
+            if (ey >= ey1)
+                continue;
+        }
         const size_t e = size_t(ey) * g.nxs + ex;
         cpAsyncWait<4>();
         __syncwarp(); // the mask bytes were staged by other lanes
