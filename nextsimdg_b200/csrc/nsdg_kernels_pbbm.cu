@@ -10,10 +10,11 @@ void prepareKernelsPBBM()
 }
 void launchStripPBBM(const UniformBBMArgs& a, bool spherical, unsigned nStrips, cudaStream_t s)
 {
+    const unsigned nb = (nStrips + kPbbmWarps - 1) / kPbbmWarps;
     if (spherical)
-        subcycle_strip_pbbm<true><<<(nStrips + kPbbmWarps<true> - 1) / kPbbmWarps<true>, 32 * kPbbmWarps<true>, pbbmSmemBytes<true>(), s>>>(a);
+        subcycle_strip_pbbm<true><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<true>(), s>>>(a);
     else
-        subcycle_strip_pbbm<false><<<(nStrips + kPbbmWarps<false> - 1) / kPbbmWarps<false>, 32 * kPbbmWarps<false>, pbbmSmemBytes<false>(), s>>>(a);
+        subcycle_strip_pbbm<false><<<nb, 32 * kPbbmWarps, pbbmSmemBytes<false>(), s>>>(a);
 }
 
 } // namespace nsdg

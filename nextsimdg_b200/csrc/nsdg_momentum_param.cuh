@@ -717,46 +717,31 @@ template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
     double UVr[2][2];
     double pad[2];
 };
-/*
- * NSDG_PBBM_LOCKSTEP: the loop body of this kernel is ~65 KB of straight-line code and ncu shows more than one
- * `stall_no_instruction` per issued instruction: eight warps per SM, each in a different phase of the body, thrash the
- * instruction caches.  In lockstep mode the eight warps form ONE block and meet at a barrier at the top of every element
- * row, so they walk the body together and every fetched line serves all of them.
- */
-#ifndef NSDG_PBBM_LOCKSTEP
-#define NSDG_PBBM_LOCKSTEP 0
-#endif
-template <bool SPH> constexpr bool kPbbmLockstep = (NSDG_PBBM_LOCKSTEP != 0) && !SPH; // 8 spherical stages exceed the shared memory of an SM
-template <bool SPH> constexpr int kPbbmWarps = kPbbmLockstep<SPH> ? 8 : 2;
-template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps<SPH>; }
+constexpr int kPbbmWarps = 2;
+template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps; }
 
 template <bool SPH>
-__global__ void __launch_bounds__(32 * kPbbmWarps<SPH>, kPbbmLockstep<SPH> ? 1 : (SPH ? 3 : 4)) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
+__global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
 {
-    constexpr bool LOCKSTEP = kPbbmLockstep<SPH>;
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GB = geoPlanes(SPH); // first BBM-specific plane
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-    // lockstep: every warp of the block takes part in the row barriers; a warp without a strip walks an empty row range
-    const int wRaw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    bool valid = wRaw < a.nsx * a.nsy;
-    if (!LOCKSTEP && !valid)
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
         return;
-    const int w = valid ? wRaw : 0;
     PbbmStage<SPH>& st = reinterpret_cast<PbbmStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-    valid = valid && !skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy));
-    if (!LOCKSTEP && !valid)
+    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
         return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
     const bool lastLane = active && (lane == 31 || exRaw == g.nx - 1);
     const bool loadsRight = (lane == 31) || (exRaw >= g.nx - 1);
-    const int ey0 = a.R * sy, ey1 = valid ? min(ey0 + a.R, g.ny) : ey0;
+    const int ey0 = a.R * sy, ey1 = min(ey0 + a.R, g.ny);
     const size_t Npad = g.Npad;
     const int col0 = CG * ex;
     auto geo = [&](int k) { return st.GEO[k][lane]; };
@@ -851,12 +836,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps<SPH>, kPbbmLockstep<SPH> ? 1 :
         vl[2] = rv;
     }
 
-    for (int ey = ey0; ey < (LOCKSTEP ? ey0 + a.R : ey1); ++ey) {
-        if constexpr (LOCKSTEP) {
-            __syncthreads(); // the warps of the block walk the row body together (instruction-cache sharing)
-            if (ey >= ey1)
-                continue;
-        }
+    for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         cpAsyncWait<4>();
         __syncwarp(); // the mask bytes were staged by other lanes
