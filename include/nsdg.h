@@ -235,7 +235,9 @@ int nsdg_get_timing(nsdg_handle h, nsdg_timing* t);
 int nsdg_halo_export(nsdg_handle h, unsigned char* ipc_handle /* NSDG_IPC_HANDLE_BYTES */);
 /* map the arena of the neighbour across `side` (enum nsdg_side) */
 int nsdg_halo_connect(nsdg_handle h, int side, const unsigned char* peer_ipc_handle);
-/* all neighbour sides connected: from now on nsdg_step / nsdg_update / nsdg_subcycles exchange halos.
+/* all neighbour sides connected: from now on nsdg_step / nsdg_update / nsdg_subcycles exchange halos.  Resets this box's
+ * exchange epochs: after a re-mesh EVERY box of the partition calls export / connect / ready again, and none may start
+ * exchanging before all have returned from nsdg_halo_ready (a barrier in the launcher).
  * A box whose neighbour does not deliver within 30 s of wall-clock time (device %globaltimer) gives up; the entry
  * point then returns an error ("halo exchange timed out") instead of a result computed on stale ring data. */
 int nsdg_halo_ready(nsdg_handle h);

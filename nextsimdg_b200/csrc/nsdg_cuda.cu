@@ -679,6 +679,11 @@ public:
             throw std::runtime_error("nsdg_halo_connect: no neighbour on that side");
         cudaIpcMemHandle_t hnd;
         std::memcpy(&hnd, handle, sizeof(hnd));
+        if (peerArena[side]) { // reconnecting (the neighbour re-meshed): drop the mapping of its old arena
+            haloActive = false;
+            cudaIpcCloseMemHandle(peerArena[side]);
+            peerArena[side] = nullptr;
+        }
         void* ptr = nullptr;
         NSDG_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
         peerArena[side] = static_cast<unsigned char*>(ptr);
@@ -688,6 +693,14 @@ public:
         for (int s = 0; s < kHaloSides; ++s)
             if (hasNeighbour(s) && !peerArena[s])
                 throw std::runtime_error("nsdg_halo_ready: a neighbour side is not connected");
+        // a (re)connected partition starts from epoch zero on every box: the launcher lets no box exchange before all have
+        // passed this point (partition.connect_halos), so resetting my own flags and counters here cannot race a neighbour
+        if (cfg.global_nx > 0) {
+            NSDG_CUDA_CHECK(cudaMemsetAsync(haloState.p, 0, sizeof(HaloDevState), stream));
+            NSDG_CUDA_CHECK(cudaMemsetAsync(arena.p + arenaLayout.flagsOffsetBytes(), 0, 256, stream));
+            NSDG_CUDA_CHECK(cudaMemsetAsync(haloError.p, 0, sizeof(int), stream));
+            NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
         haloActive = cfg.global_nx > 0;
     }
     void closePeers()
