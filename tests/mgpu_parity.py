@@ -73,6 +73,31 @@ def main():
                 if not ok:
                     failures.append((rheo, kind, "reference", r))
         dist.barrier()
+    # a re-mesh on live, connected boxes: nsdg_set_mesh disconnects the halos, every box exports / connects / readies again
+    # (epochs restart at zero on all of them) and the rerun from the same initial data reproduces the first run bit for bit
+    from nextsimdg_b200 import CUDAMEVPDynamics
+    from nextsimdg_b200.partition import Partition, connect_halos, probe_inputs
+
+    ms, forc = probe_inputs("uniform")
+    gny, gnx = ms["mask"].shape
+    part = Partition.strong(rank, world, gnx, gny)
+    dyn = CUDAMEVPDynamics(nsteps=nsteps, device=local, partition=part)
+    runs = []
+    for attempt in range(2):
+        dyn.setData(part.crop_state(ms))
+        connect_halos(dyn, part, gather)
+        lw = part.local_window()
+        dyn.shared = {"hice": np.ascontiguousarray(ms["hice"][..., 0][lw]), "cice": np.ascontiguousarray(ms["cice"][..., 0][lw]),
+                      **{k: np.ascontiguousarray(v[lw]) for k, v in forc.items()}}
+        dyn.update(600.0)
+        runs.append((dyn.uice.copy(), dyn.vice.copy(), dyn.shared["hice"].copy()))
+    same = all(np.array_equal(a, b) for a, b in zip(*runs)) and float(np.abs(runs[0][0]).max()) > 0
+    flags = gather(bool(same))
+    dyn.close()
+    if rank == 0:
+        say(f"mgpu[{world}] re-mesh + reconnect on live boxes reproduces the first run bitwise: {'ok' if all(flags) else 'FAIL'}")
+        if not all(flags):
+            failures.append(("remesh", flags))
     ok = torch.tensor([0 if failures else 1], device="cuda")
     dist.broadcast(ok, 0)
     dist.destroy_process_group()
