@@ -359,6 +359,9 @@ def probe_inputs(kind: str):
     if kind == "spherical":
         ms = synthetic.topaz_like_spherical(64)
         return ms, synthetic.smooth_forcing(64, 64)
+    if kind == "topaz128":  # BASELINE.json configs[3] at full size
+        ms = synthetic.topaz_like_spherical(128)
+        return ms, synthetic.smooth_forcing(128, 128)
     ms = synthetic.para_state(96, 64, dxy=8000.0, distort=0.04 if kind == "distorted" else 0.0, irregular_mask=True)
     return ms, synthetic.smooth_forcing(96, 64)
 

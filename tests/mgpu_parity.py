@@ -57,7 +57,9 @@ def main():
         report.append(line)
 
     nsteps, nts = 40, 2
-    for rheo, kind in PROBE_CASES:
+    # + BASELINE.json configs[3]: the TOPAZ-like 128 x 128 spherical grid, 120 subcycles ("100+"), 2-D partitioned
+    for rheo, kind in list(PROBE_CASES) + [("mevp", "topaz128")]:
+        nsteps, nts = (120, 1) if kind == "topaz128" else (40, 2)
         errs = partition_probe(rheo, kind, rank, world, local, gather, nsteps=nsteps, nts=nts)
         if rank == 0:
             single = errs.pop("single")
@@ -81,7 +83,7 @@ def main():
     ms, forc = probe_inputs("uniform")
     gny, gnx = ms["mask"].shape
     part = Partition.strong(rank, world, gnx, gny)
-    dyn = CUDAMEVPDynamics(nsteps=nsteps, device=local, partition=part)
+    dyn = CUDAMEVPDynamics(nsteps=40, device=local, partition=part)
     runs = []
     for attempt in range(2):
         dyn.setData(part.crop_state(ms))
