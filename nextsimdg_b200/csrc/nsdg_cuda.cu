@@ -1286,8 +1286,66 @@ public:
         const UniformBBMArgs ba = makeUniformBBMArgs(deltaT);
         const unsigned nbStripF = (unsigned(nsx) * nsy + 3) / 4;
         const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
+        /*
+         * Partitioned box, fast kernels: the halo exchange of subcycle k is hidden behind the INTERIOR strips of subcycle k+1.
+         * After the deferred lines of subcycle k the work forks: the halo stream runs the exchange and then the EDGE strips
+         * of subcycle k+1 (the one-strip-wide band along the neighbour sides: the only strips that read ring nodes, and the
+         * only ones whose nodes travel), the compute stream runs the interior strips at the same time; both join before the
+         * deferred lines of subcycle k+1.  Interior strips touch neither ring nodes nor travelling lines (those lie inside
+         * edge strips or are deferred-line nodes, which no strip writes), so the two branches share no written data; the
+         * results are bitwise those of the plain sequence.  The fork / join is captured into the subcycle graph like
+         * everything else.  (Round 1 tried the opposite split -- frame strips and their lines BEFORE the exchange, a second
+         * lines pass after -- and lost 5 %: two extra launches, a split lines pass, a frame kernel running alone at poor
+         * occupancy.  Here the edge strips run concurrently with the interior ones and there is one lines pass.)
+         */
+        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && !std::getenv("NSDG_NO_HALO_OVERLAP");
+        if (overlap && !haloStream) {
+            int lo = 0, hi = 0;
+            NSDG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            NSDG_CUDA_CHECK(cudaStreamCreateWithPriority(&haloStream, cudaStreamNonBlocking, hi)); // edge strips first when both are ready
+            for (cudaEvent_t* e : { &evLines2, &evFrame, &evHalo })
+                NSDG_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+        StripSubset fr { 1, hasNeighbour(NSDG_LEFT) ? 1 : 0, hasNeighbour(NSDG_RIGHT) ? 1 : 0, hasNeighbour(NSDG_BOTTOM) ? 1 : 0,
+            hasNeighbour(NSDG_TOP) ? 1 : 0 };
+        UniformArgs uaE = ua, uaI = ua;
+        UniformBBMArgs baE = ba, baI = ba;
+        uaE.sub = baE.sub = fr; // subset 1: the edge band
+        fr.subset = 2;
+        uaI.sub = baI.sub = fr; // subset 2: everything else
+        auto strips = [&](const UniformArgs& x, const UniformBBMArgs& y) {
+            if (fastMEVP())
+                launchStripFast(x, nbStripF);
+            else
+                launchPairFastBBM(y, nbStripF, nLineF, true, false);
+        };
+        auto lines = [&]() {
+            if (fastMEVP())
+                launchLinesFast(ua, nLineF);
+            else
+                launchPairFastBBM(ba, nbStripF, nLineF, false, true);
+        };
         auto body = [&]() {
             for (int i = 0; i < n; ++i) {
+                if (overlap) {
+                    if (i == 0) {
+                        strips(ua, ba); // the halos are valid on entry
+                    } else {
+                        NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
+                        NSDG_CUDA_CHECK(cudaStreamWaitEvent(haloStream, evLines2, 0));
+                        std::swap(stream, haloStream);
+                        exchangeNodes(u, v); // of subcycle i - 1
+                        strips(uaE, baE);
+                        NSDG_CUDA_CHECK(cudaEventRecord(evFrame, stream));
+                        std::swap(stream, haloStream);
+                        strips(uaI, baI);
+                        NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evFrame, 0));
+                    }
+                    lines();
+                    if (i == n - 1)
+                        exchangeNodes(u, v); // leave with valid halos, as the plain sequence does
+                    continue;
+                }
                 if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
@@ -1300,62 +1358,6 @@ public:
                 exchangeNodes(u, v); // no-op for a single domain
             }
         };
-        /*
-         * Partitioned box, fast kernels: the halo exchange is hidden behind the interior strips.  Stream H runs the FRAME
-         * (the band of strips, two thick, along the neighbour sides -- every node line that travels is computed there),
-         * the deferred lines that lie inside it, and the exchange; the compute stream runs the interior strips, then the
-         * remaining deferred lines once the frame's line-buffer contributions exist.  Per subcycle H waits for the
-         * previous subcycle's second lines pass, the compute stream for the frame; nothing else is shared: interior strips
-         * read neither ring nodes nor frame-complete line nodes, and the second lines pass writes none of the travelling lines.
-         *
-         * MEASURED (2 GPUs, 2048^2 per GPU): 70.9 ms per 100 subcycles against 67.5 ms for the plain sequence -- the
-         * exchange it hides costs 27 us per subcycle, the two extra launches, the split lines pass and the frame kernel's
-         * poor occupancy cost ~60 us.  It is therefore OFF unless NSDG_HALO_OVERLAP=1 (profiles/r1_weak_scaling.txt).
-         */
-        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && std::getenv("NSDG_HALO_OVERLAP");
-        if (overlap) {
-            if (!haloStream) {
-                NSDG_CUDA_CHECK(cudaStreamCreateWithFlags(&haloStream, cudaStreamNonBlocking));
-                for (cudaEvent_t* e : { &evLines2, &evFrame, &evHalo })
-                    NSDG_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-            }
-            StripSubset fr { 1, hasNeighbour(NSDG_LEFT) ? 2 : 0, hasNeighbour(NSDG_RIGHT) ? 2 : 0, hasNeighbour(NSDG_BOTTOM) ? 2 : 0,
-                hasNeighbour(NSDG_TOP) ? 2 : 0 };
-            UniformArgs uaF = ua, uaI = ua;
-            UniformBBMArgs baF = ba, baI = ba;
-            uaF.sub = baF.sub = fr;
-            fr.subset = 2;
-            uaI.sub = baI.sub = fr;
-            auto pair = [&](const UniformArgs& x, const UniformBBMArgs& y, bool strips, bool lines) {
-                if (fastMEVP()) {
-                    if (strips)
-                        launchStripFast(x, nbStripF);
-                    if (lines)
-                        launchLinesFast(x, nLineF);
-                } else
-                    launchPairFastBBM(y, nbStripF, nLineF, !lines, !strips);
-            };
-            NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
-            for (int i = 0; i < n; ++i) {
-                // ---- stream H: frame strips, frame lines, exchange ----
-                NSDG_CUDA_CHECK(cudaStreamWaitEvent(haloStream, evLines2, 0));
-                std::swap(stream, haloStream);
-                pair(uaF, baF, true, true);
-                NSDG_CUDA_CHECK(cudaEventRecord(evFrame, stream));
-                exchangeNodes(u, v);
-                NSDG_CUDA_CHECK(cudaEventRecord(evHalo, stream));
-                std::swap(stream, haloStream);
-                // ---- compute stream: interior strips, then the remaining deferred lines ----
-                pair(uaI, baI, true, false);
-                NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evFrame, 0));
-                pair(uaI, baI, false, true);
-                NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
-            }
-            NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evHalo, 0));
-            NSDG_CUDA_CHECK(cudaGetLastError());
-            launches += 4L * n;
-            return;
-        }
         // partitioned boxes too: the exchange epochs are device state, the launch arguments never change
         if (cfg.use_cuda_graph && n > 1) {
             if (!graphExec || graphN != n || graphDeltaT != deltaT) {
@@ -1380,7 +1382,7 @@ public:
         // kernels per subcycle: strip + lines + one exchange kernel per active phase (a graph replay runs them without
         // passing through exchange(), which counts only at capture time)
         const int phasesActive = haloActive ? (hasNeighbour(NSDG_LEFT) || hasNeighbour(NSDG_RIGHT) ? 1 : 0) + (hasNeighbour(NSDG_BOTTOM) || hasNeighbour(NSDG_TOP) ? 1 : 0) : 0;
-        launches = launchesBefore + long(n) * (2 + phasesActive);
+        launches = launchesBefore + long(n) * (2 + phasesActive) + (overlap ? long(n - 1) : 0); // + the edge-strip launches
     }
 
     void subcycles(int n, float* ms) override
