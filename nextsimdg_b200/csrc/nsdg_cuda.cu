@@ -124,6 +124,7 @@ public:
     unsigned char* peerArena[kHaloSides] = { nullptr, nullptr, nullptr, nullptr }; //!< IPC-mapped neighbour arenas
     DevBuf<int> haloError;
     DevBuf<HaloDevState> haloState; //!< exchange epochs and block counters, advanced on the device
+    DevBuf<int> edgeStrips; //!< strips of the edge band (compact launch beside the interior strips)
     bool haloActive = false;
     // staging
     DevBuf<double> staging;
@@ -461,6 +462,19 @@ public:
             arena.alloc(arenaLayout.totalBytes());
             haloError.alloc(1);
             haloState.alloc(1); // zeroed: epochs restart with a new arena
+            // the edge band: strips of the first / last strip column or row towards a neighbour (the only strips that read ring
+            // nodes and the only ones whose nodes travel)
+            std::vector<int> band;
+            for (int sy = 0; sy < nsy; ++sy)
+                for (int sx = 0; sx < nsx; ++sx)
+                    if ((hasNeighbour(NSDG_LEFT) && sx == 0) || (hasNeighbour(NSDG_RIGHT) && sx == nsx - 1)
+                        || (hasNeighbour(NSDG_BOTTOM) && sy == 0) || (hasNeighbour(NSDG_TOP) && sy == nsy - 1))
+                        band.push_back(sy * nsx + sx);
+            edgeStrips.alloc(band.size());
+            if (!band.empty()) {
+                NSDG_CUDA_CHECK(cudaMemcpy(edgeStrips.p, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
+                legacySync();
+            }
         }
         meshSet = true;
     }
@@ -1216,7 +1230,7 @@ public:
     void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            const unsigned nStrips = unsigned(nsx) * nsy;
+            const unsigned nStrips = ba.sub.list ? unsigned(ba.sub.count) : unsigned(nsx) * nsy;
             if (!linesOnly && fastParamBBM)
                 launchStripPBBM(ba, g.spherical != 0, nStrips, stream);
             else if (!linesOnly)
@@ -1228,7 +1242,7 @@ public:
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            const unsigned nStrips = unsigned(nsx) * nsy;
+            const unsigned nStrips = ua.sub.list ? unsigned(ua.sub.count) : unsigned(nsx) * nsy;
             if (fastParamMEVP)
                 launchStripPMEVP(ua, g.spherical != 0, nStrips, stream);
             else
@@ -1298,7 +1312,7 @@ public:
          * lines pass after -- and lost 5 %: two extra launches, a split lines pass, a frame kernel running alone at poor
          * occupancy.  Here the edge strips run concurrently with the interior ones and there is one lines pass.)
          */
-        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && !std::getenv("NSDG_NO_HALO_OVERLAP");
+        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && edgeStrips.n > 0 && !std::getenv("NSDG_NO_HALO_OVERLAP");
         if (overlap && !haloStream) {
             int lo = 0, hi = 0;
             NSDG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1310,7 +1324,11 @@ public:
             hasNeighbour(NSDG_TOP) ? 1 : 0 };
         UniformArgs uaE = ua, uaI = ua;
         UniformBBMArgs baE = ba, baI = ba;
+        fr.list = edgeStrips.p; // compact launch: a full grid of which 95 % of the warps exit at once costs more than it hides
+        fr.count = int(edgeStrips.n);
         uaE.sub = baE.sub = fr; // subset 1: the edge band
+        fr.list = nullptr;
+        fr.count = 0;
         fr.subset = 2;
         uaI.sub = baI.sub = fr; // subset 2: everything else
         auto strips = [&](const UniformArgs& x, const UniformBBMArgs& y) {
