@@ -1311,8 +1311,15 @@ public:
          * everything else.  (Round 1 tried the opposite split -- frame strips and their lines BEFORE the exchange, a second
          * lines pass after -- and lost 5 %: two extra launches, a split lines pass, a frame kernel running alone at poor
          * occupancy.  Here the edge strips run concurrently with the interior ones and there is one lines pass.)
+         *
+         * MEASURED (2048^2 per GPU, same box, A/B): 2 GPUs 68.2 ms per step with the overlap against 67.4 ms without, 4 GPUs
+         * 70.0 against 69.8 ms; strong scaling (2048^2 in total) 36.2 against 36.6 ms and 21.8 against 21.6-21.9 ms.  With the
+         * one-kernel exchange inside the graph there is almost nothing left to hide: the exchange itself costs a few
+         * microseconds per subcycle when the boxes run in step, and what separates N GPUs from one is the ring's 65th strip
+         * column (+1.6 %) and strip kernels that run ~3 % slower when every GPU of the box is busy.  OFF unless
+         * NSDG_HALO_OVERLAP=1; parity with it is in profiles/r2_mgpu_parity_n{2,4}.txt.
          */
-        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && edgeStrips.n > 0 && !std::getenv("NSDG_NO_HALO_OVERLAP");
+        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && edgeStrips.n > 0 && std::getenv("NSDG_HALO_OVERLAP");
         if (overlap && !haloStream) {
             int lo = 0, hi = 0;
             NSDG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
