@@ -78,8 +78,6 @@ public:
     bool uniform = false;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr; //!< update(): forcing uploads / early downloads beside the compute stream
-    cudaStream_t haloStream = nullptr; //!< partitioned boxes: frame strips + halo exchange beside the interior strips
-    cudaEvent_t evLines2 = nullptr, evFrame = nullptr, evHalo = nullptr;
     cudaEvent_t evForcing = nullptr, evCopyDone = nullptr;
     bool forcingPending = false;
     cudaEvent_t ev[5] {};
@@ -124,7 +122,6 @@ public:
     unsigned char* peerArena[kHaloSides] = { nullptr, nullptr, nullptr, nullptr }; //!< IPC-mapped neighbour arenas
     DevBuf<int> haloError;
     DevBuf<HaloDevState> haloState; //!< exchange epochs and block counters, advanced on the device
-    DevBuf<int> edgeStrips; //!< strips of the edge band (compact launch beside the interior strips)
     bool haloActive = false;
     // staging
     DevBuf<double> staging;
@@ -163,9 +160,7 @@ public:
         for (auto& e : ev)
             if (e)
                 cudaEventDestroy(e);
-        if (haloStream)
-            cudaStreamDestroy(haloStream);
-        for (cudaEvent_t e : { evForcing, evCopyDone, evLines2, evFrame, evHalo })
+        for (cudaEvent_t e : { evForcing, evCopyDone })
             if (e)
                 cudaEventDestroy(e);
         if (copyStream)
@@ -462,19 +457,6 @@ public:
             arena.alloc(arenaLayout.totalBytes());
             haloError.alloc(1);
             haloState.alloc(1); // zeroed: epochs restart with a new arena
-            // the edge band: strips of the first / last strip column or row towards a neighbour (the only strips that read ring
-            // nodes and the only ones whose nodes travel)
-            std::vector<int> band;
-            for (int sy = 0; sy < nsy; ++sy)
-                for (int sx = 0; sx < nsx; ++sx)
-                    if ((hasNeighbour(NSDG_LEFT) && sx == 0) || (hasNeighbour(NSDG_RIGHT) && sx == nsx - 1)
-                        || (hasNeighbour(NSDG_BOTTOM) && sy == 0) || (hasNeighbour(NSDG_TOP) && sy == nsy - 1))
-                        band.push_back(sy * nsx + sx);
-            edgeStrips.alloc(band.size());
-            if (!band.empty()) {
-                NSDG_CUDA_CHECK(cudaMemcpy(edgeStrips.p, band.data(), band.size() * sizeof(int), cudaMemcpyHostToDevice));
-                legacySync();
-            }
         }
         meshSet = true;
     }
@@ -1230,7 +1212,7 @@ public:
     void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            const unsigned nStrips = ba.sub.list ? unsigned(ba.sub.count) : unsigned(nsx) * nsy;
+            const unsigned nStrips = unsigned(nsx) * nsy;
             if (!linesOnly && fastParamBBM)
                 launchStripPBBM(ba, g.spherical != 0, nStrips, stream);
             else if (!linesOnly)
@@ -1242,7 +1224,7 @@ public:
     void launchStripFast(const UniformArgs& ua, unsigned nbStrip)
     {
         if constexpr (CG == 2 && DGA == 6) {
-            const unsigned nStrips = ua.sub.list ? unsigned(ua.sub.count) : unsigned(nsx) * nsy;
+            const unsigned nStrips = unsigned(nsx) * nsy;
             if (fastParamMEVP)
                 launchStripPMEVP(ua, g.spherical != 0, nStrips, stream);
             else
@@ -1300,77 +1282,8 @@ public:
         const UniformBBMArgs ba = makeUniformBBMArgs(deltaT);
         const unsigned nbStripF = (unsigned(nsx) * nsy + 3) / 4;
         const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
-        /*
-         * Partitioned box, fast kernels: the halo exchange of subcycle k is hidden behind the INTERIOR strips of subcycle k+1.
-         * After the deferred lines of subcycle k the work forks: the halo stream runs the exchange and then the EDGE strips
-         * of subcycle k+1 (the one-strip-wide band along the neighbour sides: the only strips that read ring nodes, and the
-         * only ones whose nodes travel), the compute stream runs the interior strips at the same time; both join before the
-         * deferred lines of subcycle k+1.  Interior strips touch neither ring nodes nor travelling lines (those lie inside
-         * edge strips or are deferred-line nodes, which no strip writes), so the two branches share no written data; the
-         * results are bitwise those of the plain sequence.  The fork / join is captured into the subcycle graph like
-         * everything else.  (Round 1 tried the opposite split -- frame strips and their lines BEFORE the exchange, a second
-         * lines pass after -- and lost 5 %: two extra launches, a split lines pass, a frame kernel running alone at poor
-         * occupancy.  Here the edge strips run concurrently with the interior ones and there is one lines pass.)
-         *
-         * MEASURED (2048^2 per GPU, same box, A/B): 2 GPUs 68.2 ms per step with the overlap against 67.4 ms without, 4 GPUs
-         * 70.0 against 69.8 ms; strong scaling (2048^2 in total) 36.2 against 36.6 ms and 21.8 against 21.6-21.9 ms.  With the
-         * one-kernel exchange inside the graph there is almost nothing left to hide: the exchange itself costs a few
-         * microseconds per subcycle when the boxes run in step, and what separates N GPUs from one is the ring's 65th strip
-         * column (+1.6 %) and strip kernels that run ~3 % slower when every GPU of the box is busy.  OFF unless
-         * NSDG_HALO_OVERLAP=1; parity with it is in profiles/r2_mgpu_parity_n{2,4}.txt.
-         */
-        const bool overlap = haloActive && (fastMEVP() || fastBBM()) && edgeStrips.n > 0 && std::getenv("NSDG_HALO_OVERLAP");
-        if (overlap && !haloStream) {
-            int lo = 0, hi = 0;
-            NSDG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            NSDG_CUDA_CHECK(cudaStreamCreateWithPriority(&haloStream, cudaStreamNonBlocking, hi)); // edge strips first when both are ready
-            for (cudaEvent_t* e : { &evLines2, &evFrame, &evHalo })
-                NSDG_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        }
-        StripSubset fr { 1, hasNeighbour(NSDG_LEFT) ? 1 : 0, hasNeighbour(NSDG_RIGHT) ? 1 : 0, hasNeighbour(NSDG_BOTTOM) ? 1 : 0,
-            hasNeighbour(NSDG_TOP) ? 1 : 0 };
-        UniformArgs uaE = ua, uaI = ua;
-        UniformBBMArgs baE = ba, baI = ba;
-        fr.list = edgeStrips.p; // compact launch: a full grid of which 95 % of the warps exit at once costs more than it hides
-        fr.count = int(edgeStrips.n);
-        uaE.sub = baE.sub = fr; // subset 1: the edge band
-        fr.list = nullptr;
-        fr.count = 0;
-        fr.subset = 2;
-        uaI.sub = baI.sub = fr; // subset 2: everything else
-        auto strips = [&](const UniformArgs& x, const UniformBBMArgs& y) {
-            if (fastMEVP())
-                launchStripFast(x, nbStripF);
-            else
-                launchPairFastBBM(y, nbStripF, nLineF, true, false);
-        };
-        auto lines = [&]() {
-            if (fastMEVP())
-                launchLinesFast(ua, nLineF);
-            else
-                launchPairFastBBM(ba, nbStripF, nLineF, false, true);
-        };
         auto body = [&]() {
             for (int i = 0; i < n; ++i) {
-                if (overlap) {
-                    if (i == 0) {
-                        strips(ua, ba); // the halos are valid on entry
-                    } else {
-                        NSDG_CUDA_CHECK(cudaEventRecord(evLines2, stream));
-                        NSDG_CUDA_CHECK(cudaStreamWaitEvent(haloStream, evLines2, 0));
-                        std::swap(stream, haloStream);
-                        exchangeNodes(u, v); // of subcycle i - 1
-                        strips(uaE, baE);
-                        NSDG_CUDA_CHECK(cudaEventRecord(evFrame, stream));
-                        std::swap(stream, haloStream);
-                        strips(uaI, baI);
-                        NSDG_CUDA_CHECK(cudaStreamWaitEvent(stream, evFrame, 0));
-                    }
-                    lines();
-                    if (i == n - 1)
-                        exchangeNodes(u, v); // leave with valid halos, as the plain sequence does
-                    continue;
-                }
                 if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
@@ -1383,6 +1296,16 @@ public:
                 exchangeNodes(u, v); // no-op for a single domain
             }
         };
+        /*
+         * Hiding the exchange behind strips that do not need it was built twice and is NOT in the library.  Round 1: frame
+         * strips and their lines first, exchange beside the interior strips, a second lines pass -- 5 % slower (two extra
+         * launches, a split lines pass, a frame kernel alone at poor occupancy).  Round 2: after the lines of subcycle k the
+         * graph forks into {exchange(k), then the edge band of subcycle k+1 as a compact launch} and {interior strips of k+1},
+         * one lines pass after the join -- measured A/B on the same boxes at 2048^2 per GPU: 68.2 against 67.4 ms per step on
+         * 2 GPUs, 70.0 against 69.8 ms on 4.  With the one-kernel exchange inside the graph there is nothing left to hide: the
+         * exchange costs a few microseconds per subcycle when the boxes run in step; what separates N GPUs from one is the
+         * ring's 65th strip column and strip kernels that run ~3 % slower when every GPU of the box is busy.
+         */
         // partitioned boxes too: the exchange epochs are device state, the launch arguments never change
         if (cfg.use_cuda_graph && n > 1) {
             if (!graphExec || graphN != n || graphDeltaT != deltaT) {
@@ -1407,7 +1330,7 @@ public:
         // kernels per subcycle: strip + lines + one exchange kernel per active phase (a graph replay runs them without
         // passing through exchange(), which counts only at capture time)
         const int phasesActive = haloActive ? (hasNeighbour(NSDG_LEFT) || hasNeighbour(NSDG_RIGHT) ? 1 : 0) + (hasNeighbour(NSDG_BOTTOM) || hasNeighbour(NSDG_TOP) ? 1 : 0) : 0;
-        launches = launchesBefore + long(n) * (2 + phasesActive) + (overlap ? long(n - 1) : 0); // + the edge-strip launches
+        launches = launchesBefore + long(n) * (2 + phasesActive);
     }
 
     void subcycles(int n, float* ms) override

@@ -431,8 +431,8 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-    const int w = stripOfWarp(a.sub, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), a.nsx * a.nsy);
-    if (w < 0)
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
         return;
     PmevpStage<SPH>& st = reinterpret_cast<PmevpStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
@@ -728,8 +728,8 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
     constexpr int GB = geoPlanes(SPH); // first BBM-specific plane
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-    const int w = stripOfWarp(a.sub, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), a.nsx * a.nsy);
-    if (w < 0)
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
         return;
     PbbmStage<SPH>& st = reinterpret_cast<PbbmStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;

@@ -124,17 +124,7 @@ __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefet
  */
 struct StripSubset {
     int subset, frL, frR, frB, frT;
-    const int* list; //!< compact launch: the strips of the launch, one warp per entry (nullptr: warp w takes strip w)
-    int count;
 };
-//! the strip a warp works on, or -1.  A compact launch (the edge band of a partitioned box: ~5 % of the strips) carries
-//! the list of its strips, so that its grid holds only warps with work.
-__device__ __forceinline__ int stripOfWarp(const StripSubset& f, int warp, int nStrips)
-{
-    if (f.list != nullptr)
-        return warp < f.count ? f.list[warp] : -1;
-    return warp < nStrips ? warp : -1;
-}
 __device__ __forceinline__ bool inFrame(const StripSubset& f, int nsx, int nsy, int sx, int sy)
 {
     return sx < f.frL || sx >= nsx - f.frR || sy < f.frB || sy >= nsy - f.frT;
@@ -344,8 +334,8 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-    const int w = stripOfWarp(a.sub, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), a.nsx * a.nsy);
-    if (w < 0)
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
         return;
     UmevpStage& st = reinterpret_cast<UmevpStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
-    const int w = stripOfWarp(a.sub, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), a.nsx * a.nsy);
-    if (w < 0)
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.nsx * a.nsy)
         return;
     UbbmStage& st = reinterpret_cast<UbbmStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;

@@ -10,5 +10,4 @@ if [ "$N" = "2" ]; then
   (timeout 900 python -m pytest tests/test_gpu_parity.py -q -k "multi_gpu or two_devices") > gpurun_out/r2_mgpu_pytest_n$N.log 2>&1; tail -3 gpurun_out/r2_mgpu_pytest_n$N.log
 fi
 run 29512 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_weak_n$N.json 2> gpurun_out/r2_bench_weak_n$N.err; tail -2 gpurun_out/r2_bench_weak_n$N.err; head -c 300 gpurun_out/r2_bench_weak_n$N.json; echo
-NSDG_HALO_OVERLAP=1 run 29514 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_weak_n${N}_overlap.json 2> /dev/null; head -c 300 gpurun_out/r2_bench_weak_n${N}_overlap.json; echo
 run 29513 bench.py --gpus $N --steps 5 --warmup 3 --scaling strong > gpurun_out/r2_bench_strong_n$N.json 2> gpurun_out/r2_bench_strong_n$N.err; tail -2 gpurun_out/r2_bench_strong_n$N.err; head -c 300 gpurun_out/r2_bench_strong_n$N.json; echo
