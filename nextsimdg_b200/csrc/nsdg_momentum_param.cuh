@@ -44,6 +44,10 @@
 
 namespace nsdg {
 
+#ifndef NSDG_PARAM_SEP
+#define NSDG_PARAM_SEP 1 //!< the constant tables as 1-d passes (q2Values / q2Derivs, evalGaussSep, projectSep) in the parametric kernels
+#endif
+
 //! planes: xxi[3] yxi[3] (per Gauss row qy), xeta[3] yeta[3] (per Gauss column qx), 1/J[9] (spherical: 1/(J cos)), gamma,
 //! spherical only: cos(lat)[9], sin(lat)[9]
 constexpr int kGeoPlanes = 22, kGeoPlanesSph = 40;
@@ -140,6 +144,28 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
 {
     constexpr double iR = 1.0 / EarthRadius;
     double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3]; // [jy][qx]: value / xi-derivative contracted in x
+#if NSDG_PARAM_SEP
+    double Uxi[3][3], Ueta[3][3], Vxi[3][3], Veta[3][3]; // [qy][qx]: reference derivatives in the Gauss points
+    [[maybe_unused]] double Uq[3][3], Vq[3][3];
+#pragma unroll
+    for (int jy = 0; jy < 3; ++jy) {
+        q2Values(ul[3 * jy], ul[3 * jy + 1], ul[3 * jy + 2], Au[jy][0], Au[jy][1], Au[jy][2]);
+        q2Derivs(ul[3 * jy], ul[3 * jy + 1], ul[3 * jy + 2], Adu[jy][0], Adu[jy][1], Adu[jy][2]);
+        q2Values(vl[3 * jy], vl[3 * jy + 1], vl[3 * jy + 2], Av[jy][0], Av[jy][1], Av[jy][2]);
+        q2Derivs(vl[3 * jy], vl[3 * jy + 1], vl[3 * jy + 2], Adv[jy][0], Adv[jy][1], Adv[jy][2]);
+    }
+#pragma unroll
+    for (int qx = 0; qx < 3; ++qx) {
+        q2Values(Adu[0][qx], Adu[1][qx], Adu[2][qx], Uxi[0][qx], Uxi[1][qx], Uxi[2][qx]);
+        q2Derivs(Au[0][qx], Au[1][qx], Au[2][qx], Ueta[0][qx], Ueta[1][qx], Ueta[2][qx]);
+        q2Values(Adv[0][qx], Adv[1][qx], Adv[2][qx], Vxi[0][qx], Vxi[1][qx], Vxi[2][qx]);
+        q2Derivs(Av[0][qx], Av[1][qx], Av[2][qx], Veta[0][qx], Veta[1][qx], Veta[2][qx]);
+        if constexpr (SPH) {
+            q2Values(Au[0][qx], Au[1][qx], Au[2][qx], Uq[0][qx], Uq[1][qx], Uq[2][qx]);
+            q2Values(Av[0][qx], Av[1][qx], Av[2][qx], Vq[0][qx], Vq[1][qx], Vq[2][qx]);
+        }
+    }
+#else
     static_for<3>([&](auto JY) {
         static_for<3>([&](auto QX) {
             constexpr int jy = decltype(JY)::value, qx = decltype(QX)::value;
@@ -162,11 +188,15 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
             Adv[jy][qx] = s3;
         });
     });
+#endif
     static_for<3>([&](auto QY) {
         constexpr int qy = decltype(QY)::value;
         const double xxi = geo(0 + qy), yxi = geo(3 + qy);
         static_for<3>([&](auto QX) {
             constexpr int qx = decltype(QX)::value, q = qy * 3 + qx;
+#if NSDG_PARAM_SEP
+            const double uxi = Uxi[qy][qx], ueta = Ueta[qy][qx], vxi = Vxi[qy][qx], veta = Veta[qy][qx];
+#else
             double uxi = 0, ueta = 0, vxi = 0, veta = 0; // reference derivatives
             static_for<3>([&](auto JY) {
                 constexpr int jy = decltype(JY)::value;
@@ -180,6 +210,7 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
                     veta = fma(lp, Av[jy][qx], veta);
                 }
             });
+#endif
             const double xeta = geo(6 + qx), yeta = geo(9 + qx), iJ = geo(12 + q);
             // J d/dx = yeta d/dxi - yxi d/deta ;  J d/dy = xxi d/deta - xeta d/dxi   (ParametricMap.cpp:248-254)
             if constexpr (!SPH) {
@@ -190,6 +221,9 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
                 e12[q] = 0.5 * (uy + vx);
             } else {
                 // values of u, v in the Gauss point for the metric terms (divM / iMM, ParametricMap.cpp:321-337)
+#if NSDG_PARAM_SEP
+                const double uq = Uq[qy][qx], vq = Vq[qy][qx];
+#else
                 double uq = 0, vq = 0;
                 static_for<3>([&](auto JY) {
                     constexpr int jy = decltype(JY)::value;
@@ -199,6 +233,7 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
                         vq = fma(l, Av[jy][qx], vq);
                     }
                 });
+#endif
                 const double cl = geo(22 + q), sl = geo(31 + q);
                 const double Js = (xxi * yeta - yxi * xeta) * sl; // J sin(lat)
                 const double k = iJ * iR; //                         1 / (R J cos)
@@ -219,6 +254,10 @@ __device__ __forceinline__ void gaussStrain(const GEO& geo, const double (&ul)[9
 //! DG coefficients (first NC basis functions) of a field of the DG space given by its Gauss-point values
 template <int NC> __device__ __forceinline__ void coeffFromGauss(const double (&r)[9], double (&s)[NC])
 {
+#if NSDG_PARAM_SEP
+    projectSep<NC>(r, s);
+    return;
+#endif
     static_for<NC>([&](auto J) {
         constexpr int j = decltype(J)::value;
         double acc = 0.0;
@@ -233,6 +272,10 @@ template <int NC> __device__ __forceinline__ void coeffFromGauss(const double (&
 }
 template <int NC> __device__ __forceinline__ void gaussFromCoeff(const double (&s)[NC], double (&r)[9])
 {
+#if NSDG_PARAM_SEP
+    evalGaussSep<NC>(s, r);
+    return;
+#endif
     static_for<9>([&](auto QQ) {
         constexpr int q = decltype(QQ)::value;
         double acc = 0.0;
@@ -568,7 +611,11 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
             constexpr int q = decltype(QQ)::value;
             const double Pa = st.P[q][lane];
             const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+#if NSDG_MEVP_SQRT & 2
+            const double iD = rsqrtBranchFree(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+#else
             const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+#endif
             const double pd = 0.125 * Pa * iD;
             e11[q] = fma(pd, 5.0 * g11 + 3.0 * g22, -0.5 * Pa);
             e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);
@@ -717,11 +764,14 @@ template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
     double UVr[2][2];
     double pad[2];
 };
-constexpr int kPbbmWarps = 2;
+#ifndef NSDG_PBBM_WARPS
+#define NSDG_PBBM_WARPS 2 //!< warps per block (1 or 2): 8 warps per SM on Cartesian meshes, 6 on spherical ones (shared memory)
+#endif
+constexpr int kPbbmWarps = NSDG_PBBM_WARPS;
 template <bool SPH> constexpr size_t pbbmSmemBytes() { return sizeof(PbbmStage<SPH>) * kPbbmWarps; }
 
 template <bool SPH>
-__global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
+__global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) subcycle_strip_pbbm(const __grid_constant__ UniformBBMArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
@@ -881,13 +931,29 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 dc[j] = st.D[j][lane];
             const double scale = geo(GB + 6), invTdK = geo(GB + 7);
             const double cohScale = a.C_lab * scale, comprScale = a.compr_strength * scale;
+#if NSDG_PARAM_SEP
+            double t11q[9], t12q[9], t22q[9], dq[9];
+            evalGaussSep<DGs>(s11c, t11q);
+            evalGaussSep<DGs>(s12c, t12q);
+            evalGaussSep<DGs>(s22c, t22q);
+            evalGaussSep<DGA>(dc, dq);
+#endif
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
+#if NSDG_PARAM_SEP
+                double t11 = t11q[q], t12 = t12q[q], t22 = t22q[q], d = dq[q];
+#else
                 double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
                 double d = evalGauss<DGA, 3, q>(dc);
+#endif
                 const double h = st.G[q][lane], expC = st.G[9 + q][lane], Pmax = st.G[18 + q][lane];
                 const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+#if NSDG_PARAM_SEP
+                d = d < 1e-12 ? 1e-12 : d; // compare + select (fmin / fmax: five instructions each for their NaN rules)
+                d = d > 1.0 ? 1.0 : d;
+#else
                 d = fmin(fmax(d, 1e-12), 1.0);
+#endif
                 double sigma_n = 0.5 * (t11 + t22);
                 const double de = d * expC, de2 = de * de;
                 const double tv = a.lambda0 * (de2 * de2);
@@ -906,14 +972,26 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 t12 = (t12 + Dunit * g12 * (1.0 - a.nu0)) * mult;
                 sigma_n = 0.5 * (t11 + t22);
                 const double tau2 = 0.25 * (t11 - t22) * (t11 - t22) + t12 * t12;
+#if NSDG_BBM_SQRT & 2
+                const double tau = sqrtBranchFree(tau2);
+#else
                 const double tau = fastSqrt(tau2);
+#endif
                 const double cohesion = cohScale * h, compr = comprScale * h;
                 const double mc = tau + a.tan_phi * sigma_n;
                 // one division: the compressive cap, when active, replaces the Mohr-Coulomb value (same operands, same result)
                 const bool capped = sigma_n < -compr;
                 double dcrit = (capped || mc > 0.0) ? (capped ? -compr : cohesion) * fastRcp(capped ? sigma_n : mc) : 1.0;
+#if NSDG_PARAM_SEP
+                dcrit = dcrit > 1.0 ? 1.0 : dcrit;
+#else
                 dcrit = fmin(dcrit, 1.0);
+#endif
+#if NSDG_BBM_SQRT & 4
+                const double sqrtE = sqrtBranchFree(elasticity);
+#else
                 const double sqrtE = fastSqrt(elasticity);
+#endif
                 const double relax = (1.0 - dcrit) * a.deltaT * (sqrtE * invTdK);
                 double dn = d - d * relax;
                 t11 -= t11 * relax;
@@ -973,7 +1051,11 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, SPH ? 3 : 4) subcycle_strip_p
                 for (int j = 0; j < DGs; ++j)
                     plane[size_t(j) * Npad + e] = s[j];
             }
+#if !NSDG_PARAM_SEP
             gaussFromCoeff<DGs>(s, r);
+#endif
+            // r already holds the values of the stored coefficients in the Gauss points: after projectDG8x3 it lies in the
+            // DG8 space, where (evaluate) o (B^) is the identity
         };
         component(a.s11, e11);
         component(a.s12, e12);

@@ -75,6 +75,143 @@ struct UnitOps {
 inline constexpr UnitOps kUnitOps {};
 
 /*
+ * The same tables as two 1-d passes.  DG8 is the tensor product of {p0, p1, p2} = {1, t, t^2 - 1/12} (t = x - 1/2)
+ * without the (2,2) mode -- coefficient j <-> (a, b): 0 (0,0), 1 (1,0), 2 (0,1), 3 (2,0), 4 (0,2), 5 (1,1), 6 (2,1),
+ * 7 (1,2); DG6 is its first six -- and the 9 Gauss points are the product of the 1-d points t = -g, 0, +g.  So
+ *   evaluation in the 9 points  (PSI<DG,3>, 55 / 43 multiply-adds as a table)  = 28 / 25 operations, 3 constants,
+ *   the projection B (iMJwPSI on a rectangle, 55 / 43)                         = 40 / 36 operations, 4 constants,
+ * using p1(+-g) = +-g, p2(+-g) = 1/15, p2(0) = -1/12 and 1 / int p_a^2 = 1, 12, 180.  Same linear maps, other grouping.
+ */
+namespace sep {
+    inline constexpr double g = 0.5 - gausspoint(3, 0); //!< sqrt(3/20)
+    inline constexpr double p2e = 1.0 / 15.0, p2c = -1.0 / 12.0;
+    inline constexpr double we = 5.0 / 18.0, wc = 8.0 / 18.0;
+    inline constexpr double o1 = 12.0 * we * g; //!< odd mode: 12 w_e g
+    inline constexpr double q2 = 10.0 / 3.0; //!< quadratic mode: 180 w_e / 15 = 180 w_c / 24
+}
+//! 1-d pass: values in the points (-g, 0, +g) of c0 p0 + c1 p1 + c2 p2
+NSDG_HD void sepEval1(double c0, double c1, double c2, double& vm, double& v0, double& vp)
+{
+    const double e = fma(sep::p2e, c2, c0), o = sep::g * c1;
+    v0 = fma(sep::p2c, c2, c0);
+    vm = e - o;
+    vp = e + o;
+}
+NSDG_HD void sepEval1(double c0, double c1, double& vm, double& v0, double& vp)
+{
+    const double o = sep::g * c1;
+    v0 = c0;
+    vm = c0 - o;
+    vp = c0 + o;
+}
+//! values of a DG8 (NC = 8) or DG6 (NC = 6) row in the 9 Gauss points, q = 3 qy + qx
+template <int NC> NSDG_HD void evalGaussSep(const double (&c)[NC], double (&out)[9])
+{
+    static_assert(NC == 8 || NC == 6);
+    double X0[3], X1[3], X2[3]; // x pass: coefficient of p_b(y) in the three x points
+    sepEval1(c[0], c[1], c[3], X0[0], X0[1], X0[2]);
+    if constexpr (NC == 8) {
+        sepEval1(c[2], c[5], c[6], X1[0], X1[1], X1[2]);
+        sepEval1(c[4], c[7], X2[0], X2[1], X2[2]);
+    } else {
+        sepEval1(c[2], c[5], X1[0], X1[1], X1[2]);
+        X2[0] = X2[1] = X2[2] = c[4];
+    }
+#pragma unroll
+    for (int qx = 0; qx < 3; ++qx)
+        sepEval1(X0[qx], X1[qx], X2[qx], out[qx], out[3 + qx], out[6 + qx]);
+}
+//! 1-d pass of the projection: the three weighted moments of values in the points (-g, 0, +g)
+NSDG_HD void sepProj1(double rm, double r0, double rp, double& m0, double& m1, double& m2)
+{
+    const double s = rm + rp, d = rp - rm;
+    m0 = fma(sep::we, s, sep::wc * r0);
+    m1 = sep::o1 * d;
+    m2 = sep::q2 * fma(-2.0, r0, s);
+}
+//! DG8 / DG6 coefficients of the L2 projection of Gauss-point values on a rectangle (the table UnitOps::B)
+template <int NC> NSDG_HD void projectSep(const double (&r)[9], double (&c)[NC])
+{
+    static_assert(NC == 8 || NC == 6);
+    double Y0[3], Y1[3], Y2[3]; // y pass: moment b of the column qx
+#pragma unroll
+    for (int qx = 0; qx < 3; ++qx)
+        sepProj1(r[qx], r[3 + qx], r[6 + qx], Y0[qx], Y1[qx], Y2[qx]);
+    sepProj1(Y0[0], Y0[1], Y0[2], c[0], c[1], c[3]);
+    if constexpr (NC == 8) {
+        sepProj1(Y1[0], Y1[1], Y1[2], c[2], c[5], c[6]);
+        const double s = Y2[0] + Y2[2];
+        c[4] = fma(sep::we, s, sep::wc * Y2[1]);
+        c[7] = sep::o1 * (Y2[2] - Y2[0]);
+    } else {
+        const double s = Y1[0] + Y1[2];
+        c[2] = fma(sep::we, s, sep::wc * Y1[1]);
+        c[5] = sep::o1 * (Y1[2] - Y1[0]);
+        c[4] = fma(sep::we, Y2[0] + Y2[2], sep::wc * Y2[1]);
+    }
+}
+//! Q2 interpolation in 1-d from the nodes t = -1/2, 0, 1/2 to the Gauss points -g, 0, +g: values (vm, v0, vp) and derivatives
+//! (dm, d0, dp) of c0 L0 + c1 L1 + c2 L2, L0 = 2t^2 - t, L1 = 1 - 4t^2, L2 = 2t^2 + t: f = 2t^2 S + (1 - 4t^2) c1 + t D,
+//! f' = 4t (S - 2 c1) + D with S = c0 + c2, D = c2 - c0 (the tables UnitOps::L, ::Lp; 10 operations instead of 14)
+NSDG_HD void q2Values(double c0, double c1, double c2, double& vm, double& v0, double& vp)
+{
+    const double e = fma(2.0 * sep::g * sep::g, c0 + c2, (1.0 - 4.0 * sep::g * sep::g) * c1), o = sep::g * (c2 - c0);
+    vm = e - o;
+    v0 = c1;
+    vp = e + o;
+}
+NSDG_HD void q2Derivs(double c0, double c1, double c2, double& dm, double& d0, double& dp)
+{
+    const double t = (4.0 * sep::g) * fma(-2.0, c1, c0 + c2);
+    d0 = c2 - c0;
+    dm = d0 - t;
+    dp = d0 + t;
+}
+
+/*
+ * The divergence tables likewise: D1[(c,d)][(a,b)] = A1[c][a] A0[d][b], D2 = A0[c][a] A1[d][b] with the 1-d integrals of the
+ * Q2 node functions (nodes t = -1/2, 0, 1/2) against p_b, A0 = [[1/6, -1/12, 1/90], [2/3, 0, -1/45], [1/6, 1/12, 1/90]], and of
+ * their derivatives, A1 = [[-1, 1/3, 0], [0, -2/3, 0], [1, 1/3, 0]] (p2 is orthogonal to the linear derivatives, so only the
+ * modes a <= 1 of the differentiated direction contribute): 26 operations per table and stress component instead of 40.
+ */
+NSDG_HD void sepMass1(double c0, double c1, double c2, double& w0, double& w1, double& w2)
+{
+    const double e = fma(1.0 / 90.0, c2, (1.0 / 6.0) * c0), o = (1.0 / 12.0) * c1;
+    w0 = e - o;
+    w2 = e + o;
+    w1 = fma(-1.0 / 45.0, c2, (2.0 / 3.0) * c0);
+}
+//! T (+)= scale * D s for one DG8 stress component: D = UnitOps::D1 (DIR = 0) or D2 (DIR = 1); scale3 = scale / 3;
+//! T[k], k = 3 jy + jx as in the tables
+template <int DIR, bool ACC> NSDG_HD void divergenceSep(const double (&s)[8], double scale, double scale3, double (&T)[9])
+{
+    double W0[3], W1[3]; // undifferentiated direction first: modes 0 and 1 of the differentiated one at the three nodes
+    if constexpr (DIR == 0) {
+        sepMass1(s[0], s[2], s[4], W0[0], W0[1], W0[2]);
+        sepMass1(s[1], s[5], s[7], W1[0], W1[1], W1[2]);
+    } else {
+        sepMass1(s[0], s[1], s[3], W0[0], W0[1], W0[2]);
+        sepMass1(s[2], s[5], s[6], W1[0], W1[1], W1[2]);
+    }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        constexpr int st = (DIR == 0) ? 1 : 3; // stride of the differentiated direction in k
+        const int k0 = (DIR == 0) ? 3 * n : n;
+        if constexpr (ACC) {
+            const double t = W1[n] * scale3;
+            T[k0] = fma(-W0[n], scale, T[k0] + t);
+            T[k0 + st] = fma(-2.0, t, T[k0 + st]);
+            T[k0 + 2 * st] = fma(W0[n], scale, T[k0 + 2 * st] + t);
+        } else {
+            const double t = W1[n] * scale3;
+            T[k0] = fma(-W0[n], scale, t);
+            T[k0 + st] = -2.0 * t;
+            T[k0 + 2 * st] = fma(W0[n], scale, t);
+        }
+    }
+}
+
+/*
  * Mask bytes (land mask of the element row, Dirichlet bytes of its two node lines) travel with the u, v staging group:
  * copied global -> shared by cp.async one element row ahead and read at the top of the row.  Typed register loads a row
  * ahead do not work: the compiler unpacks the bytes (PRMT) or evaluates `mask != 0` into a predicate right behind the
@@ -221,7 +358,47 @@ __device__ __forceinline__ double fastRcp(double x)
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
+//! the same, pinned where it stands (volatile): the compiler cannot sink it into a branch around a select that discards it
+__device__ __forceinline__ double fastRcpPinned(double x)
+{
+    double r;
+    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 __device__ __forceinline__ double fastSqrt(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
+/*
+ * Branch-free square root: hardware seed (MUFU.RSQ64H, ~2^-22), one coupled Newton step on (sqrt x, 1 / (2 sqrt x)) and a
+ * residual correction -- 7 multiply-adds, no slow-path call, so the scheduler may interleave neighbouring Gauss points /
+ * nodes across it (the library rsqrt() brings a BSSY / BRA / CALL / BSYNC group that fences them).  Faithful to < 1 ulp for
+ * normal x; zero, negative and subnormal arguments give 0 (callers pass sums of squares and elasticities).
+ */
+__device__ __forceinline__ double sqrtBranchFree(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, x), h, g);
+    return x >= 2.2250738585072014e-308 ? g : 0.0;
+}
+
+//! branch-free reciprocal root for normal positive x: hardware seed and the third-order step of the library rsqrt(), without
+//! its exponent check and slow-path call (5 multiply-adds)
+__device__ __forceinline__ double rsqrtBranchFree(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(x, -(y * y), 1.0);
+    return fma(fma(0.375, e, 0.5), y * e, y);
+}
+#ifndef NSDG_MEVP_SQRT
+#define NSDG_MEVP_SQRT 0 //!< bit 0: branch-free root in the mEVP node update, bit 1: branch-free 1 / Delta in the mEVP law
+#endif
 
 //! mEVP momentum update of one node from the per-node constants (+ Dirichlet)
 __device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double cA, double rx, double ry, double uO, double vO,
@@ -229,7 +406,11 @@ __device__ __forceinline__ void momentumNodeUniform(const UniformArgs& a, double
 {
     const double uOcnRel = uO - un;
     const double vOcnRel = vn - vO;
+#if NSDG_MEVP_SQRT & 1
+    const double absocn = sqrtBranchFree(uOcnRel * uOcnRel + vOcnRel * vOcnRel);
+#else
     const double absocn = fastSqrt(uOcnRel * uOcnRel + vOcnRel * vOcnRel);
+#endif
     const double drag = cA * absocn;
     const double inv = fastRcp((1.0 + a.beta) + drag);
     unew = inv * (a.beta * un + rx + drag * uO - a.dtfc * un + dSx * ilm);
@@ -514,7 +695,11 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
             constexpr int q = decltype(QQ)::value;
             const double Pa = st.P[q][lane];
             const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+#if NSDG_MEVP_SQRT & 2
+            const double iD = rsqrtBranchFree(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+#else
             const double iD = rsqrt(a.DeltaMin2 + 1.25 * (g11 * g11 + g22 * g22) + 1.50 * g11 * g22 + g12 * g12);
+#endif
             const double pd = 0.125 * Pa * iD;
             e11[q] = fma(pd, 5.0 * g11 + 3.0 * g22, -0.5 * Pa);
             e22[q] = fma(pd, 5.0 * g22 + 3.0 * g11, -0.5 * Pa);

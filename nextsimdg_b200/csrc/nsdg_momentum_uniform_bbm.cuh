@@ -106,7 +106,11 @@ __device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, 
     double ilm, bool dirichlet, double un, double vn, double dSx, double dSy, double& unew, double& vnew, double& uAvg, double& vAvg)
 {
     const double du = uO - un, dv = vO - vn;
+#if NSDG_BBM_SQRT & 1
+    const double cPrime = cA * sqrtBranchFree(du * du + dv * dv); // dte * cPrime of the reference
+#else
     const double cPrime = cA * fastSqrt(du * du + dv * dv); // dte * cPrime of the reference
+#endif
     const double alpha = 1.0 + cPrime * a.cosA;
     const double beta = a.dtfc + cPrime * a.sinA;
     const double rDenom = fastRcp(alpha * alpha + beta * beta);
@@ -122,6 +126,12 @@ __device__ __forceinline__ void momentumNodeUniformBBM(const UniformBBMArgs& a, 
     }
 }
 
+#ifndef NSDG_UBBM_SEP
+#define NSDG_UBBM_SEP 4 //!< Gauss-point evaluation and projection as two 1-d passes (evalGaussSep / projectSep) instead of tables
+#endif
+#ifndef NSDG_BBM_SQRT
+#define NSDG_BBM_SQRT 7 //!< bit 0: branch-free root in the BBM node update, bit 1: in the law (tau), bit 2: in the law (sqrt E); bit 3 / 4: the two reciprocals of the law unconditional
+#endif
 #ifndef NSDG_UBBM_DIRECT_ND
 #define NSDG_UBBM_DIRECT_ND 1 //!< node constants and means loaded where they are used (see NSDG_UMEVP_DIRECT_ND): 1.16 -> 1.06 ms
 #endif
@@ -139,8 +149,8 @@ struct UbbmStage {
     double pad[2];
 };
 #ifndef NSDG_UBBM_WARPS
-#define NSDG_UBBM_WARPS 4
-#define NSDG_UBBM_MINB 2
+#define NSDG_UBBM_WARPS 1 // one-warp blocks: the staging buffer sits at a compile-time shared-memory address (240 instructions
+#define NSDG_UBBM_MINB 8 //  fewer per element row than with 4 x 2; 0.887 against 0.902 ms).  8 warps per SM either way: 255 registers
 #endif
 constexpr int kUbbmWarps = NSDG_UBBM_WARPS;
 #ifndef NSDG_COOP_UBBM
@@ -180,6 +190,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
     const size_t Npad = g.Npad;
     const int col0 = CG * ex;
     const double idx = 1.0 / a.dx, idy = 1.0 / a.dy;
+    [[maybe_unused]] const double dx3 = a.dx * (1.0 / 3.0), dy3 = a.dy * (1.0 / 3.0);
 
     auto issueUV = [&](int row) {
         if (row < ey1) {
@@ -297,6 +308,33 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 
         // ---- velocity gradient in the 9 Gauss points (as in the mEVP kernel) ----
         double e11[9], e12[9], e22[9];
+#if NSDG_UBBM_SEP >= 3
+        {
+            double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3]; // [jy][qx]: value / x derivative along the node row jy
+#pragma unroll
+            for (int jy = 0; jy < 3; ++jy) {
+                q2Values(ul[3 * jy], ul[3 * jy + 1], ul[3 * jy + 2], Au[jy][0], Au[jy][1], Au[jy][2]);
+                q2Derivs(ul[3 * jy], ul[3 * jy + 1], ul[3 * jy + 2], Adu[jy][0], Adu[jy][1], Adu[jy][2]);
+                q2Values(vl[3 * jy], vl[3 * jy + 1], vl[3 * jy + 2], Av[jy][0], Av[jy][1], Av[jy][2]);
+                q2Derivs(vl[3 * jy], vl[3 * jy + 1], vl[3 * jy + 2], Adv[jy][0], Adv[jy][1], Adv[jy][2]);
+            }
+            const double ix = ice ? idx : 0.0, iy = ice ? idy : 0.0, hx = 0.5 * ix, hy = 0.5 * iy; // quirk Q8: no strain on land
+#pragma unroll
+            for (int qx = 0; qx < 3; ++qx) {
+                double ux[3], uy[3], vx[3], vy[3]; // [qy]
+                q2Values(Adu[0][qx], Adu[1][qx], Adu[2][qx], ux[0], ux[1], ux[2]);
+                q2Derivs(Au[0][qx], Au[1][qx], Au[2][qx], uy[0], uy[1], uy[2]);
+                q2Values(Adv[0][qx], Adv[1][qx], Adv[2][qx], vx[0], vx[1], vx[2]);
+                q2Derivs(Av[0][qx], Av[1][qx], Av[2][qx], vy[0], vy[1], vy[2]);
+#pragma unroll
+                for (int qy = 0; qy < 3; ++qy) {
+                    e11[3 * qy + qx] = ux[qy] * ix;
+                    e22[3 * qy + qx] = vy[qy] * iy;
+                    e12[3 * qy + qx] = fma(uy[qy], hy, vx[qy] * hx);
+                }
+            }
+        }
+#else
         {
             double Au[3][3], Adu[3][3], Av[3][3], Adv[3][3];
             static_for<3>([&](auto JY) {
@@ -343,6 +381,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 });
             });
         }
+#endif
 
         // ---- stress and damage coefficients of the row, then the BBM law point by point:
         //      e** become the updated Gauss-point stresses, dG the updated damage ----
@@ -360,15 +399,31 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 #pragma unroll
             for (int j = 0; j < DGA; ++j)
                 dc[j] = st.D[j][lane];
+#if NSDG_UBBM_SEP
+            double t11q[9], t12q[9], t22q[9], dq[9];
+            evalGaussSep<DGs>(s11c, t11q);
+            evalGaussSep<DGs>(s12c, t12q);
+            evalGaussSep<DGs>(s22c, t22q);
+            evalGaussSep<DGA>(dc, dq);
+#endif
             cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
             stageBarrier<kCoopUbbmG>();
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
+#if NSDG_UBBM_SEP
+                double t11 = t11q[q], t12 = t12q[q], t22 = t22q[q], d = dq[q];
+#else
                 double t11 = evalGauss<DGs, 3, q>(s11c), t12 = evalGauss<DGs, 3, q>(s12c), t22 = evalGauss<DGs, 3, q>(s22c);
                 double d = evalGauss<DGA, 3, q>(dc);
+#endif
                 const double h = st.G[q][lane], expC = st.G[9 + q][lane], Pmax = st.G[18 + q][lane];
                 const double g11 = e11[q], g12 = e12[q], g22 = e22[q];
+#if NSDG_UBBM_SEP >= 4
+                d = d < 1e-12 ? 1e-12 : d; // compare + select: fmin / fmax cost five instructions each for their NaN rules
+                d = d > 1.0 ? 1.0 : d;
+#else
                 d = fmin(fmax(d, 1e-12), 1.0);
+#endif
                 double sigma_n = 0.5 * (t11 + t22);
                 const double de = d * expC, de2 = de * de;
                 const double tv = a.lambda0 * (de2 * de2);
@@ -379,7 +434,12 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 const bool full = compress && (Pmax >= -sigma_n);
                 const double mnum = compress ? tv * sigma_n : tv;
                 const double mden = compress ? fma(sigma_n + Pmax, a.deltaT, tv * sigma_n) : tv + a.deltaT;
+#if NSDG_BBM_SQRT & 8
+                const double mrcp = mnum * fastRcpPinned(mden);
+                const double mult = full ? 1.0 : mrcp;
+#else
                 const double mult = full ? 1.0 : mnum * fastRcp(mden);
+#endif
                 const double elasticity = h * a.young * d * expC;
                 const double Dunit = a.dunitK * elasticity;
                 t11 = (t11 + Dunit * (g11 + a.nu0 * g22)) * mult;
@@ -387,14 +447,31 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 t12 = (t12 + Dunit * g12 * (1.0 - a.nu0)) * mult;
                 sigma_n = 0.5 * (t11 + t22);
                 const double tau2 = 0.25 * (t11 - t22) * (t11 - t22) + t12 * t12;
+#if NSDG_BBM_SQRT & 2
+                const double tau = sqrtBranchFree(tau2);
+#else
                 const double tau = fastSqrt(tau2);
+#endif
                 const double cohesion = a.cohScale * h, compr = a.comprScale * h;
                 const double mc = tau + a.tan_phi * sigma_n;
                 // one division: the compressive cap, when active, replaces the Mohr-Coulomb value (same operands, same result)
                 const bool capped = sigma_n < -compr;
+#if NSDG_BBM_SQRT & 16
+                const double drcp = (capped ? -compr : cohesion) * fastRcpPinned(capped ? sigma_n : mc);
+                double dcrit = (capped || mc > 0.0) ? drcp : 1.0;
+#else
                 double dcrit = (capped || mc > 0.0) ? (capped ? -compr : cohesion) * fastRcp(capped ? sigma_n : mc) : 1.0;
+#endif
+#if NSDG_UBBM_SEP >= 4
+                dcrit = dcrit > 1.0 ? 1.0 : dcrit;
+#else
                 dcrit = fmin(dcrit, 1.0);
+#endif
+#if NSDG_BBM_SQRT & 4
+                const double sqrtE = sqrtBranchFree(elasticity);
+#else
                 const double sqrtE = fastSqrt(elasticity);
+#endif
                 const double relax = (1.0 - dcrit) * a.deltaT * (sqrtE * a.invTdK);
                 dG[q] = d - d * relax;
                 e11[q] = t11 - t11 * relax;
@@ -404,6 +481,16 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         }
 
         // ---- damage projection (iMJwPSI_dam = psi_j w / m_j on a rectangle, j < 6) ----
+#if NSDG_UBBM_SEP
+        {
+            double dnew[DGA];
+            projectSep<DGA>(dG, dnew);
+#pragma unroll
+            for (int j = 0; j < DGA; ++j)
+                if (active)
+                    a.damage[size_t(j) * Npad + e] = dnew[j];
+        }
+#else
         static_for<DGA>([&](auto J) {
             constexpr int j = decltype(J)::value;
             double acc = 0.0;
@@ -416,6 +503,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
             if (active)
                 a.damage[size_t(j) * Npad + e] = acc;
         });
+#endif
 
         // ---- per stress component: project, store, accumulate the divergence contributions ----
         double Tx[9], Ty[9];
@@ -425,6 +513,13 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         auto component = [&](double* plane, const double (&r)[9], auto COMP) {
             constexpr int comp = decltype(COMP)::value;
             double s[DGs];
+#if NSDG_UBBM_SEP
+            projectSep<DGs>(r, s);
+#pragma unroll
+            for (int j = 0; j < DGs; ++j)
+                if (active)
+                    plane[size_t(j) * Npad + e] = s[j];
+#else
             static_for<DGs>([&](auto J) {
                 constexpr int j = decltype(J)::value;
                 double acc = 0.0;
@@ -438,6 +533,19 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                 if (active)
                     plane[size_t(j) * Npad + e] = acc;
             });
+#endif
+#if NSDG_UBBM_SEP >= 2
+            if (ice) { // comp 0 comes first: Tx is assigned; s12 assigns Ty; the others accumulate
+                if constexpr (comp == 0)
+                    divergenceSep<0, false>(s, a.dy, dy3, Tx);
+                if constexpr (comp == 1) {
+                    divergenceSep<1, true>(s, a.dx, dx3, Tx);
+                    divergenceSep<0, false>(s, a.dy, dy3, Ty);
+                }
+                if constexpr (comp == 2)
+                    divergenceSep<1, true>(s, a.dx, dx3, Ty);
+            }
+#else
             if (ice) {
                 static_for<9>([&](auto K) {
                     constexpr int k = decltype(K)::value;
@@ -460,6 +568,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
                         Ty[k] = fma(d2, a.dx, Ty[k]);
                 });
             }
+#endif
         };
 #if NSDG_UBBM_DIRECT_ND
         // node constants and means of the row's two node lines: the loads are issued NSDG_UBBM_ND_HOIST projections
