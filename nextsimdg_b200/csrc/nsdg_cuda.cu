@@ -26,6 +26,35 @@
 
 namespace nsdg {
 
+/*
+ * Tensor map of a plane field for the TMA staging of the strip kernels (nsdg_momentum_uniform.cuh): the 2-d tensor
+ * {Npad doubles (contiguous), ncomp planes (pitch Npad doubles)}, tile = 32 elements x all planes.  cuTensorMapEncodeTiled is a
+ * driver entry point; it is looked up through the runtime so that the library keeps linking against cudart only.
+ */
+inline CUtensorMap planeTensorMap(const double* base, size_t Npad, int ncomp)
+{
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q {};
+        NSDG_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess)
+            throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
+        return reinterpret_cast<Encode>(fn);
+    }();
+    CUtensorMap m {};
+    const cuuint64_t dims[2] = { cuuint64_t(Npad), cuuint64_t(ncomp) };
+    const cuuint64_t strides[1] = { cuuint64_t(Npad) * sizeof(double) };
+    const cuuint32_t box[2] = { 32u, cuuint32_t(ncomp) };
+    const cuuint32_t estr[2] = { 1u, 1u };
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+    return m;
+}
+
 static thread_local std::string g_lastError;
 
 static inline unsigned blocksFor(size_t n, unsigned bs = 128) { return unsigned((n + bs - 1) / bs); }
@@ -107,6 +136,7 @@ public:
     DevBuf<double> u, v, u0, v0, cgH, cgA, gradX, gradY, uO, vO, uA, vA, lmass, avgU, avgV, taux, tauy;
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
+    CUtensorMap bbmTm[8] {}; //!< TMA staging of the fast BBM kernels: s11, s12, s22, damage, h, expC, Pmax, geometry
     DevBuf<double> ncCA, ncRx, ncRy, ncIlm; // per-node constants of the fast paths (plus uO, vO)
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
     DevBuf<double> vcon; // compact node constants of the vertical deferred lines (vcon_kernel)
@@ -423,6 +453,10 @@ public:
                 prepareKernelsUBBM();
                 prepareKernelsPBBM();
             }
+            const double* fields[7] = { s11, s12, s22, damage, gaussA, gaussB, gaussC };
+            const int comps[7] = { DGs, DGs, DGs, DGA, Q, Q, Q };
+            for (int i = 0; i < 7; ++i)
+                bbmTm[i] = planeTensorMap(fields[i], Npad, comps[i]);
         }
         fastParamMEVP = !uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !cfg.force_general
             && !std::getenv("NSDG_NO_FAST_PARAM");
@@ -1207,6 +1241,8 @@ public:
         a.vcon = vcon;
         a.C_lab = p.C_lab;
         a.compr_strength = p.compr_strength;
+        for (int i = 0; i < 8; ++i)
+            a.tm[i] = bbmTm[i];
         return a;
     }
     void launchPairFastBBM(const UniformBBMArgs& ba, unsigned nbStrip, size_t nLine, bool stripOnly = false, bool linesOnly = false)

@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 {
     constexpr int CG = 2, NR = 3, DGs = 8;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
@@ -480,8 +480,6 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
     PmevpStage<SPH>& st = reinterpret_cast<PmevpStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
-        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
@@ -776,7 +774,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GB = geoPlanes(SPH); // first BBM-specific plane
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
@@ -784,8 +782,6 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
     PbbmStage<SPH>& st = reinterpret_cast<PbbmStage<SPH>*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
-        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;

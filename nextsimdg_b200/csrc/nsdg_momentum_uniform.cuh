@@ -26,6 +26,7 @@
 #pragma once
 #include "nsdg_momentum.cuh"
 
+#include <cuda.h> // CUtensorMap (type only; the driver entry point is looked up at run time)
 #include <utility>
 
 namespace nsdg {
@@ -253,27 +254,10 @@ __device__ __forceinline__ double2 ldPinned2(const double* p)
 //! pull the line holding `p` into L2 (no register, no scoreboard): used one element row ahead
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-/*
- * Strip subsets for overlapping the halo exchange with interior work (partitioned boxes).  The FRAME is the band of
- * strips, fr* strips thick, along the sides that have a neighbour box; every node line that travels in the halo
- * exchange is computed by frame strips alone.  subset 0: all strips; 1: frame strips only; 2: interior strips only.
- * For the lines kernels subset 1 selects the deferred-line nodes all of whose strips are frame strips, 2 the others.
- */
-struct StripSubset {
-    int subset, frL, frR, frB, frT;
-};
-__device__ __forceinline__ bool inFrame(const StripSubset& f, int nsx, int nsy, int sx, int sy)
-{
-    return sx < f.frL || sx >= nsx - f.frR || sy < f.frB || sy >= nsy - f.frT;
-}
-//! true if this strip (or line node, given the conjunction over its strips) is not part of the launched subset
-__device__ __forceinline__ bool skipSubset(const StripSubset& f, bool frame) { return f.subset != 0 && ((f.subset == 1) != frame); }
-
 //! arguments of the uniform mEVP kernels
 struct UniformArgs {
     GridDims g;
     int R, nsx, nsy;
-    StripSubset sub;
     double *s11, *s12, *s22; //!< DG8 planes
     const double* Pa; //!< Gauss-point planes of P/alpha, P = P* h exp(-20(1-a))
     const uint8_t* landmask;
@@ -465,6 +449,40 @@ template <bool COOP> __device__ __forceinline__ void stageBarrier()
     if constexpr (COOP)
         __syncwarp();
 }
+/*
+ * TMA staging.  A staging group (the 8 planes of a stress component, the 9 Gauss-point planes of a coefficient field, ...)
+ * is a 32-element x NC-plane tile of the 2-d tensor {Npad elements (contiguous), NC planes (pitch Npad)}: ONE
+ * cp.async.bulk.tensor instruction (SASS: UTMALDG), issued by lane 0, moves the tile global -> shared as [NC][32] doubles and
+ * reports its bytes to an mbarrier, where the per-lane cp.async form issues one copy and one 64-bit address computation per
+ * PLANE and lane (57 per element row in the uniform BBM kernel).  The barrier has one arrival (lane 0's arrive.expect_tx with
+ * the group's byte count); consumers spin on try_wait.parity, the phase flips once per element row.  The non-tensor form
+ * (cp.async.bulk, one 256-byte row per instruction) was tried first and does NOT save instructions: its operands are uniform
+ * registers, so per-lane addresses compile into an ELECT / R2UR / UBLKCP loop over the lanes (8 instructions per plane).
+ * Tensor maps are built on the host (planeTensorMap, nsdg_cuda.cu) and travel inside the kernel's __grid_constant__ arguments.
+ */
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(uint64_t* b, unsigned arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(b)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbarInitFence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* b, unsigned parity)
+{
+    asm volatile("{\n.reg .pred p;\nW%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D%=;\nbra W%=;\nD%=:\n}" ::"r"(smemAddr(b)),
+                 "r"(parity)
+                 : "memory");
+}
+//! tile (x .. x + 31, all planes) of a plane tensor -> dst[NC][32]; dst 128-byte aligned
+__device__ __forceinline__ void tmaLoadTile(void* dst, const CUtensorMap* map, int x, uint64_t* b)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smemAddr(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(0), "r"(smemAddr(b))
+                 : "memory");
+}
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -508,12 +526,140 @@ constexpr size_t kUmevpSmemBytes = sizeof(UmevpStage) * kUmevpWarps;
 #ifndef NSDG_UMEVP_MINBLOCKS
 #define NSDG_UMEVP_MINBLOCKS 3
 #endif
+/*
+ * Deferred-line nodes (strip boundaries: every 32nd element column, every R-th element row, the domain's top / right edge).
+ * A node of horizontal line L (node row min(2 R L, 2 ny)) or vertical line L (node column min(64 L, 2 nx)) sums the raw
+ * contributions its 2 - 4 elements left in hbuf / vbuf, always in the same order, and is advanced like any other node.
+ */
+//! contributions of one deferred node; horizontal: cr = node column c on line L, vertical: cr = node row r on line L
+template <class ARGS>
+__device__ __forceinline__ void lineNodeSum(const ARGS& a, bool horizontal, int L, int cr, int& r, int& c, double& sumX, double& sumY)
+{
+    constexpr int CG = 2, NR = 3;
+    const GridDims& g = a.g;
+    sumX = 0.0;
+    sumY = 0.0;
+    if (horizontal) {
+        c = cr;
+        r = min(CG * a.R * L, CG * g.ny);
+        const int jx = c % CG, exr = c / CG;
+        const bool above = r < CG * g.ny;
+        auto add = [&](int side, int ex, int j) {
+            const double2 t = __ldcg(reinterpret_cast<const double2*>(a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2));
+            sumX += t.x;
+            sumY += t.y;
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !above)
+                break;
+            if (jx == 0 && exr > 0)
+                add(side, exr - 1, CG);
+            if (exr < g.nx)
+                add(side, exr, jx);
+        }
+    } else {
+        r = cr;
+        c = min(CG * 32 * L, CG * g.nx);
+        const int jy = r % CG, eyr = r / CG;
+        const bool right = c < CG * g.nx;
+        auto add = [&](int side, int ey, int j) {
+            const double2 t = __ldcg(reinterpret_cast<const double2*>(a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2));
+            sumX += t.x;
+            sumY += t.y;
+        };
+        for (int side = 0; side < 2; ++side) {
+            if (side == 1 && !right)
+                break;
+            if (jy == 0 && eyr > 0)
+                add(side, eyr - 1, CG);
+            add(side, eyr, jy);
+        }
+    }
+}
+//! node constants of a deferred node: rows of the node arrays (horizontal) or the compact per-line copies (vertical, vcon_kernel)
+template <class ARGS>
+__device__ __forceinline__ void lineNodeConsts(const ARGS& a, const double* const (&src)[kNodeConsts], bool horizontal, int L, int r, size_t n,
+    double (&k)[kNodeConsts], bool& d)
+{
+    const GridDims& g = a.g;
+    if (horizontal) {
+#pragma unroll
+        for (int i = 0; i < kNodeConsts; ++i)
+            k[i] = __ldg(src[i] + n);
+        d = __ldg(a.nodemask + n) & 1;
+    } else {
+        const size_t m = size_t(L - 1) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
+#pragma unroll
+        for (int i = 0; i < kNodeConsts; ++i)
+            k[i] = __ldg(a.vcon + i * pitch + m);
+        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
+    }
+}
+//! one deferred node of the mEVP paths (uniform and parametric)
+__device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizontal, int L, int cr)
+{
+    const GridDims& g = a.g;
+    int r, c;
+    if (horizontal) {
+        c = cr;
+        r = min(2 * a.R * L, 2 * g.ny);
+    } else {
+        r = cr;
+        c = min(64 * L, 2 * g.nx);
+    }
+    const size_t n = size_t(r) * g.cgs + c;
+    // request everything that does not depend on the contributions first (node constants, Dirichlet flag, u, v)
+    double k[kNodeConsts];
+    bool d;
+    const double* const src[kNodeConsts] = { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
+    lineNodeConsts(a, src, horizontal, L, r, n, k, d);
+    const double uOld = a.u[n], vOld = a.v[n];
+    double sumX, sumY;
+    lineNodeSum(a, horizontal, L, cr, r, c, sumX, sumY);
+    double un, vn;
+    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
+    a.u[n] = un;
+    a.v[n] = vn;
+}
+
+//! thread t of a lines kernel -> its deferred node; false for the vertical-line slots that lie on a horizontal line
+template <class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARGS& a, long t, bool& horizontal, int& L, int& cr)
+{
+    const GridDims& g = a.g;
+    const long nH = long(a.nsy) * g.cgnx;
+    const long nV = long(a.nsx) * g.cgny;
+    if (t >= nH + nV)
+        return false;
+    horizontal = t < nH;
+    if (horizontal) {
+        L = int(t / g.cgnx) + 1;
+        cr = int(t % g.cgnx);
+    } else {
+        const long tv = t - nH;
+        L = int(tv / g.cgny) + 1;
+        cr = int(tv % g.cgny);
+        if (cr > 0 && (cr % (2 * a.R) == 0 || cr == 2 * g.ny))
+            return false;
+    }
+    return true;
+}
+
+//! deferred-line nodes for the uniform mEVP path as a kernel of their own (see subcycle_lines in nsdg_momentum.cuh)
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constant__ UniformArgs a)
+{
+    bool horizontal;
+    int L, cr;
+    if (lineNodeOfThread(a, long(blockIdx.x) * blockDim.x + threadIdx.x, horizontal, L, cr))
+        lineNodeMEVP(a, horizontal, L, cr);
+}
+
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcycle_strip_umevp(const __grid_constant__ UniformArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
@@ -521,8 +667,6 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     UmevpStage& st = reinterpret_cast<UmevpStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
-        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
@@ -853,107 +997,6 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         }
     }
     cpAsyncWait<0>();
-}
-
-//! deferred-line nodes for the uniform mEVP path (see subcycle_lines in nsdg_momentum.cuh)
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constant__ UniformArgs a)
-{
-    constexpr int CG = 2, NR = 3;
-    const GridDims& g = a.g;
-    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long nH = long(a.nsy) * g.cgnx;
-    const long nV = long(a.nsx) * g.cgny;
-    if (t >= nH + nV)
-        return;
-    // decode the node first, request everything that does not depend on the contributions (node constants, Dirichlet
-    // flag, u, v), THEN gather the raw contributions: three dependent memory phases become one
-    const bool horizontal = t < nH;
-    int c, r, vline = 0, L;
-    if (horizontal) {
-        L = int(t / g.cgnx) + 1;
-        c = int(t % g.cgnx);
-        r = min(CG * a.R * L, CG * g.ny);
-    } else {
-        const long tv = t - nH;
-        L = int(tv / g.cgny) + 1;
-        vline = L - 1;
-        r = int(tv % g.cgny);
-        c = min(CG * 32 * L, CG * g.nx);
-        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
-            return;
-    }
-    const size_t n = size_t(r) * g.cgs + c;
-    double k[kNodeConsts];
-    bool d;
-    if (horizontal) {
-        const double* src[kNodeConsts] = { a.cA, a.rx, a.ry, a.uO, a.vO, a.ilm };
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(src[i] + n);
-        d = __ldg(a.nodemask + n) & 1;
-    } else { // vertical line: compact copies (vcon_kernel)
-        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(a.vcon + i * pitch + m);
-        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
-    }
-    const double uOld = a.u[n], vOld = a.v[n];
-    double sumX = 0.0, sumY = 0.0;
-    if (horizontal) {
-        const int jx = c % CG, exr = c / CG;
-        const bool above = r < CG * g.ny;
-        if (a.sub.subset) { // frame-complete: every strip that contributes to the node is a frame strip
-            bool fr = true;
-            for (int side = 0; side < (above ? 2 : 1); ++side) {
-                if (jx == 0 && exr > 0)
-                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, (exr - 1) / 32, L - 1 + side);
-                if (exr < g.nx)
-                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, exr / 32, L - 1 + side);
-            }
-            if (skipSubset(a.sub, fr))
-                return;
-        }
-        auto add = [&](int side, int ex, int j) {
-            const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
-            sumX += hb[0];
-            sumY += hb[1];
-        };
-        for (int side = 0; side < 2; ++side) {
-            if (side == 1 && !above)
-                break;
-            if (jx == 0 && exr > 0)
-                add(side, exr - 1, CG);
-            if (exr < g.nx)
-                add(side, exr, jx);
-        }
-    } else {
-        const int jy = r % CG, eyr = r / CG;
-        const bool right = c < CG * g.nx;
-        if (a.sub.subset) {
-            const int sy = min(eyr, g.ny - 1) / a.R; // the node lies strictly inside one strip row
-            const bool fr = inFrame(a.sub, a.nsx, a.nsy, L - 1, sy) && (!right || inFrame(a.sub, a.nsx, a.nsy, L, sy));
-            if (skipSubset(a.sub, fr))
-                return;
-        }
-        auto add = [&](int side, int ey, int j) {
-            const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
-            sumX += vb[0];
-            sumY += vb[1];
-        };
-        for (int side = 0; side < 2; ++side) {
-            if (side == 1 && !right)
-                break;
-            if (jy == 0 && eyr > 0)
-                add(side, eyr - 1, CG);
-            add(side, eyr, jy);
-        }
-    }
-    double un, vn;
-    momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
-    a.u[n] = un;
-    a.v[n] = vn;
 }
 
 } // namespace nsdg

@@ -22,7 +22,6 @@ namespace nsdg {
 struct UniformBBMArgs {
     GridDims g;
     int R, nsx, nsy;
-    StripSubset sub;
     double *s11, *s12, *s22; //!< DG8 planes
     double* damage; //!< DG6 planes
     const double *gH, *gE, *gP; //!< Gauss-point planes: h, expC, Pmax
@@ -42,6 +41,7 @@ struct UniformBBMArgs {
     const double* geo;
     const double* vcon; //!< compact per-vertical-line node constants (vcon_kernel)
     double C_lab, compr_strength;
+    CUtensorMap tm[8]; //!< TMA staging: s11, s12, s22 (8 planes each), damage (6), h, expC, Pmax (9 each), geometry (parametric)
 };
 
 //! per-node constants of BrittleCGDynamicsKernel::updateMomentum (BrittleCGDynamicsKernel.hpp:209-240); the factor
@@ -146,8 +146,16 @@ struct UbbmStage {
     double2 UV[2][2][32];
     MaskStage M;
     double UVr[2][2];
-    double pad[2];
+    uint64_t bar[2]; //!< mbarriers of the S (+ damage) and G groups (TMA staging)
+    double pad[6]; //!< sizeof % 128 == 0: TMA destinations are 128-byte aligned in every warp's stage
 };
+#ifndef NSDG_UBBM_BULK
+#define NSDG_UBBM_BULK 1 //!< plane rows by TMA (one tensor copy per field and row, lane 0) instead of one cp.async per plane and lane
+#endif
+constexpr bool kUbbmBulk = NSDG_UBBM_BULK != 0;
+static_assert(sizeof(UbbmStage) % 128 == 0 && offsetof(UbbmStage, G) % 128 == 0 && offsetof(UbbmStage, S) % 128 == 0 && offsetof(UbbmStage, D) % 128 == 0
+        && offsetof(UbbmStage, bar) % 8 == 0,
+    "TMA destinations need 128-byte alignment");
 #ifndef NSDG_UBBM_WARPS
 #define NSDG_UBBM_WARPS 1 // one-warp blocks: the staging buffer sits at a compile-time shared-memory address (240 instructions
 #define NSDG_UBBM_MINB 8 //  fewer per element row than with 4 x 2; 0.887 against 0.902 ms).  8 warps per SM either way: 255 registers
@@ -166,12 +174,50 @@ constexpr bool kCoopUbbm = NSDG_COOP_UBBM != 0; //!< plane rows staged cooperati
 constexpr bool kCoopUbbmG = kCoopUbbm || NSDG_COOP_UBBM_G != 0; //!< the read-only Gauss-point planes alone
 constexpr size_t kUbbmSmemBytes = sizeof(UbbmStage) * kUbbmWarps;
 
+//! one deferred node of the BBM paths (uniform and parametric), see lineNodeMEVP
+__device__ __forceinline__ void lineNodeBBM(const UniformBBMArgs& a, bool horizontal, int L, int cr)
+{
+    const GridDims& g = a.g;
+    int r, c;
+    if (horizontal) {
+        c = cr;
+        r = min(2 * a.R * L, 2 * g.ny);
+    } else {
+        r = cr;
+        c = min(64 * L, 2 * g.nx);
+    }
+    const size_t n = size_t(r) * g.cgs + c;
+    double k[kNodeConsts];
+    bool d;
+    const double* const src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
+    lineNodeConsts(a, src, horizontal, L, r, n, k, d);
+    const double uOld = a.u[n], vOld = a.v[n], aU = a.avgU[n], aV = a.avgV[n];
+    double sumX, sumY;
+    lineNodeSum(a, horizontal, L, cr, r, c, sumX, sumY);
+    double un, vn, ua, va;
+    momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
+    a.u[n] = un;
+    a.v[n] = vn;
+    a.avgU[n] = aU + ua;
+    a.avgV[n] = aV + va;
+}
+
+//! deferred-line nodes for the uniform BBM path as a kernel of their own
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant__ UniformBBMArgs a)
+{
+    bool horizontal;
+    int L, cr;
+    if (lineNodeOfThread(a, long(blockIdx.x) * blockDim.x + threadIdx.x, horizontal, L, cr))
+        lineNodeBBM(a, horizontal, L, cr);
+}
+
 template <int DUMMY = 0>
 __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_strip_ubbm(const __grid_constant__ UniformBBMArgs a)
 {
     constexpr int CG = 2, NR = 3, DGs = 8, DGA = 6;
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(128) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.nsx * a.nsy)
@@ -179,8 +225,6 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
     UbbmStage& st = reinterpret_cast<UbbmStage*>(smemRaw)[threadIdx.x >> 5];
     const GridDims& g = a.g;
     const int sx = w % a.nsx, sy = w / a.nsx;
-    if (skipSubset(a.sub, inFrame(a.sub, a.nsx, a.nsy, sx, sy)))
-        return;
     const int exRaw = 32 * sx + lane;
     const bool active = exRaw < g.nx;
     const int ex = active ? exRaw : g.nx - 1;
@@ -208,7 +252,29 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         }
         cpAsyncCommit();
     };
+    unsigned phaseS = 0, phaseG = 0;
+    if constexpr (kUbbmBulk) {
+        if (lane == 0) {
+            mbarInit(&st.bar[0], 1);
+            mbarInit(&st.bar[1], 1);
+        }
+        mbarInitFence();
+        __syncwarp();
+    }
     auto issueG = [&](int row) {
+        if constexpr (kUbbmBulk) {
+            if (row < ey1) {
+                __syncwarp(); // every lane has consumed the region that is refilled
+                if (lane == 0) {
+                    const int x = row * g.nxs + 32 * sx;
+                    mbarExpectTx(&st.bar[1], 27 * 256);
+                    tmaLoadTile(&st.G[0][0], &a.tm[4], x, &st.bar[1]);
+                    tmaLoadTile(&st.G[9][0], &a.tm[5], x, &st.bar[1]);
+                    tmaLoadTile(&st.G[18][0], &a.tm[6], x, &st.bar[1]);
+                }
+            }
+            return;
+        }
         stageBarrier<kCoopUbbmG>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
@@ -219,6 +285,20 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        if constexpr (kUbbmBulk) {
+            if (row < ey1) {
+                __syncwarp();
+                if (lane == 0) {
+                    const int x = row * g.nxs + 32 * sx;
+                    mbarExpectTx(&st.bar[0], 30 * 256);
+                    tmaLoadTile(&st.S[0][0], &a.tm[0], x, &st.bar[0]);
+                    tmaLoadTile(&st.S[8][0], &a.tm[1], x, &st.bar[0]);
+                    tmaLoadTile(&st.S[16][0], &a.tm[2], x, &st.bar[0]);
+                    tmaLoadTile(&st.D[0][0], &a.tm[3], x, &st.bar[0]);
+                }
+            }
+            return;
+        }
         stageBarrier<kCoopUbbm>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
@@ -284,7 +364,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        cpAsyncWait<3>();
+        cpAsyncWait<kUbbmBulk ? 1 : 3>(); // u, v of this row (bulk staging: only the UV and ND groups are cp.async groups)
         __syncwarp(); // the mask bytes were staged by other lanes
         const bool ice = active && (st.M.LM[lane] != 0);
         const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
@@ -385,8 +465,13 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
 
         // ---- stress and damage coefficients of the row, then the BBM law point by point:
         //      e** become the updated Gauss-point stresses, dG the updated damage ----
-        cpAsyncWait<3>();
-        stageBarrier<kCoopUbbm>(); // S and D were staged cooperatively
+        if constexpr (kUbbmBulk) {
+            mbarWait(&st.bar[0], phaseS);
+            phaseS ^= 1u;
+        } else {
+            cpAsyncWait<3>();
+            stageBarrier<kCoopUbbm>(); // S and D were staged cooperatively
+        }
         double dG[9];
         {
             double s11c[DGs], s12c[DGs], s22c[DGs], dc[DGA];
@@ -406,8 +491,13 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
             evalGaussSep<DGs>(s22c, t22q);
             evalGaussSep<DGA>(dc, dq);
 #endif
-            cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
-            stageBarrier<kCoopUbbmG>();
+            if constexpr (kUbbmBulk) {
+                mbarWait(&st.bar[1], phaseG);
+                phaseG ^= 1u;
+            } else {
+                cpAsyncWait<2>(); // Gauss constants (issued right after the S group one row ago)
+                stageBarrier<kCoopUbbmG>();
+            }
             static_for<9>([&](auto QQ) {
                 constexpr int q = decltype(QQ)::value;
 #if NSDG_UBBM_SEP
@@ -651,7 +741,7 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
             }
         }
         // ---- momentum update of the completed nodes ----
-        cpAsyncWait<3>();
+        cpAsyncWait<kUbbmBulk ? 1 : 3>();
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
@@ -710,102 +800,6 @@ __global__ void __launch_bounds__(32 * kUbbmWarps, NSDG_UBBM_MINB) subcycle_stri
         }
     }
     cpAsyncWait<0>();
-}
-
-//! deferred-line nodes for the uniform BBM path
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant__ UniformBBMArgs a)
-{
-    constexpr int CG = 2, NR = 3;
-    const GridDims& g = a.g;
-    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long nH = long(a.nsy) * g.cgnx;
-    const long nV = long(a.nsx) * g.cgny;
-    if (t >= nH + nV)
-        return;
-    int c, r, vline = 0;
-    double sumX = 0.0, sumY = 0.0;
-    if (t < nH) {
-        const int L = int(t / g.cgnx) + 1;
-        c = int(t % g.cgnx);
-        r = min(CG * a.R * L, CG * g.ny);
-        const int jx = c % CG, exr = c / CG;
-        const bool above = r < CG * g.ny;
-        if (a.sub.subset) { // frame-complete: every strip that contributes to the node is a frame strip
-            bool fr = true;
-            for (int side = 0; side < (above ? 2 : 1); ++side) {
-                if (jx == 0 && exr > 0)
-                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, (exr - 1) / 32, L - 1 + side);
-                if (exr < g.nx)
-                    fr = fr && inFrame(a.sub, a.nsx, a.nsy, exr / 32, L - 1 + side);
-            }
-            if (skipSubset(a.sub, fr))
-                return;
-        }
-        auto add = [&](int side, int ex, int j) {
-            const double* hb = a.hbuf + ((size_t(L - 1) * 2 + side) * g.nx + ex) * (NR * 2) + j * 2;
-            sumX += hb[0];
-            sumY += hb[1];
-        };
-        for (int side = 0; side < 2; ++side) {
-            if (side == 1 && !above)
-                break;
-            if (jx == 0 && exr > 0)
-                add(side, exr - 1, CG);
-            if (exr < g.nx)
-                add(side, exr, jx);
-        }
-    } else {
-        const long tv = t - nH;
-        const int L = int(tv / g.cgny) + 1;
-        vline = L - 1;
-        r = int(tv % g.cgny);
-        c = min(CG * 32 * L, CG * g.nx);
-        if (r > 0 && (r % (CG * a.R) == 0 || r == CG * g.ny))
-            return;
-        const int jy = r % CG, eyr = r / CG;
-        const bool right = c < CG * g.nx;
-        if (a.sub.subset) {
-            const int sy = min(eyr, g.ny - 1) / a.R; // the node lies strictly inside one strip row
-            const bool fr = inFrame(a.sub, a.nsx, a.nsy, L - 1, sy) && (!right || inFrame(a.sub, a.nsx, a.nsy, L, sy));
-            if (skipSubset(a.sub, fr))
-                return;
-        }
-        auto add = [&](int side, int ey, int j) {
-            const double* vb = a.vbuf + ((size_t(L - 1) * 2 + side) * g.ny + ey) * (NR * 2) + j * 2;
-            sumX += vb[0];
-            sumY += vb[1];
-        };
-        for (int side = 0; side < 2; ++side) {
-            if (side == 1 && !right)
-                break;
-            if (jy == 0 && eyr > 0)
-                add(side, eyr - 1, CG);
-            add(side, eyr, jy);
-        }
-    }
-    const size_t n = size_t(r) * g.cgs + c;
-    double k[kNodeConsts];
-    bool d;
-    if (t < nH) {
-        const double* src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(src[i] + n);
-        d = __ldg(a.nodemask + n) & 1;
-    } else { // vertical line: compact copies (vcon_kernel)
-        const size_t m = size_t(vline) * g.cgny + r, pitch = size_t(a.nsx) * g.cgny;
-#pragma unroll
-        for (int i = 0; i < kNodeConsts; ++i)
-            k[i] = __ldg(a.vcon + i * pitch + m);
-        d = __ldg(a.vcon + kNodeConsts * pitch + m) != 0.0;
-    }
-    double un, vn, ua, va;
-    momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], d, a.u[n], a.v[n], d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
-    a.u[n] = un;
-    a.v[n] = vn;
-    a.avgU[n] += ua;
-    a.avgV[n] += va;
 }
 
 } // namespace nsdg
