@@ -136,6 +136,7 @@ public:
     DevBuf<double> u, v, u0, v0, cgH, cgA, gradX, gradY, uO, vO, uA, vA, lmass, avgU, avgV, taux, tauy;
     DevBuf<double> cgSSH, mass1, gu1, gv1;
     DevBuf<double> hbuf, vbuf;
+    CUtensorMap mevpTm[5] {}; //!< TMA staging of the fast mEVP kernels: s11, s12, s22, P / alpha, geometry
     CUtensorMap bbmTm[8] {}; //!< TMA staging of the fast BBM kernels: s11, s12, s22, damage, h, expC, Pmax, geometry
     DevBuf<double> ncCA, ncRx, ncRy, ncIlm; // per-node constants of the fast paths (plus uO, vO)
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
@@ -467,6 +468,10 @@ public:
                 prepareKernelsUMEVP();
                 prepareKernelsPMEVP();
             }
+            const double* fields[4] = { s11, s12, s22, gaussA };
+            const int comps[4] = { DGs, DGs, DGs, Q };
+            for (int i = 0; i < 4; ++i)
+                mevpTm[i] = planeTensorMap(fields[i], Npad, comps[i]);
         }
         if (fastMEVP() || fastBBM())
             vcon.alloc(size_t(kVconPlanes) * nsx * g.cgny);
@@ -481,6 +486,9 @@ public:
                     paramgeom_bbm_kernel<true><<<blocksFor(N), 128, 0, stream>>>(g, p, helem, geo);
                 else
                     paramgeom_bbm_kernel<false><<<blocksFor(N), 128, 0, stream>>>(g, p, helem, geo);
+                bbmTm[7] = planeTensorMap(geo, Npad, geoPlanesBBM(spherical));
+            } else {
+                mevpTm[4] = planeTensorMap(geo, Npad, geoPlanes(spherical));
             }
             NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
@@ -1190,6 +1198,8 @@ public:
         a.beta = p.beta;
         a.dtfc = deltaT * p.fc;
         a.DeltaMin2 = p.DeltaMin * p.DeltaMin;
+        for (int i = 0; i < 5; ++i)
+            a.tm[i] = mevpTm[i];
         return a;
     }
     UniformBBMArgs makeUniformBBMArgs(double deltaT) const

@@ -44,6 +44,10 @@
 
 namespace nsdg {
 
+#ifndef NSDG_PARAM_TMA
+#define NSDG_PARAM_TMA 1 //!< plane rows of the parametric kernels by TMA (one tensor copy per field and row) instead of cp.async per plane
+#endif
+constexpr bool kParamTma = NSDG_PARAM_TMA != 0;
 #ifndef NSDG_PARAM_SEP
 #define NSDG_PARAM_SEP 1 //!< the constant tables as 1-d passes (q2Values / q2Derivs, evalGaussSep, projectSep) in the parametric kernels
 #endif
@@ -452,8 +456,12 @@ template <bool SPH> struct PmevpStage {
     double2 UV[2][2][32];
     MaskStage M;
     double UVr[2][2];
-    double pad[2];
+    uint64_t bar[3]; //!< mbarriers of the P, S and GEO groups (TMA staging)
+    double pad[5];
 };
+static_assert(sizeof(PmevpStage<false>) % 128 == 0 && sizeof(PmevpStage<true>) % 128 == 0 && offsetof(PmevpStage<false>, S) % 128 == 0
+        && offsetof(PmevpStage<false>, GEO) % 128 == 0 && offsetof(PmevpStage<true>, GEO) % 128 == 0,
+    "TMA destinations need 128-byte alignment");
 #ifndef NSDG_COOP_PARAM_CART
 #define NSDG_COOP_PARAM_CART 0
 #endif
@@ -507,13 +515,43 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
         }
         cpAsyncCommit();
     };
+    unsigned phase = 0; // TMA staging: the three groups are waited for together, once per row
+    if constexpr (kParamTma) {
+        if (lane == 0)
+            for (int i = 0; i < 3; ++i)
+                mbarInit(&st.bar[i], 1);
+        mbarInitFence();
+        __syncwarp();
+    }
+    //! TMA: lane 0 posts the group's bytes and issues one tensor copy per field (after every lane has consumed the region)
+    auto tmaGroup = [&](int row, int bar, unsigned bytes, auto&& copies) {
+        if (row < ey1) {
+            __syncwarp();
+            if (lane == 0) {
+                mbarExpectTx(&st.bar[bar], bytes);
+                copies(row * g.nxs + 32 * sx, &st.bar[bar]);
+            }
+        }
+    };
     auto issueP = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 0, 9 * 256, [&](int x, uint64_t* b) { tmaLoadTile(&st.P[0][0], &a.tm[3], x, b); });
+            return;
+        }
         stageBarrier<kCoopPmevp<SPH>>(); // every lane has consumed the region that is refilled
         if (row < ey1)
             stagePlanes<9, kCoopPmevp<SPH>>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 1, 24 * 256, [&](int x, uint64_t* b) {
+                tmaLoadTile(&st.S[0][0], &a.tm[0], x, b);
+                tmaLoadTile(&st.S[8][0], &a.tm[1], x, b);
+                tmaLoadTile(&st.S[16][0], &a.tm[2], x, b);
+            });
+            return;
+        }
         stageBarrier<kCoopPmevp<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
@@ -524,6 +562,10 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 2, geoPlanes(SPH) * 256, [&](int x, uint64_t* b) { tmaLoadTile(&st.GEO[0][0], &a.tm[4], x, b); });
+            return;
+        }
         stageBarrier<kCoopPmevp<SPH>>();
         if (row < ey1)
             stagePlanes<geoPlanes(SPH), kCoopPmevp<SPH>>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
@@ -576,7 +618,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         // ---- the two upper node rows of u, v ----
-        cpAsyncWait<4>();
+        cpAsyncWait<kParamTma ? 1 : 4>(); // (TMA staging: only the UV and ND groups are cp.async groups)
         __syncwarp(); // the mask bytes were staged by other lanes
         const bool ice = active && (st.M.LM[lane] != 0);
         const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
@@ -599,8 +641,14 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
         issueUV(ey + 1);
 
         // ---- strain in the 9 Gauss points ----
-        cpAsyncWait<2>(); // P, S and GEO of this row have landed
-        stageBarrier<kCoopPmevp<SPH>>(); //     (staged cooperatively: visible to every lane after the warp barrier)
+        if constexpr (kParamTma) {
+            for (int i = 0; i < 3; ++i)
+                mbarWait(&st.bar[i], phase);
+            phase ^= 1u;
+        } else {
+            cpAsyncWait<2>(); // P, S and GEO of this row have landed
+            stageBarrier<kCoopPmevp<SPH>>(); //     (staged cooperatively: visible to every lane after the warp barrier)
+        }
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 
@@ -659,7 +707,7 @@ __global__ void __launch_bounds__(32 * pmevpWarps(SPH), SPH ? 4 : NSDG_PMEVP_MIN
 
         const bool bottomDeferred = stripScatter(g, StripPos { lane, sx, sy, ex, ey, ey0, ey1, active, lastLane }, a.hbuf, a.vbuf, Tx, Ty);
         // ---- momentum update of the completed nodes (rows 2ey, 2ey+1; columns 2ex, 2ex+1) ----
-        cpAsyncWait<4>();
+        cpAsyncWait<kParamTma ? 1 : 4>();
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
@@ -760,8 +808,11 @@ template <bool SPH> struct PbbmStage : NodeStage<kPbbmDirectND<SPH>> {
     double2 UV[2][2][32];
     MaskStage M;
     double UVr[2][2];
-    double pad[2];
+    uint64_t bar[3]; //!< mbarriers of the S (+ damage), G and GEO groups (TMA staging)
+    double pad[5];
 };
+static_assert(sizeof(PbbmStage<false>) % 128 == 0 && sizeof(PbbmStage<true>) % 128 == 0 && sizeof(NodeStage<false>) % 128 == 0,
+    "TMA destinations need 128-byte alignment (G, S, D, GEO are multiples of 256 bytes behind the optional node-constant rows)");
 #ifndef NSDG_PBBM_WARPS
 #define NSDG_PBBM_WARPS 2 //!< warps per block (1 or 2): 8 warps per SM on Cartesian meshes, 6 on spherical ones (shared memory)
 #endif
@@ -809,7 +860,32 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
         }
         cpAsyncCommit();
     };
+    unsigned phase = 0; // TMA staging: the three groups are waited for together, once per row
+    if constexpr (kParamTma) {
+        if (lane == 0)
+            for (int i = 0; i < 3; ++i)
+                mbarInit(&st.bar[i], 1);
+        mbarInitFence();
+        __syncwarp();
+    }
+    auto tmaGroup = [&](int row, int bar, unsigned bytes, auto&& copies) {
+        if (row < ey1) {
+            __syncwarp(); // every lane has consumed the region that is refilled
+            if (lane == 0) {
+                mbarExpectTx(&st.bar[bar], bytes);
+                copies(row * g.nxs + 32 * sx, &st.bar[bar]);
+            }
+        }
+    };
     auto issueG = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 1, 27 * 256, [&](int x, uint64_t* b) {
+                tmaLoadTile(&st.G[0][0], &a.tm[4], x, b);
+                tmaLoadTile(&st.G[9][0], &a.tm[5], x, b);
+                tmaLoadTile(&st.G[18][0], &a.tm[6], x, b);
+            });
+            return;
+        }
         stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
@@ -820,6 +896,15 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 0, 30 * 256, [&](int x, uint64_t* b) {
+                tmaLoadTile(&st.S[0][0], &a.tm[0], x, b);
+                tmaLoadTile(&st.S[8][0], &a.tm[1], x, b);
+                tmaLoadTile(&st.S[16][0], &a.tm[2], x, b);
+                tmaLoadTile(&st.D[0][0], &a.tm[3], x, b);
+            });
+            return;
+        }
         stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
@@ -831,6 +916,10 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
         cpAsyncCommit();
     };
     auto issueGEO = [&](int row) {
+        if constexpr (kParamTma) {
+            tmaGroup(row, 2, geoPlanesBBM(SPH) * 256, [&](int x, uint64_t* b) { tmaLoadTile(&st.GEO[0][0], &a.tm[7], x, b); });
+            return;
+        }
         stageBarrier<kCoopPbbm<SPH>>();
         if (row < ey1)
             stagePlanes<geoPlanesBBM(SPH), kCoopPbbm<SPH>>(st.GEO, a.geo, Npad, size_t(row) * g.nxs + 32 * sx, lane);
@@ -884,7 +973,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
 
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
-        cpAsyncWait<4>();
+        cpAsyncWait<kParamTma ? 1 : 4>();
         __syncwarp(); // the mask bytes were staged by other lanes
         const bool ice = active && (st.M.LM[lane] != 0);
         const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
@@ -907,8 +996,14 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
         issueUV(ey + 1);
 
         // ---- strain in the 9 Gauss points ----
-        cpAsyncWait<2>(); // S, G and GEO of this row have landed
-        stageBarrier<kCoopPbbm<SPH>>();
+        if constexpr (kParamTma) {
+            for (int i = 0; i < 3; ++i)
+                mbarWait(&st.bar[i], phase);
+            phase ^= 1u;
+        } else {
+            cpAsyncWait<2>(); // S, G and GEO of this row have landed
+            stageBarrier<kCoopPbbm<SPH>>();
+        }
         double e11[9], e12[9], e22[9];
         gaussStrain<SPH>(geo, ul, vl, ice, e11, e12, e22);
 
@@ -1085,7 +1180,7 @@ __global__ void __launch_bounds__(32 * kPbbmWarps, (SPH ? 6 : 8) / kPbbmWarps) s
 
         const bool bottomDeferred = stripScatter(g, StripPos { lane, sx, sy, ex, ey, ey0, ey1, active, lastLane }, a.hbuf, a.vbuf, Tx, Ty);
         // ---- momentum update of the completed nodes ----
-        cpAsyncWait<4>();
+        cpAsyncWait<kParamTma ? 1 : 4>();
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;

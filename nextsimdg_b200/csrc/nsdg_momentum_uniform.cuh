@@ -271,6 +271,7 @@ struct UniformArgs {
     double keep; //!< 1 - 1/alpha
     double beta, dtfc; //!< beta ; deltaT * fc
     double DeltaMin2;
+    CUtensorMap tm[5]; //!< TMA staging: s11, s12, s22 (8 planes each), P / alpha (9), geometry (parametric meshes)
 };
 
 /*
@@ -515,8 +516,14 @@ struct UmevpStage {
     double2 UV[2][2][32];
     MaskStage M;
     double UVr[2][2]; //!< right-most node column of the strip (lane 31 / last element of the row)
-    double pad[2];
+    uint64_t bar[2]; //!< mbarriers of the P and S groups (TMA staging)
+    double pad[6];
 };
+static_assert(sizeof(UmevpStage) % 128 == 0 && offsetof(UmevpStage, S) % 128 == 0, "TMA destinations need 128-byte alignment");
+#ifndef NSDG_UMEVP_TMA
+#define NSDG_UMEVP_TMA 0 //!< P and S rows by TMA (one tensor copy per field and row) instead of cooperative 16-byte cp.async.cg
+#endif
+constexpr bool kUmevpTma = NSDG_UMEVP_TMA != 0;
 #ifndef NSDG_UMEVP_WARPS
 #define NSDG_UMEVP_WARPS 4
 #endif
@@ -694,14 +701,40 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         }
         cpAsyncCommit();
     };
+    unsigned phaseP = 0, phaseS = 0;
+    if constexpr (kUmevpTma) {
+        if (lane == 0) {
+            mbarInit(&st.bar[0], 1);
+            mbarInit(&st.bar[1], 1);
+        }
+        mbarInitFence();
+        __syncwarp();
+    }
     auto issueP = [&](int row) {
         __syncwarp(); // every lane has consumed the region that is refilled
+        if constexpr (kUmevpTma) {
+            if (row < ey1 && lane == 0) {
+                mbarExpectTx(&st.bar[0], 9 * 256);
+                tmaLoadTile(&st.P[0][0], &a.tm[3], row * g.nxs + 32 * sx, &st.bar[0]);
+            }
+            return;
+        }
         if (row < ey1)
             stagePlanes<9>(st.P, a.Pa, Npad, size_t(row) * g.nxs + 32 * sx, lane);
         cpAsyncCommit();
     };
     auto issueS = [&](int row) {
         __syncwarp();
+        if constexpr (kUmevpTma) {
+            if (row < ey1 && lane == 0) {
+                const int x = row * g.nxs + 32 * sx;
+                mbarExpectTx(&st.bar[1], 24 * 256);
+                tmaLoadTile(&st.S[0][0], &a.tm[0], x, &st.bar[1]);
+                tmaLoadTile(&st.S[8][0], &a.tm[1], x, &st.bar[1]);
+                tmaLoadTile(&st.S[16][0], &a.tm[2], x, &st.bar[1]);
+            }
+            return;
+        }
         if (row < ey1) {
             const size_t first = size_t(row) * g.nxs + 32 * sx;
             stagePlanes<8>(st.S, a.s11, Npad, first, lane);
@@ -760,7 +793,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
     for (int ey = ey0; ey < ey1; ++ey) {
         const size_t e = size_t(ey) * g.nxs + ex;
         // ---- the two upper node rows of u, v from the staging buffer ----
-        cpAsyncWait<3>();
+        cpAsyncWait<kUmevpTma ? 1 : 3>(); // (TMA staging: only the UV and ND groups are cp.async groups)
         __syncwarp(); // the mask bytes were staged by other lanes
         const bool ice = active && (st.M.LM[lane] != 0);
         const unsigned nm[2] = { nodeMaskWord(st.M, 0, lane), nodeMaskWord(st.M, 1, lane) };
@@ -833,8 +866,13 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
         }
 
         // ---- VP law in the Gauss points: e** become the integrands r** (MEVPStressUpdateStep.hpp:62-117) ----
-        cpAsyncWait<3>();
-        __syncwarp(); // P was staged cooperatively
+        if constexpr (kUmevpTma) {
+            mbarWait(&st.bar[0], phaseP);
+            phaseP ^= 1u;
+        } else {
+            cpAsyncWait<3>();
+            __syncwarp(); // P was staged cooperatively
+        }
         static_for<9>([&](auto QQ) {
             constexpr int q = decltype(QQ)::value;
             const double Pa = st.P[q][lane];
@@ -856,8 +894,13 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
 #pragma unroll
         for (int k = 0; k < 9; ++k)
             Tx[k] = Ty[k] = 0.0;
-        cpAsyncWait<3>();
-        __syncwarp(); // S was staged cooperatively
+        if constexpr (kUmevpTma) {
+            mbarWait(&st.bar[1], phaseS);
+            phaseS ^= 1u;
+        } else {
+            cpAsyncWait<3>();
+            __syncwarp(); // S was staged cooperatively
+        }
         auto component = [&](double* plane, const double (&r)[9], auto COMP) {
             constexpr int comp = decltype(COMP)::value; // 0: s11, 1: s12, 2: s22
             double s[DGs];
@@ -948,7 +991,7 @@ __global__ void __launch_bounds__(32 * kUmevpWarps, NSDG_UMEVP_MINBLOCKS) subcyc
             }
         }
         // ---- momentum update of the completed nodes (rows 2ey, 2ey+1; columns 2ex, 2ex+1) ----
-        cpAsyncWait<3>();
+        cpAsyncWait<kUmevpTma ? 1 : 3>();
 #pragma unroll
         for (int jy = 0; jy < CG; ++jy) {
             const size_t n0 = size_t(CG * ey + jy) * g.cgs + col0;
