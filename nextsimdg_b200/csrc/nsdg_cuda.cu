@@ -141,6 +141,7 @@ public:
     DevBuf<double> ncCA, ncRx, ncRy, ncIlm; // per-node constants of the fast paths (plus uO, vO)
     DevBuf<double> geo; // per-element geometry planes of the parametric fast path
     DevBuf<double> vcon; // compact node constants of the vertical deferred lines (vcon_kernel)
+    DevBuf<double> vavg; // fast BBM paths: mean velocities of the vertical deferred lines during the subcycle loop (vavg_kernel)
     bool fastUniformMEVP = false, fastUniformBBM = false;
     bool fastParamMEVP = false; //!< factored-operator kernel on non-uniform Cartesian meshes (nsdg_momentum_param.cuh)
     bool fastParamBBM = false;
@@ -475,6 +476,7 @@ public:
         }
         if (fastMEVP() || fastBBM())
             vcon.alloc(size_t(kVconPlanes) * nsx * g.cgny);
+        vavg.alloc(fastBBM() ? size_t(2) * nsx * g.cgny : 0);
         if (fastParamMEVP || fastParamBBM) {
             geo.alloc(size_t(fastParamBBM ? geoPlanesBBM(spherical) : geoPlanes(spherical)) * Npad);
             if (spherical)
@@ -1249,6 +1251,7 @@ public:
         a.dunitK = deltaT / (1. - p.nu0 * p.nu0);
         a.geo = geo;
         a.vcon = vcon;
+        a.vavg = vavg;
         a.C_lab = p.C_lab;
         a.compr_strength = p.compr_strength;
         for (int i = 0; i < 8; ++i)
@@ -1328,7 +1331,10 @@ public:
         const UniformBBMArgs ba = makeUniformBBMArgs(deltaT);
         const unsigned nbStripF = (unsigned(nsx) * nsy + 3) / 4;
         const size_t nLineF = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
+        const dim3 vavgGrid(unsigned((g.cgny + 127) / 128), unsigned(nsx));
         auto body = [&]() {
+            if (fastBBM())
+                vavg_kernel<true><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
             for (int i = 0; i < n; ++i) {
                 if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
@@ -1341,6 +1347,8 @@ public:
                     launchSubcycle<NSDG_MEVP>(a);
                 exchangeNodes(u, v); // no-op for a single domain
             }
+            if (fastBBM())
+                vavg_kernel<false><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
         };
         /*
          * Hiding the exchange behind strips that do not need it was built twice and is NOT in the library.  Round 1: frame
@@ -1376,7 +1384,7 @@ public:
         // kernels per subcycle: strip + lines + one exchange kernel per active phase (a graph replay runs them without
         // passing through exchange(), which counts only at capture time)
         const int phasesActive = haloActive ? (hasNeighbour(NSDG_LEFT) || hasNeighbour(NSDG_RIGHT) ? 1 : 0) + (hasNeighbour(NSDG_BOTTOM) || hasNeighbour(NSDG_TOP) ? 1 : 0) : 0;
-        launches = launchesBefore + long(n) * (2 + phasesActive);
+        launches = launchesBefore + long(n) * (2 + phasesActive) + (fastBBM() ? 2 : 0);
     }
 
     void subcycles(int n, float* ms) override
@@ -1409,6 +1417,9 @@ public:
         const unsigned nwarps = unsigned(nsx) * nsy, nbStrip = (nwarps + 3) / 4;
         const size_t nLine = size_t(nsy) * g.cgnx + size_t(nsx) * g.cgny;
         double ts = 0, tl = 0, th = 0;
+        const dim3 vavgGrid(unsigned((g.cgny + 127) / 128), unsigned(nsx));
+        if (fastBBM())
+            vavg_kernel<true><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
         for (int i = 0; i < n; ++i) {
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
             if (fastMEVP())
@@ -1439,6 +1450,10 @@ public:
             ts += x;
             tl += y;
             th += z;
+        }
+        if (fastBBM()) {
+            vavg_kernel<false><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
+            NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
         checkHaloError();
         *stripMs = float(ts / n);

@@ -14,7 +14,8 @@ void launchStripUBBM(const UniformBBMArgs& a, unsigned nStrips, cudaStream_t s)
 }
 void launchLinesUBBM(const UniformBBMArgs& a, size_t nLine, cudaStream_t s)
 {
-    subcycle_lines_ubbm<0><<<unsigned((nLine + 127) / 128), 128, 0, s>>>(a);
+    (void)nLine;
+    subcycle_lines_ubbm<0><<<linesGrid(a.g, a.nsx, a.nsy), 128, 0, s>>>(a);
 }
 
 } // namespace nsdg

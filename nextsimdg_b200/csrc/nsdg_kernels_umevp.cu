@@ -14,7 +14,8 @@ void launchStripUMEVP(const UniformArgs& a, unsigned nStrips, cudaStream_t s)
 }
 void launchLinesUMEVP(const UniformArgs& a, size_t nLine, cudaStream_t s)
 {
-    subcycle_lines_umevp<0><<<unsigned((nLine + 127) / 128), 128, 0, s>>>(a);
+    (void)nLine;
+    subcycle_lines_umevp<0><<<linesGrid(a.g, a.nsx, a.nsy), 128, 0, s>>>(a);
 }
 
 } // namespace nsdg

@@ -629,27 +629,25 @@ __device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizont
     a.v[n] = vn;
 }
 
-//! thread t of a lines kernel -> its deferred node; false for the vertical-line slots that lie on a horizontal line
-template <class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARGS& a, long t, bool& horizontal, int& L, int& cr)
+//! a thread of a lines kernel -> its deferred node.  Grid: y = line (the nsy horizontal lines, then the nsx vertical ones),
+//! x * blockDim + thread = position along the line (no integer divisions); false for positions beyond the line and for the
+//! vertical-line slots that lie on a horizontal line
+template <class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARGS& a, bool& horizontal, int& L, int& cr)
 {
     const GridDims& g = a.g;
-    const long nH = long(a.nsy) * g.cgnx;
-    const long nV = long(a.nsx) * g.cgny;
-    if (t >= nH + nV)
-        return false;
-    horizontal = t < nH;
+    cr = int(blockIdx.x * blockDim.x + threadIdx.x);
+    horizontal = int(blockIdx.y) < a.nsy;
     if (horizontal) {
-        L = int(t / g.cgnx) + 1;
-        cr = int(t % g.cgnx);
-    } else {
-        const long tv = t - nH;
-        L = int(tv / g.cgny) + 1;
-        cr = int(tv % g.cgny);
-        if (cr > 0 && (cr % (2 * a.R) == 0 || cr == 2 * g.ny))
-            return false;
+        L = int(blockIdx.y) + 1;
+        return cr < g.cgnx;
     }
-    return true;
+    L = int(blockIdx.y) - a.nsy + 1;
+    if (cr >= g.cgny)
+        return false;
+    return !(cr > 0 && (cr % (2 * a.R) == 0 || cr == 2 * g.ny));
 }
+//! launch geometry of a lines kernel
+inline dim3 linesGrid(const GridDims& g, int nsx, int nsy) { return dim3(unsigned((max(g.cgnx, g.cgny) + 127) / 128), unsigned(nsx + nsy)); }
 
 //! deferred-line nodes for the uniform mEVP path as a kernel of their own (see subcycle_lines in nsdg_momentum.cuh)
 template <int DUMMY = 0>
@@ -657,7 +655,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constan
 {
     bool horizontal;
     int L, cr;
-    if (lineNodeOfThread(a, long(blockIdx.x) * blockDim.x + threadIdx.x, horizontal, L, cr))
+    if (lineNodeOfThread(a, horizontal, L, cr))
         lineNodeMEVP(a, horizontal, L, cr);
 }
 

@@ -40,6 +40,7 @@ struct UniformBBMArgs {
     // parametric fast path (nsdg_momentum_param.cuh): per-element geometry planes; h_el varies per element
     const double* geo;
     const double* vcon; //!< compact per-vertical-line node constants (vcon_kernel)
+    double* vavg; //!< compact per-vertical-line mean velocities during the subcycle loop: avgU [nsx][cgny], then avgV (vavg_kernel)
     double C_lab, compr_strength;
     CUtensorMap tm[8]; //!< TMA staging: s11, s12, s22 (8 planes each), damage (6), h, expC, Pmax (9 each), geometry (parametric)
 };
@@ -191,15 +192,37 @@ __device__ __forceinline__ void lineNodeBBM(const UniformBBMArgs& a, bool horizo
     bool d;
     const double* const src[kNodeConsts] = { a.cA, a.ax, a.ay, a.uO, a.vO, a.ilm };
     lineNodeConsts(a, src, horizontal, L, r, n, k, d);
-    const double uOld = a.u[n], vOld = a.v[n], aU = a.avgU[n], aV = a.avgV[n];
+    // the running means of a vertical line's nodes live in a compact per-line array while the subcycles run: a node column
+    // of the row-major CG arrays costs a 32-byte sector per 8-byte value, read and written, every subcycle
+    double* const mU = horizontal ? a.avgU + n : a.vavg + size_t(L - 1) * g.cgny + r;
+    double* const mV = horizontal ? a.avgV + n : mU + size_t(a.nsx) * g.cgny;
+    const double uOld = a.u[n], vOld = a.v[n], aU = *mU, aV = *mV;
     double sumX, sumY;
     lineNodeSum(a, horizontal, L, cr, r, c, sumX, sumY);
     double un, vn, ua, va;
     momentumNodeUniformBBM(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn, ua, va);
     a.u[n] = un;
     a.v[n] = vn;
-    a.avgU[n] = aU + ua;
-    a.avgV[n] = aV + va;
+    *mU = aU + ua;
+    *mV = aV + va;
+}
+
+//! mean velocities of the vertical deferred lines: CG arrays -> compact per-line arrays before the subcycle loop (GATHER) and
+//! back after it.  One thread per (line, node row); the nodes that belong to a horizontal line stay in the CG arrays.
+template <bool GATHER>
+__global__ void vavg_kernel(GridDims g, int nsx, int R, double* __restrict__ avgU, double* __restrict__ avgV, double* __restrict__ vavg)
+{
+    const int r = int(blockIdx.x * blockDim.x + threadIdx.x), L = int(blockIdx.y) + 1;
+    if (r >= g.cgny || (r > 0 && (r % (2 * R) == 0 || r == 2 * g.ny)))
+        return;
+    const size_t n = size_t(r) * g.cgs + min(64 * L, 2 * g.nx), m = size_t(L - 1) * g.cgny + r, pitch = size_t(nsx) * g.cgny;
+    if constexpr (GATHER) {
+        vavg[m] = avgU[n];
+        vavg[pitch + m] = avgV[n];
+    } else {
+        avgU[n] = vavg[m];
+        avgV[n] = vavg[pitch + m];
+    }
 }
 
 //! deferred-line nodes for the uniform BBM path as a kernel of their own
@@ -208,7 +231,7 @@ __global__ void __launch_bounds__(128) subcycle_lines_ubbm(const __grid_constant
 {
     bool horizontal;
     int L, cr;
-    if (lineNodeOfThread(a, long(blockIdx.x) * blockDim.x + threadIdx.x, horizontal, L, cr))
+    if (lineNodeOfThread(a, horizontal, L, cr))
         lineNodeBBM(a, horizontal, L, cr);
 }
 
