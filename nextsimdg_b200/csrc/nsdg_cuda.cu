@@ -412,10 +412,21 @@ public:
         }
 
         // ---- strips and deferred-line buffers ----
-        // element rows per warp strip: 16 on large grids; fewer on small ones so that the strip kernel still
-        // offers ~12 warps to each of the 148 SMs (a 128 x 128 grid has only 4 strips per element row)
+        // element rows per warp strip: 12-24 on large grids (wave quantisation, below); on small ones as few as keep
+        // every strip resident at once (a 128 x 128 grid has only 4 strips per element row)
         nsx = (nx + 31) / 32;
-        R = int(std::max<long>(1, std::min<long>(16, long(nsx) * ny / (148 * 12))));
+        {
+            // small grids: the fewest rows per strip with which all strips are resident at once (one wave).  Warps per SM: 12
+            // for the uniform mEVP kernel (168 registers), 6 for the spherical BBM kernel (shared memory), 8 for the others.
+            // Measured per subcycle (strip + lines): 256^2 BBM 20.6 -> 18.3 us (R = 1 -> 2), 512^2 mEVP 47.8 -> 40.2 us (4 -> 5),
+            // 512^2 BBM 62.7 -> 60.9 us (4 -> 7); the TOPAZ-like 128^2 grid keeps R = 1
+            int smsR = 148;
+            cudaDeviceGetAttribute(&smsR, cudaDevAttrMultiProcessorCount, cfg.device);
+            const bool mevpFastR = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !std::getenv("NSDG_NO_FAST_UNIFORM");
+            const long warpsPerSM = mevpFastR ? 12 : (cfg.rheology == NSDG_BBM && spherical ? 6 : 8);
+            const long slotsR = long(smsR) * warpsPerSM;
+            R = int(std::max<long>(1, std::min<long>(16, (long(nsx) * ny + slotsR - 1) / slotsR)));
+        }
         if (R == 16) {
             // large grid: pick R in [12, 24] against wave quantisation.  The strip kernels run 4 warps per block and
             // `bps` blocks per SM (3 for the uniform mEVP kernel, 2 for the 246/255-register ones); with B blocks the
