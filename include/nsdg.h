@@ -141,8 +141,10 @@ int nsdg_get_field(nsdg_handle h, int field, double* host, int ncomp);
  *                                 (c1 below, c2 above), 1 = Y-edge (c1 left of the edge, c2 right of it), edge = index of
  *                                 the edge whose normal velocity the flux uses (DGTransport.cpp:466-481)
  *   periodic_segment_sizes      : entries per segment (VectorManipulations::CGAveragePeriodic works segment by segment)
- * Effect: the advection applies upwind fluxes across the periodic edges (DGTransport.cpp:466-481) and prepareIteration
- * averages cgH, cgA across the seam (CGDynamicsKernel.cpp:264-266).  Not available on partition boxes. */
+ * Effect: the advection applies upwind fluxes across the periodic edges (DGTransport.cpp:466-481), prepareIteration
+ * averages cgH, cgA across the seam (CGDynamicsKernel.cpp:264-266) and every subcycle averages the stress divergence across
+ * it before the momentum update (CGDynamicsKernel.cpp:395-397).  A handle with periodic edges runs the generic subcycle
+ * kernels until the next nsdg_set_mesh.  Not available on partition boxes. */
 int nsdg_set_boundaries(nsdg_handle h, const long* const* dirichlet, const size_t* ndirichlet, const long* periodic,
     const size_t* periodic_segment_sizes, size_t nsegments);
 

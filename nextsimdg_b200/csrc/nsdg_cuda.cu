@@ -126,6 +126,8 @@ public:
     std::vector<std::array<long, 4>> periodic; //!< ParametricMesh::periodic, flattened: {type, c1, c2, edge}
     std::vector<std::pair<size_t, size_t>> periodicSegs; //!< (first entry, count) of every periodic segment
     DevBuf<long> d_periodic; //!< the flattened list on the device (CGAveragePeriodic)
+    DevBuf<long> d_seamNodes; //!< the CG nodes of the periodic seams, each once (seam_update_kernel)
+    DevBuf<double> seamX, seamY; //!< their stress divergence between the lines kernel and the seam update
     DevBuf<double> scratchDG; // DGA planes scratch (set/get via DG2CG / CG2DG)
     // operators
     DevBuf<double> tAdvX, tAdvY, tiMass, sAdvX, sAdvY, siMass;
@@ -320,6 +322,9 @@ public:
         perNbr.release();
         perEdge.release();
         d_periodic.release();
+        d_seamNodes.release();
+        seamX.release();
+        seamY.release();
         uniform = detectUniform();
 
         vx.alloc(nnodes);
@@ -1004,6 +1009,9 @@ public:
         perNbr.release();
         perEdge.release();
         d_periodic.release();
+        d_seamNodes.release();
+        seamX.release();
+        seamY.release();
         size_t total = 0;
         for (size_t sgm = 0; sgm < nseg; ++sgm) {
             periodicSegs.emplace_back(total, segSizes[sgm]);
@@ -1038,6 +1046,40 @@ public:
             NSDG_CUDA_CHECK(cudaMemcpy(perEdge, he.data(), he.size() * sizeof(int), cudaMemcpyHostToDevice));
             NSDG_CUDA_CHECK(cudaMemcpy(d_periodic, per, 4 * total * sizeof(long), cudaMemcpyHostToDevice));
             legacySync();
+            // the momentum solve with periodic seams (CGDynamicsKernel.cpp:395-397) runs on the generic kernels: the nodes of
+            // the seams, each once, flagged in the node mask; their stress divergence is averaged between lines kernel and update
+            if (cfg.rheology != NSDG_FREEDRIFT) {
+                if (haloActive)
+                    throw std::runtime_error("nsdg_set_boundaries: periodic edges on a partitioned box are not supported");
+                std::vector<long> nodes;
+                for (const auto& e : periodic)
+                    for (int j = 0; j <= CG; ++j) {
+                        const long lb = e[2], rt = e[1];
+                        const long n0lb = long(CG * (lb / nx)) * g.cgs + CG * (lb % nx), n0rt = long(CG * (rt / nx)) * g.cgs + CG * (rt % nx);
+                        if (e[0] == 0) {
+                            nodes.push_back(n0lb + j);
+                            nodes.push_back(n0rt + long(CG) * g.cgs + j);
+                        } else {
+                            nodes.push_back(n0lb + long(j) * g.cgs);
+                            nodes.push_back(n0rt + CG + long(j) * g.cgs);
+                        }
+                    }
+                std::sort(nodes.begin(), nodes.end());
+                nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+                d_seamNodes.alloc(nodes.size());
+                NSDG_CUDA_CHECK(cudaMemcpy(d_seamNodes, nodes.data(), nodes.size() * sizeof(long), cudaMemcpyHostToDevice));
+                legacySync();
+                seamX.alloc(ncg);
+                seamY.alloc(ncg);
+                seam_flag_kernel<0><<<blocksFor(nodes.size()), 128, 0, stream>>>(d_seamNodes, long(nodes.size()), d_nodemask);
+                fastUniformMEVP = fastUniformBBM = fastParamMEVP = fastParamBBM = false; // until the next nsdg_set_mesh
+                ensureStreamedOps();
+                constOpsOwner(cfg.device) = nullptr;
+                if (graphExec) {
+                    cudaGraphExecDestroy(graphExec);
+                    graphExec = nullptr;
+                }
+            }
         }
         NSDG_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
@@ -1172,6 +1214,8 @@ public:
         a.gradY = gradY;
         a.lmass = lmass;
         a.nodemask = d_nodemask;
+        a.seamX = seamX;
+        a.seamY = seamY;
         a.hbuf = hbuf;
         a.vbuf = vbuf;
         a.deltaT = deltaT;
@@ -1313,6 +1357,11 @@ public:
         else
             subcycle_strip<CG, DGA, RHEO, false, false><<<nbStrip, 128, 0, stream>>>(a);
         subcycle_lines<CG, RHEO><<<blocksFor(nLine), 128, 0, stream>>>(a);
+        if (d_seamNodes.n > 0) { // CGAveragePeriodic(tx), (ty), then the seam nodes' momentum update
+            averagePeriodic(seamX);
+            averagePeriodic(seamY);
+            seam_update_kernel<RHEO><<<blocksFor(d_seamNodes.n), 128, 0, stream>>>(a, d_seamNodes, long(d_seamNodes.n));
+        }
     }
 
     /*

@@ -31,8 +31,12 @@
  * byte mask built once from the sorted Dirichlet lists: the stress divergence is zeroed there
  * before the momentum update and u,v after it, as in the reference's sweep order.
  * Quirk Q8: strain and divergence skip land elements, the stress update does not.
- * The periodic averaging at the end of stressDivergence (CGAveragePeriodic, dynamics/src/include/VectorManipulations.hpp:26-65)
- * has no device counterpart: IDynamics never marks periodic edges (DynamicsKernel.hpp:54), the lists are always empty.
+ * The periodic averaging at the end of stressDivergence (CGAveragePeriodic, dynamics/src/include/VectorManipulations.hpp:26-65;
+ * CGDynamicsKernel.cpp:395-397): nodes that appear in a periodic list carry bit 1 of the node mask.  Strips and lines do not
+ * advance them; they leave the node's (Dirichlet-zeroed) stress divergence in seamX / seamY, the host averages those arrays
+ * across the seam segment by segment like the reference (cg_average_periodic_kernel) and seam_update_kernel advances every
+ * seam node once.  IDynamics never marks periodic edges (DynamicsKernel.hpp:54): the lists are set through
+ * nsdg_set_boundaries, which also switches the handle to these generic kernels.
  */
 #pragma once
 #include "nsdg_state.cuh"
@@ -56,7 +60,8 @@ struct SubcycleArgs {
     // node state
     double *u, *v, *avgU, *avgV;
     const double *u0, *v0, *cgH, *cgA, *uAtm, *vAtm, *uOcn, *vOcn, *gradX, *gradY, *lmass;
-    const uint8_t* nodemask; //!< bit0: Dirichlet node
+    const uint8_t* nodemask; //!< bit0: Dirichlet node, bit1: node of a periodic seam
+    double *seamX, *seamY; //!< stress divergence of the periodic-seam nodes (CG arrays; null without periodic edges)
     // deferred line buffers: raw contributions
     double* hbuf; //!< [line 1..nsy][side 0 below,1 above][ex][jx 0..CG][comp]
     double* vbuf; //!< [line 1..nsx][side 0 left,1 right][ey][jy 0..CG][comp]
@@ -71,7 +76,7 @@ static __constant__ MomentumOps c_mops; //!< the single operator set of a unifor
 //! node-constant inputs of the momentum equation
 struct NodeIn {
     double cgH, cgA, uA, vA, uO, vO, gx, gy, lm, u0, v0;
-    bool dirichlet;
+    bool dirichlet, seam;
 };
 
 template <int RHEO> __device__ __forceinline__ NodeIn loadNode(const SubcycleArgs& a, size_t n)
@@ -92,7 +97,9 @@ template <int RHEO> __device__ __forceinline__ NodeIn loadNode(const SubcycleArg
     } else {
         in.u0 = in.v0 = 0;
     }
-    in.dirichlet = __ldg(a.nodemask + n) & 1;
+    const uint8_t m = __ldg(a.nodemask + n);
+    in.dirichlet = m & 1;
+    in.seam = m & 2;
     return in;
 }
 
@@ -100,12 +107,13 @@ template <int RHEO> __device__ __forceinline__ NodeIn loadNode(const SubcycleArg
 //! BrittleCGDynamicsKernel.hpp:209-253 (quirk Q3 verbatim), followed by applyBoundaries.
 //! (un,vn) = current velocity, (dSx,dSy) = stress divergence sums (dStressX/Y).  avgInc = u/nSteps
 //! of the BBM running mean, which in the reference is taken BEFORE the Dirichlet zeroing.
-template <int RHEO>
+//! ZERO_DS = false: (dSx, dSy) has been through dirichletZero and the periodic average already (seam_update_kernel)
+template <int RHEO, bool ZERO_DS = true>
 __device__ __forceinline__ void momentumNode(const SubcycleArgs& a, const NodeIn& in, double un, double vn, double dSx,
     double dSy, double& unew, double& vnew, double& avgIncU, double& avgIncV)
 {
     const PhysParams& p = a.p;
-    if (in.dirichlet) { // dirichletZero(dStress), CGDynamicsKernel.cpp:393-394
+    if (ZERO_DS && in.dirichlet) { // dirichletZero(dStress), CGDynamicsKernel.cpp:393-394
         dSx = 0.0;
         dSy = 0.0;
     }
@@ -510,6 +518,11 @@ __global__ void __launch_bounds__(128) subcycle_strip(const __grid_constant__ Su
                 }
                 const NodeIn in = loadNode<RHEO>(a, n0 + jx);
                 momentumNode<RHEO>(a, in, ul[jy * NR + jx], vl[jy * NR + jx], -sumX, -sumY, un[jx], vn[jx], aiu[jx], aiv[jx]);
+                if (in.seam && !skip[jx]) { // periodic seam: leave the divergence for the average, seam_update_kernel advances the node
+                    a.seamX[n0 + jx] = in.dirichlet ? 0.0 : -sumX;
+                    a.seamY[n0 + jx] = in.dirichlet ? 0.0 : -sumY;
+                    skip[jx] = true;
+                }
             }
 #pragma unroll
             for (int jx = 0; jx < CG; ++jx)
@@ -594,6 +607,11 @@ template <int CG, int RHEO> __global__ void __launch_bounds__(128) subcycle_line
     }
     const size_t n = size_t(r) * g.cgs + c;
     const NodeIn in = loadNode<RHEO>(a, n);
+    if (in.seam) {
+        a.seamX[n] = in.dirichlet ? 0.0 : -sumX;
+        a.seamY[n] = in.dirichlet ? 0.0 : -sumY;
+        return;
+    }
     double un, vn, aiu, aiv;
     momentumNode<RHEO>(a, in, a.u[n], a.v[n], -sumX, -sumY, un, vn, aiu, aiv);
     a.u[n] = un;
@@ -602,6 +620,31 @@ template <int CG, int RHEO> __global__ void __launch_bounds__(128) subcycle_line
         a.avgU[n] += aiu;
         a.avgV[n] += aiv;
     }
+}
+
+//! the nodes of the periodic seams (each once), after their stress divergence has been averaged across the seam
+template <int RHEO> __global__ void seam_update_kernel(const __grid_constant__ SubcycleArgs a, const long* __restrict__ nodes, long count)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= count)
+        return;
+    const size_t n = size_t(nodes[t]);
+    const NodeIn in = loadNode<RHEO>(a, n);
+    double un, vn, aiu, aiv;
+    momentumNode<RHEO, false>(a, in, a.u[n], a.v[n], a.seamX[n], a.seamY[n], un, vn, aiu, aiv);
+    a.u[n] = un;
+    a.v[n] = vn;
+    if constexpr (RHEO == NSDG_BBM) {
+        a.avgU[n] += aiu;
+        a.avgV[n] += aiv;
+    }
+}
+//! bit 1 of the node mask for the listed nodes
+template <int DUMMY = 0> __global__ void seam_flag_kernel(const long* __restrict__ nodes, long count, uint8_t* __restrict__ nodemask)
+{
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t < count)
+        nodemask[nodes[t]] |= 2; // the list holds every node once
 }
 
 #undef NSDG_OP
