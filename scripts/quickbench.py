@@ -12,7 +12,8 @@ if os.environ.get("QB_SPH"):  # TOPAZ-like spherical grid of the same size (pola
     f = synthetic.smooth_forcing(n, n)
     ms["hice"] = np.ascontiguousarray(np.asarray(ms["hice"]).reshape(n, n, -1)[..., 0])
     ms["cice"] = np.ascontiguousarray(np.asarray(ms["cice"]).reshape(n, n, -1)[..., 0])
-d = (CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics)(nsteps=100)
+kw = {"dgadv": 3, "cgdegree": 1} if os.environ.get("QB_CG1") else {}  # the reference's other compile-time build (DG1 / CG1)
+d = (CUDABBMDynamics if rheo == "bbm" else CUDAMEVPDynamics)(nsteps=100, **kw)
 d.setData(ms)
 d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy(), **{k: v.copy() for k, v in f.items()}}
 d.update(120.0)
