@@ -145,6 +145,7 @@ public:
     DevBuf<double> vcon; // compact node constants of the vertical deferred lines (vcon_kernel)
     DevBuf<double> vavg; // fast BBM paths: mean velocities of the vertical deferred lines during the subcycle loop (vavg_kernel)
     bool fastUniformMEVP = false, fastUniformBBM = false;
+    bool fastUniformMEVP1 = false; //!< DG1 / CG1 build on a uniform mesh: subcycle_strip_umevp1 + the generic lines kernel
     bool fastParamMEVP = false; //!< factored-operator kernel on non-uniform Cartesian meshes (nsdg_momentum_param.cuh)
     bool fastParamBBM = false;
     bool fastMEVP() const { return fastUniformMEVP || fastParamMEVP; }
@@ -428,7 +429,8 @@ public:
             int smsR = 148;
             cudaDeviceGetAttribute(&smsR, cudaDevAttrMultiProcessorCount, cfg.device);
             const bool mevpFastR = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6 && !std::getenv("NSDG_NO_FAST_UNIFORM");
-            const long warpsPerSM = mevpFastR ? 12 : (cfg.rheology == NSDG_BBM && spherical ? 6 : 8);
+            const bool mevp1R = uniform && cfg.rheology == NSDG_MEVP && CG == 1 && !cfg.force_general && !std::getenv("NSDG_NO_FAST_UNIFORM");
+            const long warpsPerSM = mevp1R ? 16 : mevpFastR ? 12 : (cfg.rheology == NSDG_BBM && spherical ? 6 : 8);
             const long slotsR = long(smsR) * warpsPerSM;
             R = int(std::max<long>(1, std::min<long>(16, (long(nsx) * ny + slotsR - 1) / slotsR)));
         }
@@ -459,8 +461,9 @@ public:
         vbuf.alloc(size_t(nsx) * 2 * ny * NR * 2);
         fastUniformMEVP = uniform && cfg.rheology == NSDG_MEVP && CG == 2 && DGA == 6;
         fastUniformBBM = uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6;
+        fastUniformMEVP1 = uniform && cfg.rheology == NSDG_MEVP && CG == 1 && !cfg.force_general;
         if (std::getenv("NSDG_NO_FAST_UNIFORM")) // testing knob: generic strip kernel on the uniform operator set
-            fastUniformMEVP = fastUniformBBM = false;
+            fastUniformMEVP = fastUniformBBM = fastUniformMEVP1 = false;
         fastParamBBM = !uniform && cfg.rheology == NSDG_BBM && CG == 2 && DGA == 6 && !cfg.force_general
             && !std::getenv("NSDG_NO_FAST_PARAM");
         if (fastBBM()) {
@@ -485,6 +488,15 @@ public:
                 prepareKernelsUMEVP();
                 prepareKernelsPMEVP();
             }
+            const double* fields[4] = { s11, s12, s22, gaussA };
+            const int comps[4] = { DGs, DGs, DGs, Q };
+            for (int i = 0; i < 4; ++i)
+                mevpTm[i] = planeTensorMap(fields[i], Npad, comps[i]);
+        }
+        if (fastUniformMEVP1) {
+            for (auto* f : { &ncCA, &ncRx, &ncRy, &ncIlm })
+                f->alloc(ncg);
+            prepareKernelsUMEVP1();
             const double* fields[4] = { s11, s12, s22, gaussA };
             const int comps[4] = { DGs, DGs, DGs, Q };
             for (int i = 0; i < 4; ++i)
@@ -1072,7 +1084,7 @@ public:
                 seamX.alloc(ncg);
                 seamY.alloc(ncg);
                 seam_flag_kernel<0><<<blocksFor(nodes.size()), 128, 0, stream>>>(d_seamNodes, long(nodes.size()), d_nodemask);
-                fastUniformMEVP = fastUniformBBM = fastParamMEVP = fastParamBBM = false; // until the next nsdg_set_mesh
+                fastUniformMEVP = fastUniformBBM = fastParamMEVP = fastParamBBM = fastUniformMEVP1 = false; // until the next nsdg_set_mesh
                 ensureStreamedOps();
                 constOpsOwner(cfg.device) = nullptr;
                 if (graphExec) {
@@ -1373,7 +1385,7 @@ public:
     MomentumOps hostMops {};
     //! only the generic kernel on a uniform mesh reads c_mops (the fast kernels carry compile-time unit operators,
     //! free drift runs no subcycle kernel)
-    bool readsConstOps() const { return uniform && !fastMEVP() && !fastBBM() && cfg.rheology != NSDG_FREEDRIFT; }
+    bool readsConstOps() const { return uniform && !fastMEVP() && !fastBBM() && !fastUniformMEVP1 && cfg.rheology != NSDG_FREEDRIFT; }
     void ensureConstOps()
     {
         if (!readsConstOps() || constOpsOwner(cfg.device) == this)
@@ -1396,7 +1408,10 @@ public:
             if (fastBBM())
                 vavg_kernel<true><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
             for (int i = 0; i < n; ++i) {
-                if (fastMEVP()) {
+                if (fastUniformMEVP1) {
+                    launchStripUMEVP1(ua, unsigned(nsx) * nsy, stream);
+                    subcycle_lines<CG, NSDG_MEVP><<<blocksFor(nLineF), 128, 0, stream>>>(a);
+                } else if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
                 } else if (fastBBM()) {
@@ -1482,7 +1497,9 @@ public:
             vavg_kernel<true><<<vavgGrid, 128, 0, stream>>>(g, nsx, R, avgU, avgV, vavg);
         for (int i = 0; i < n; ++i) {
             NSDG_CUDA_CHECK(cudaEventRecord(ev[0], stream));
-            if (fastMEVP())
+            if (fastUniformMEVP1)
+                launchStripUMEVP1(ua, unsigned(nsx) * nsy, stream);
+            else if (fastMEVP())
                 launchStripFast(ua, nbStrip);
             else if (fastBBM())
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, true, false);
@@ -1568,13 +1585,16 @@ public:
             NSDG_CUDA_CHECK(cudaMemcpyAsync(v0, v, cgBytes, cudaMemcpyDeviceToDevice, stream));
             deltaT = dt;
             gaussconst_kernel<DGA, GS, NSDG_MEVP><<<blocksFor(g.N), 128, 0, stream>>>(
-                g, p, hice, cice, gaussA, gaussB, fastMEVP() ? 1.0 / p.alpha : 1.0);
-            if (fastMEVP()) {
+                g, p, hice, cice, gaussA, gaussB, (fastMEVP() || fastUniformMEVP1) ? 1.0 / p.alpha : 1.0);
+            if (fastMEVP() || fastUniformMEVP1) {
                 nodeconst_kernel<0><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncCA, ncRx, ncRy, ncIlm);
+                launches += 1;
+            }
+            if (fastMEVP()) { // (the DG1 / CG1 fast path advances its deferred lines with the generic lines kernel: no compact copies)
                 vcon_kernel<0><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
                     g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
-                launches += 2;
+                launches += 1;
             }
         } else { // BrittleCGDynamicsKernel.hpp:110-114
             deltaT = dt / double(cfg.nsteps);

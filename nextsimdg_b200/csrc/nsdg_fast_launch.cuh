@@ -18,11 +18,13 @@ void prepareKernelsUMEVP();
 void prepareKernelsUBBM();
 void prepareKernelsPMEVP();
 void prepareKernelsPBBM();
+void prepareKernelsUMEVP1();
 
 //! nStrips = nsx * nsy warp strips; nLine = deferred-line nodes
 void launchStripUMEVP(const UniformArgs& a, unsigned nStrips, cudaStream_t s);
 void launchLinesUMEVP(const UniformArgs& a, size_t nLine, cudaStream_t s);
 void launchStripPMEVP(const UniformArgs& a, bool spherical, unsigned nStrips, cudaStream_t s);
+void launchStripUMEVP1(const UniformArgs& a, unsigned nStrips, cudaStream_t s); //!< DG1 / CG1 build (lines: the generic lines kernel)
 void launchStripUBBM(const UniformBBMArgs& a, unsigned nStrips, cudaStream_t s);
 void launchLinesUBBM(const UniformBBMArgs& a, size_t nLine, cudaStream_t s);
 void launchStripPBBM(const UniformBBMArgs& a, bool spherical, unsigned nStrips, cudaStream_t s);

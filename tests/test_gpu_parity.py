@@ -156,6 +156,47 @@ def test_dg1_cg1_build(rheo):
         assert rel(g[ice], r[ice]) < TOL_STEP, n
 
 
+def test_dg1_cg1_uniform_fast_path(monkeypatch):
+    """DG1 / CG1 build on uniform rectangles: the dedicated strip kernel (nsdg_momentum_uniform_cg1.cuh: direct Gauss-point
+    gradient, closed-form unit-square operators, TMA staging, folded node constants) against the oracle, and against the
+    generic kernel on ragged sizes that exercise partial warps, one-row strips and every kind of deferred line."""
+    from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
+
+    n, dt = 48, 120.0
+    ms = synthetic.benchmark_box(n)
+    ms["hice"] = np.ascontiguousarray(np.asarray(ms["hice"]).reshape(n, n, -1)[..., :1])
+    ms["cice"] = np.ascontiguousarray(np.asarray(ms["cice"]).reshape(n, n, -1)[..., :1])
+    gpu, ref = pair("mevp", ms, nsteps=100, dgadv=3, cg=1)
+    run_steps(gpu, ref, ms, [synthetic.benchmark_forcing(n, k * dt) for k in range(2)], dt)
+    assert gpu.timing().uniform_path == 1
+    ice = ms["mask"].astype(bool)
+    for name, g, r in (("uice", gpu.uice, ref.uice), ("vice", gpu.vice, ref.vice), ("hice", gpu.shared["hice"], ref.shared["hice"])):
+        assert rel(g[ice], r[ice]) < TOL_STEP, name
+    for name in ("s11", "s12", "s22"):
+        assert rel(gpu.internal(name), ref.internal(name)) < 1e-8, name
+    gpu.close()
+
+    for nx, ny in ((2, 2), (33, 5), (45, 37), (64, 40), (100, 70)):
+        st = synthetic.para_state(nx, ny)
+        st["hice"], st["cice"] = np.ascontiguousarray(st["hice"][..., :3]), np.ascontiguousarray(st["cice"][..., :3])
+        f = synthetic.smooth_forcing(nx, ny)
+        out = []
+        for generic in (False, True):
+            if generic:  # testing knob read by nsdg_set_mesh
+                monkeypatch.setenv("NSDG_NO_FAST_UNIFORM", "1")
+            d = CUDAMEVPDynamics(dgadv=3, cgdegree=1, nsteps=40)
+            d.setData(st)
+            monkeypatch.delenv("NSDG_NO_FAST_UNIFORM", raising=False)
+            d.shared = {"hice": np.ascontiguousarray(st["hice"][..., 0]), "cice": np.ascontiguousarray(st["cice"][..., 0]),
+                        **{a: b.copy() for a, b in f.items()}}
+            d.update(900.0)
+            out.append((d.internal("cg_u"), d.internal("cg_v"), d.internal("s12")))
+            d.close()
+        assert np.abs(out[1][0]).max() > 0
+        assert rel(out[0][0], out[1][0]) < TOL_STEP and rel(out[0][1], out[1][1]) < TOL_STEP, (nx, ny)
+        assert rel(out[0][2], out[1][2]) < 1e-8, (nx, ny)
+
+
 @pytest.mark.parametrize("rheo", ["mevp", "bbm"])
 def test_drift_over_steps(rheo):
     """Bounded drift: 5 consecutive timesteps of the cyclone box with moving forcing."""
@@ -363,10 +404,10 @@ def test_fresh_handle_does_not_depend_on_device_heap_contents(rheo):
             assert np.array_equal(v, again[name]), (it, name)
 
 
-def test_interleaved_handles_with_different_uniform_meshes():
+def test_interleaved_handles_with_different_uniform_meshes(monkeypatch):
     """Regression: the generic uniform kernel reads its operator set from ONE __constant__ symbol per device; a second
     live handle with another cell size (or the other CG/DG build) used to overwrite the first one's operators.  Two
-    DG1/CG1 handles (always on the generic kernel) with different cell sizes are stepped alternately and must reproduce
+    DG1/CG1 handles (kept on the generic kernel) with different cell sizes are stepped alternately and must reproduce
     their solo runs bit for bit."""
     from nextsimdg_b200 import CUDAMEVPDynamics, synthetic
 
@@ -375,7 +416,9 @@ def test_interleaved_handles_with_different_uniform_meshes():
     def make(L):
         ms = synthetic.benchmark_box(n, L=L)
         d = CUDAMEVPDynamics(dgadv=3, cgdegree=1, nsteps=30)
+        monkeypatch.setenv("NSDG_NO_FAST_UNIFORM", "1")  # testing knob read by nsdg_set_mesh: the generic kernel (reads the symbol)
         d.setData(ms)
+        monkeypatch.delenv("NSDG_NO_FAST_UNIFORM", raising=False)
         d.shared = {"hice": ms["hice"].copy(), "cice": ms["cice"].copy()}
         return d
 
@@ -419,7 +462,7 @@ def test_interleaved_handles_of_both_builds_share_the_constant_operator_symbol(m
             d = CUDAMEVPDynamics(dgadv=3, cgdegree=1, nsteps=30)
         else:
             d = CUDAMEVPDynamics(nsteps=30)
-        if kind == "dg2cg2_generic":  # testing knob read by nsdg_set_mesh: generic strip kernel on the uniform operator set
+        if kind != "dg2cg2_fast":  # testing knob read by nsdg_set_mesh: generic strip kernel on the uniform operator set
             monkeypatch.setenv("NSDG_NO_FAST_UNIFORM", "1")
         d.setData(ms)
         monkeypatch.delenv("NSDG_NO_FAST_UNIFORM", raising=False)

@@ -33,16 +33,16 @@ def _ops(lines):
     return [re.sub(r"^@!?U?P\w+\s+", "", re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l).group(1).strip()).split()[0].split(".")[0] for l in lines]
 
 
-@pytest.mark.parametrize("kernel,tma", [("subcycle_strip_ubbm", True), ("subcycle_strip_pbbm", True), ("subcycle_strip_pmevp", True),
-                                        ("subcycle_strip_umevp", False)])
+@pytest.mark.parametrize("kernel,tma", [("subcycle_strip_ubbmI", True), ("subcycle_strip_pbbmI", True), ("subcycle_strip_pmevpI", True),
+                                        ("subcycle_strip_umevp1I", True), ("subcycle_strip_umevpI", False)])
 def test_strip_kernels_staging_and_spills(sass, kernel, tma):
-    found = [k for k in sass if kernel in k]
+    found = [k for k in sass if kernel in k]  # mangled names: the template argument list starts with `I`
     assert found, f"{kernel} not in the library"
     for k in found:
         ops = _ops(sass[k])
-        assert ops.count("DFMA") > 500, (k, "FP64 arithmetic expected")
+        assert ops.count("DFMA") > (100 if "umevp1" in kernel else 500), (k, "FP64 arithmetic expected")
         assert "STL" not in ops and "LDL" not in ops, (k, "register spills")
         if tma:
-            assert ops.count("UTMALDG") >= 6 and "SYNCS" in ops, (k, "TMA tensor copies + mbarrier expected")
+            assert ops.count("UTMALDG") >= 4 and "SYNCS" in ops, (k, "TMA tensor copies + mbarrier expected")
         else:
             assert ops.count("LDGSTS") > 20 and "UTMALDG" not in ops, (k, "cp.async staging expected")
