@@ -502,7 +502,7 @@ public:
             for (int i = 0; i < 4; ++i)
                 mevpTm[i] = planeTensorMap(fields[i], Npad, comps[i]);
         }
-        if (fastMEVP() || fastBBM())
+        if (fastMEVP() || fastBBM() || fastUniformMEVP1)
             vcon.alloc(size_t(kVconPlanes) * nsx * g.cgny);
         vavg.alloc(fastBBM() ? size_t(2) * nsx * g.cgny : 0);
         if (fastParamMEVP || fastParamBBM) {
@@ -1410,7 +1410,7 @@ public:
             for (int i = 0; i < n; ++i) {
                 if (fastUniformMEVP1) {
                     launchStripUMEVP1(ua, unsigned(nsx) * nsy, stream);
-                    subcycle_lines<CG, NSDG_MEVP><<<blocksFor(nLineF), 128, 0, stream>>>(a);
+                    launchLinesUMEVP1(ua, stream);
                 } else if (fastMEVP()) {
                     launchStripFast(ua, nbStripF);
                     launchLinesFast(ua, nLineF);
@@ -1508,7 +1508,9 @@ public:
             else
                 launchStrip<NSDG_MEVP>(a, nbStrip);
             NSDG_CUDA_CHECK(cudaEventRecord(ev[1], stream));
-            if (fastMEVP())
+            if (fastUniformMEVP1)
+                launchLinesUMEVP1(ua, stream);
+            else if (fastMEVP())
                 launchLinesFast(ua, nLine);
             else if (fastBBM())
                 launchPairFastBBM(makeUniformBBMArgs(lastDeltaT), nbStrip, nLine, false, true);
@@ -1591,8 +1593,8 @@ public:
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, u0, v0, lmass, ncCA, ncRx, ncRy, ncIlm);
                 launches += 1;
             }
-            if (fastMEVP()) { // (the DG1 / CG1 fast path advances its deferred lines with the generic lines kernel: no compact copies)
-                vcon_kernel<0><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+            if (fastMEVP() || fastUniformMEVP1) {
+                vcon_kernel<CG><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
                     g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 1;
             }
@@ -1604,7 +1606,7 @@ public:
                 gaussconst_bbm3_kernel<DGA, GS><<<blocksFor(g.N), 128, 0, stream>>>(g, p, hice, cice, gaussA, gaussB, gaussC);
                 nodeconst_bbm_kernel<0><<<blocksFor(size_t(g.cgnx) * g.cgny), 128, 0, stream>>>(
                     g, p, deltaT, cgH, cgA, uA, vA, gradX, gradY, lmass, ncCA, ncRx, ncRy, ncIlm);
-                vcon_kernel<0><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
+                vcon_kernel<CG><<<blocksFor(size_t(nsx) * g.cgny), 128, 0, stream>>>(
                     g, nsx, ncCA, ncRx, ncRy, uO, vO, ncIlm, d_nodemask, vcon);
                 launches += 2;
             } else

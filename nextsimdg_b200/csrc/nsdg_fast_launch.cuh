@@ -24,7 +24,8 @@ void prepareKernelsUMEVP1();
 void launchStripUMEVP(const UniformArgs& a, unsigned nStrips, cudaStream_t s);
 void launchLinesUMEVP(const UniformArgs& a, size_t nLine, cudaStream_t s);
 void launchStripPMEVP(const UniformArgs& a, bool spherical, unsigned nStrips, cudaStream_t s);
-void launchStripUMEVP1(const UniformArgs& a, unsigned nStrips, cudaStream_t s); //!< DG1 / CG1 build (lines: the generic lines kernel)
+void launchStripUMEVP1(const UniformArgs& a, unsigned nStrips, cudaStream_t s); //!< DG1 / CG1 build
+void launchLinesUMEVP1(const UniformArgs& a, cudaStream_t s);
 void launchStripUBBM(const UniformBBMArgs& a, unsigned nStrips, cudaStream_t s);
 void launchLinesUBBM(const UniformBBMArgs& a, size_t nLine, cudaStream_t s);
 void launchStripPBBM(const UniformBBMArgs& a, bool spherical, unsigned nStrips, cudaStream_t s);

@@ -15,7 +15,7 @@ void launchStripUMEVP(const UniformArgs& a, unsigned nStrips, cudaStream_t s)
 void launchLinesUMEVP(const UniformArgs& a, size_t nLine, cudaStream_t s)
 {
     (void)nLine;
-    subcycle_lines_umevp<0><<<linesGrid(a.g, a.nsx, a.nsy), 128, 0, s>>>(a);
+    subcycle_lines_umevp<2><<<linesGrid(a.g, a.nsx, a.nsy), 128, 0, s>>>(a);
 }
 
 } // namespace nsdg

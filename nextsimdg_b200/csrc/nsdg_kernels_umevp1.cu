@@ -14,4 +14,9 @@ void launchStripUMEVP1(const UniformArgs& a, unsigned nStrips, cudaStream_t s)
     subcycle_strip_umevp1<0><<<nb, 32 * kUmevp1Warps, kUmevp1SmemBytes, s>>>(a);
 }
 
+void launchLinesUMEVP1(const UniformArgs& a, cudaStream_t s)
+{
+    subcycle_lines_umevp<1><<<linesGrid(a.g, a.nsx, a.nsy), 128, 0, s>>>(a);
+}
+
 } // namespace nsdg

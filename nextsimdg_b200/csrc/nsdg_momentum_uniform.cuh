@@ -310,7 +310,7 @@ __global__ void nodeconst_kernel(GridDims g, PhysParams p, double deltaT, const 
  */
 constexpr int kNodeConsts = 6;
 constexpr int kVconPlanes = kNodeConsts + 1;
-template <int DUMMY = 0>
+template <int CG = 2>
 __global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, const double* __restrict__ k1, const double* __restrict__ k2,
     const double* __restrict__ k3, const double* __restrict__ k4, const double* __restrict__ k5, const uint8_t* __restrict__ nodemask,
     double* __restrict__ vcon)
@@ -319,7 +319,7 @@ __global__ void vcon_kernel(GridDims g, int nsx, const double* __restrict__ k0, 
     if (t >= long(nsx) * g.cgny)
         return;
     const int line = int(t / g.cgny), r = int(t % g.cgny);
-    const int c = min(2 * 32 * (line + 1), 2 * g.nx);
+    const int c = min(CG * 32 * (line + 1), CG * g.nx);
     const size_t n = size_t(r) * g.cgs + c;
     const double* src[kNodeConsts] = { k0, k1, k2, k3, k4, k5 };
 #pragma unroll
@@ -539,10 +539,10 @@ constexpr size_t kUmevpSmemBytes = sizeof(UmevpStage) * kUmevpWarps;
  * contributions its 2 - 4 elements left in hbuf / vbuf, always in the same order, and is advanced like any other node.
  */
 //! contributions of one deferred node; horizontal: cr = node column c on line L, vertical: cr = node row r on line L
-template <class ARGS>
+template <int CG = 2, class ARGS>
 __device__ __forceinline__ void lineNodeSum(const ARGS& a, bool horizontal, int L, int cr, int& r, int& c, double& sumX, double& sumY)
 {
-    constexpr int CG = 2, NR = 3;
+    constexpr int NR = CG + 1;
     const GridDims& g = a.g;
     sumX = 0.0;
     sumY = 0.0;
@@ -603,16 +603,16 @@ __device__ __forceinline__ void lineNodeConsts(const ARGS& a, const double* cons
     }
 }
 //! one deferred node of the mEVP paths (uniform and parametric)
-__device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizontal, int L, int cr)
+template <int CG = 2> __device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizontal, int L, int cr)
 {
     const GridDims& g = a.g;
     int r, c;
     if (horizontal) {
         c = cr;
-        r = min(2 * a.R * L, 2 * g.ny);
+        r = min(CG * a.R * L, CG * g.ny);
     } else {
         r = cr;
-        c = min(64 * L, 2 * g.nx);
+        c = min(CG * 32 * L, CG * g.nx);
     }
     const size_t n = size_t(r) * g.cgs + c;
     // request everything that does not depend on the contributions first (node constants, Dirichlet flag, u, v)
@@ -622,7 +622,7 @@ __device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizont
     lineNodeConsts(a, src, horizontal, L, r, n, k, d);
     const double uOld = a.u[n], vOld = a.v[n];
     double sumX, sumY;
-    lineNodeSum(a, horizontal, L, cr, r, c, sumX, sumY);
+    lineNodeSum<CG>(a, horizontal, L, cr, r, c, sumX, sumY);
     double un, vn;
     momentumNodeUniform(a, k[0], k[1], k[2], k[3], k[4], k[5], d, uOld, vOld, d ? 0.0 : -sumX, d ? 0.0 : -sumY, un, vn);
     a.u[n] = un;
@@ -632,7 +632,7 @@ __device__ __forceinline__ void lineNodeMEVP(const UniformArgs& a, bool horizont
 //! a thread of a lines kernel -> its deferred node.  Grid: y = line (the nsy horizontal lines, then the nsx vertical ones),
 //! x * blockDim + thread = position along the line (no integer divisions); false for positions beyond the line and for the
 //! vertical-line slots that lie on a horizontal line
-template <class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARGS& a, bool& horizontal, int& L, int& cr)
+template <int CG = 2, class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARGS& a, bool& horizontal, int& L, int& cr)
 {
     const GridDims& g = a.g;
     cr = int(blockIdx.x * blockDim.x + threadIdx.x);
@@ -644,19 +644,19 @@ template <class ARGS> __device__ __forceinline__ bool lineNodeOfThread(const ARG
     L = int(blockIdx.y) - a.nsy + 1;
     if (cr >= g.cgny)
         return false;
-    return !(cr > 0 && (cr % (2 * a.R) == 0 || cr == 2 * g.ny));
+    return !(cr > 0 && (cr % (CG * a.R) == 0 || cr == CG * g.ny));
 }
 //! launch geometry of a lines kernel
 inline dim3 linesGrid(const GridDims& g, int nsx, int nsy) { return dim3(unsigned((max(g.cgnx, g.cgny) + 127) / 128), unsigned(nsx + nsy)); }
 
 //! deferred-line nodes for the uniform mEVP path as a kernel of their own (see subcycle_lines in nsdg_momentum.cuh)
-template <int DUMMY = 0>
+template <int CG = 2>
 __global__ void __launch_bounds__(128) subcycle_lines_umevp(const __grid_constant__ UniformArgs a)
 {
     bool horizontal;
     int L, cr;
-    if (lineNodeOfThread(a, horizontal, L, cr))
-        lineNodeMEVP(a, horizontal, L, cr);
+    if (lineNodeOfThread<CG>(a, horizontal, L, cr))
+        lineNodeMEVP<CG>(a, horizontal, L, cr);
 }
 
 template <int DUMMY = 0>

@@ -14,8 +14,8 @@
  *    (6 constants, u, v): 256 B per element and subcycle against ~ 300 B and no staging in the generic kernel.
  *
  * The 3 stress fields and P travel by TMA (one tensor copy per field and row, nsdg_momentum_uniform.cuh), the node row by
- * per-lane cp.async.  The deferred-line nodes are advanced by the generic lines kernel (subcycle_lines<1, mEVP>,
- * nsdg_momentum.cuh), which reads the line buffers this kernel fills (same layout as the generic strip kernel's).
+ * per-lane cp.async.  The deferred-line nodes are advanced by subcycle_lines_umevp<1> (nsdg_momentum_uniform.cuh: the same
+ * per-node functions as the CG2 path, instantiated for CG = 1), which reads the line buffers this kernel fills.
  *
  * Sweeps reproduced (results equal up to rounding; tests/test_gpu_parity.py, DG1/CG1 cases):
  *   projectVelocityToStrain  dynamics/src/CGDynamicsKernel.cpp:300-337
