@@ -471,11 +471,20 @@ __device__ __forceinline__ void mbarExpectTx(uint64_t* b, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(b)), "r"(bytes) : "memory");
 }
+//! wait for the phase with the given parity.  Bounded: a tensor copy that never completes (a bad tensor map, a device fault)
+//! traps after ~2^26 polls -- some seconds -- instead of hanging the GPU; the host then sees a launch failure
 __device__ __forceinline__ void mbarWait(uint64_t* b, unsigned parity)
 {
-    asm volatile("{\n.reg .pred p;\nW%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D%=;\nbra W%=;\nD%=:\n}" ::"r"(smemAddr(b)),
-                 "r"(parity)
+    unsigned done;
+    asm volatile("{\n.reg .pred p;\n.reg .u32 n;\nmov.u32 n, 0;\n"
+                 "W%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n@p bra D%=;\n"
+                 "add.u32 n, n, 1;\nsetp.lt.u32 p, n, 0x4000000;\n@p bra W%=;\nsetp.ne.u32 p, n, n;\n"
+                 "D%=: selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smemAddr(b)), "r"(parity)
                  : "memory");
+    if (!done)
+        __trap();
 }
 //! tile (x .. x + 31, all planes) of a plane tensor -> dst[NC][32]; dst 128-byte aligned
 __device__ __forceinline__ void tmaLoadTile(void* dst, const CUtensorMap* map, int x, uint64_t* b)
