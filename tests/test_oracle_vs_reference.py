@@ -121,3 +121,45 @@ def test_reference_ssh_interpolation_is_racy_under_openmp(table, oracle_lib):
     assert np.abs(port.internal("uGradSSH") - res[0]).max() / scale < TOL
     # informational: the 4-thread result normally differs by O(1); not asserted (a race may happen to go right)
     print("reference uGradSSH, 4 threads vs 1 thread: rel diff", np.abs(res[1] - res[0]).max() / scale)
+
+
+@pytest.mark.parametrize("rheo,seam,distort", [("mevp", "x", 0.03), ("bbm", "x", 0.03), ("mevp", "y", 0.0), ("mevp", "xy", 0.03)])
+def test_port_matches_live_reference_with_periodic_seams(rheo, seam, distort, oracle_lib):
+    """Periodic lists assigned by hand (the reference's IDynamics never sets them, DynamicsKernel.hpp:54): the periodic edge
+    fluxes of the advection (DGTransport.cpp:466-481) and CGAveragePeriodic on cgH, cgA (CGDynamicsKernel.cpp:264-266) and on
+    the stress divergence of every subcycle (:395-397) -- the restatement against the reference's own kernels; the GPU path is
+    compared with the same configurations in tests/test_gpu_kat.py::test_periodic_seam_in_the_module_path."""
+    import oracle
+    from nextsimdg_b200 import synthetic
+
+    if not oracle.have_ref(2):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    oracle.load_ref(2).nso_set_threads(1)
+    nx, ny = 18, 11
+    ms = synthetic.para_state(nx, ny, distort=distort)
+    f = synthetic.smooth_forcing(nx, ny)
+    per = []
+    if "x" in seam:
+        per.append([(1, (i + 1) * nx - 1, i * nx, i * (nx + 1)) for i in range(ny)])
+    if "y" in seam:
+        per.append([(0, (ny - 1) * nx + i, i, i) for i in range(nx)])
+    if rheo == "bbm":
+        ms["damage"] = 1.0 + 0.0 * np.asarray(ms["mask"])
+    jj, ii = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    u0 = 0.3 + 0.05 * np.cos(2 * np.pi * ii / nx) * np.cos(2 * np.pi * jj / ny) + 0.0 * ms["mask"]
+    pair = [oracle.OracleDynamics(rheo, 6, 2, 3, impl=impl) for impl in ("reference", "port")]
+    for d in pair:
+        d.setData(ms)
+        d.set_boundaries(dirichlet=[[] if "y" in seam else None, [] if "x" in seam else None, [] if "y" in seam else None,
+                                    [] if "x" in seam else None], periodic=per)
+        d.shared = {"hice": np.ascontiguousarray(ms["hice"][..., 0]), "cice": np.ascontiguousarray(ms["cice"][..., 0]),
+                    **{k: v.copy() for k, v in f.items()}}
+        if rheo == "bbm":
+            d.shared["damage"] = ms["damage"].copy()
+        d._set("u", u0)
+        d._set("v", 0.1 * u0)
+        d.update(30.0 if rheo == "bbm" else 900.0)
+    for name in ("hice", "cice", "cgH", "cgA", "cg_u", "cg_v", "s11", "s12", "s22"):
+        a, b = pair[0].internal(name), pair[1].internal(name)
+        tol = TOL_STRESS if name.startswith("s") else TOL
+        assert np.abs(a - b).max() <= tol * max(np.abs(a).max(), 1e-300), name
